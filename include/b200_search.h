@@ -1,0 +1,133 @@
+/*
+ * b200_search.h -- C ABI of libb200search.so, the B200-native (sm_100a) engine for
+ * MyScaleDB's ANN / BM25 hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes only, no C++/torch types.
+ * Each entry point names the reference interface it replaces (paths relative to
+ * /root/reference/src).  INTEGRATION.md shows the C++ shim a MyScaleDB maintainer
+ * adds on the ClickHouse side (namespace Search:: / TANTIVY::ffi_* forwarding here).
+ *
+ * Conventions
+ *   - every function returns B200_OK (0) or an error code; b200_last_error() gives the
+ *     thread-local message (the reference's libraries throw SearchIndexException /
+ *     return {result, error{is_error,message}}; the C++ shim re-throws, VICommon.h:75-104);
+ *   - all entry points are re-entrant: ClickHouse calls them from one ThreadPool worker
+ *     per part (MergeTreeSelectWithHybridSearchProcessor.cpp:1212-1241);
+ *   - float vectors are row-major fp32 [n][d]; binary vectors row-major bytes [n][d/8];
+ *   - alive / filter bitmaps are LSB-first bytes, bit=1 => row may be returned
+ *     (Search::DenseBitmap::get_bitmap(), MergeTreeTextSearchManager.cpp:191-194);
+ *   - results: out_dis[nq*k], out_ids[nq*k], best first; unfilled slots id = -1
+ *     (faiss heap convention the callers test with `ids > -1`, MergeTreeVSManager.cpp:469-488);
+ *   - tie rule: better score, then smaller row id;
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *     B200_ERR_NO_DEVICE.
+ */
+#ifndef B200_SEARCH_H
+#define B200_SEARCH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_INVALID 1     /* bad argument */
+#define B200_ERR_CUDA 2        /* CUDA runtime / driver failure */
+#define B200_ERR_UNSUPPORTED 3 /* valid request this build does not implement */
+#define B200_ERR_NO_DEVICE 4   /* no sm_100 device visible */
+#define B200_ERR_NOMEM 5
+
+/* Search::Metric (MergeTreeVSManager.cpp:1560-1578) */
+#define B200_METRIC_L2 0
+#define B200_METRIC_IP 1
+#define B200_METRIC_COSINE 2
+#define B200_METRIC_HAMMING 3
+#define B200_METRIC_JACCARD 4
+
+/* device storage type of a resident corpus */
+#define B200_DTYPE_F32 0
+#define B200_DTYPE_BF16 1
+#define B200_DTYPE_BIN 2
+
+const char *b200_last_error(void);
+const char *b200_version(void);
+int b200_device_count(int *out_n);
+int b200_set_device(int device);
+
+/* ------------------------------------------------------------------------------------
+ * Brute force from host buffers.
+ * Replaces VectorIndex::tryBruteForceSearch<T> (VectorIndex/Common/BruteForceSearch.h:63-111)
+ * as called by VIWithColumnInPart::searchWithoutIndex<T> (VectorIndex/Common/VIWithDataPart.h:342-382):
+ * L2 = squared L2 ascending, IP descending, COSINE = normalise both (skip rows with
+ * sum(x^2) < FLT_EPSILON) -> IP -> 1 - ip.  x, y are NOT modified.
+ * ---------------------------------------------------------------------------------- */
+int b200_flat_knn(int metric, const float *x, int64_t nx, const float *y, int64_t ny, int d, int k,
+                  const uint8_t *alive_bits /*nullable*/, float *out_dis, int64_t *out_ids);
+
+/* Binary vectors: HAMMING (faiss::hammings_knn_mc) / JACCARD (jaccard_knn),
+ * BruteForceSearch.h:94-110.  Distances are returned as float VALUES (the reference
+ * writes int32 Hamming distances into the float buffer, :99; the shim re-encodes). */
+int b200_binary_knn(int metric, const uint8_t *x, int64_t nx, const uint8_t *y, int64_t ny, int nbytes, int k,
+                    const uint8_t *alive_bits /*nullable*/, float *out_dis, int64_t *out_ids);
+
+/* Whole-part brute force with the semantics of MergeTreeVSManager::vectorScanWithoutIndex<T>
+ * + searchWrapper<T> (VectorIndex/Storages/MergeTreeVSManager.cpp:960-1679): per-mark
+ * blocks merged with "earlier block wins ties", lightweight-delete mask row_exists
+ * (1 byte per row, 0 = deleted, :1435-1460), PREWHERE filter bitmap (:1042-1330), and the
+ * IP initial value numeric_limits<float>::min() (:1030-1037: IP scores <= FLT_MIN are never
+ * returned).  The part column is DMA'd to HBM once and scanned in one pass; block_rows only
+ * documents the mark size (results are independent of it under the tie rule).
+ * y is fp32 [ny][d] for float metrics or bytes [ny][d/8] for binary metrics (d in bits). */
+int b200_part_scan(int metric, const void *x, int64_t nx, const void *y, int64_t ny, int d, int k,
+                   int64_t block_rows, const uint8_t *row_exists /*nullable*/, const uint8_t *filter_bits /*nullable*/,
+                   float *out_dis, int64_t *out_ids);
+
+/* ------------------------------------------------------------------------------------
+ * Device-resident corpus = a FLAT vector index / cached part column in HBM.
+ * Replaces Search::VectorIndex<...>(IndexType::FLAT)::{build, search} as reached through
+ * VIWithColumnInPart::search (VectorIndex/Common/VIWithDataPart.cpp:858-957) and the
+ * VICacheManager residency model (VectorIndex/Cache/VICacheManager.cpp:65-157).
+ * ---------------------------------------------------------------------------------- */
+typedef struct b200_corpus b200_corpus;
+
+int b200_corpus_create(int metric, int dtype, int d, int64_t capacity_rows, b200_corpus **out);
+/* append fp32 (or binary bytes for B200_DTYPE_BIN) rows from host memory; converted to the
+ * corpus dtype on device; row norms are computed on device. */
+int b200_corpus_append(b200_corpus *c, const void *rows, int64_t n);
+/* adopt rows that already live in HBM in the corpus dtype, row-major [n][d] with
+ * d % 64 == 0 for bf16 (d % 4 == 0 for f32); the memory stays owned by the caller. */
+int b200_corpus_adopt_device(b200_corpus *c, const void *device_rows, int64_t n);
+int b200_corpus_size(const b200_corpus *c, int64_t *out_rows);
+int b200_corpus_free(b200_corpus *c);
+
+/* search with host queries/results (H2D of queries and D2H of results inside the call) */
+int b200_corpus_search(b200_corpus *c, const float *queries, int64_t nq, int k, const uint8_t *alive_bits /*nullable*/,
+                       float *out_dis, int64_t *out_ids);
+/* same, queries and results in device memory, asynchronous on `stream` (a cudaStream_t
+ * passed as void*; NULL = the corpus' own stream followed by a synchronise).
+ * id_offset is added to every returned id (shard base for multi-GPU merges). */
+int b200_corpus_search_device(b200_corpus *c, const float *d_queries, int64_t nq, int k,
+                              const uint8_t *d_alive_bits /*nullable*/, int64_t id_offset, float *d_out_dis,
+                              int64_t *d_out_ids, void *stream);
+/* Force a search path: 0 = auto, 1 = memory-bound scan kernel, 2 = tcgen05 bf16 GEMM. */
+int b200_corpus_set_path(b200_corpus *c, int path);
+/* CUDA-event timing of the dominant kernel (scan or GEMM) of every search on this corpus,
+ * recorded on the launching stream; used by bench.py for the roofline report. */
+int b200_corpus_enable_timing(b200_corpus *c, int on);
+int b200_corpus_kernel_time(b200_corpus *c, int reset, double *out_total_ms, int64_t *out_launches);
+/* number of kernels this library launched on the calling thread since the last reset */
+int64_t b200_launch_count(int reset);
+
+/* K-way merge of per-part / per-GPU top-k lists on device.
+ * Replaces MergeTreeBaseSearchManager::getTotalTopSearchResultImpl
+ * (VectorIndex/Storages/MergeTreeBaseSearchManager.cpp:207-299) for the sharded path:
+ * d_dis/d_ids are [n_lists][nq][k] (e.g. the NCCL all-gather buffer); output [nq][k].
+ * descending = 1 for IP / BM25. */
+int b200_topk_merge_device(const float *d_dis, const int64_t *d_ids, int n_lists, int64_t nq, int k, int descending,
+                           float *d_out_dis, int64_t *d_out_ids, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_SEARCH_H */

@@ -1,0 +1,677 @@
+// capi.cu -- the C ABI of libb200search.so (declared in include/b200_search.h) and the host
+// orchestration under it: device-resident corpora, path selection (memory-bound scan vs
+// tcgen05 GEMM), query staging, partial-list merge.
+//
+// There is deliberately no CPU compute path in this file: every entry point either runs
+// CUDA kernels on an sm_100 device or fails with B200_ERR_NO_DEVICE / B200_ERR_CUDA.
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200 {
+
+thread_local std::string g_error;
+thread_local int64_t g_launches = 0;
+
+void set_error(const std::string &msg) { g_error = msg; }
+int fail(int code, const std::string &msg) {
+    g_error = msg;
+    return code;
+}
+
+struct DeviceInfo {
+    int checked = 0;  // 0 unknown, 1 ok, -1 none
+    int num_sms = 148;
+    std::string why;
+};
+
+static int ensure_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(B200_ERR_NO_DEVICE, std::string("no CUDA device visible (") +
+                                            (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0") +
+                                            "); libb200search has no CPU fallback");
+    }
+    int dev = 0;
+    B200_CUDA_OK(cudaGetDevice(&dev));
+    int major = 0;
+    B200_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10)
+        return fail(B200_ERR_NO_DEVICE, "device compute capability major is " + std::to_string(major) +
+                                            "; this library carries sm_100a code only");
+    return B200_OK;
+}
+
+static int num_sms() {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+
+// grow-only device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return B200_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(B200_ERR_NOMEM, "cudaMalloc(" + std::to_string(want) + ") failed: " + cudaGetErrorString(e));
+        }
+        cap = want;
+        return B200_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+}  // namespace b200
+
+using namespace b200;
+
+struct b200_corpus {
+    int metric = 0, dtype = 0, d = 0, d_pad = 0;
+    int64_t cap = 0, n = 0;
+    int64_t row_bytes = 0;
+    void *data = nullptr;
+    bool owns = true;
+    float *row_scale = nullptr;  // cosine: -1/||y||
+    float *row_bias = nullptr;   // L2: ||y||^2 (GEMM path)
+    int device = 0;
+    int path = 0;
+    int sms = 148;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    // workspaces
+    DevBuf w_raw, w_q32, w_qbf, w_qnorm, w_pk, w_pi, w_lk, w_li, w_alive, w_odis, w_oids, w_stage;
+    // optional CUDA-event timing of the dominant kernel (scan or GEMM) for the roofline report
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_used, ev_free;
+    double timed_ms = 0;
+    int64_t timed_launches = 0;
+};
+
+static void timing_begin(b200_corpus *c, cudaStream_t s, std::pair<cudaEvent_t, cudaEvent_t> &ev) {
+    if (!c->timing) return;
+    if (c->ev_free.empty()) {
+        cudaEventCreate(&ev.first);
+        cudaEventCreate(&ev.second);
+    } else {
+        ev = c->ev_free.back();
+        c->ev_free.pop_back();
+    }
+    cudaEventRecord(ev.first, s);
+}
+static void timing_end(b200_corpus *c, cudaStream_t s, std::pair<cudaEvent_t, cudaEvent_t> &ev) {
+    if (!c->timing) return;
+    cudaEventRecord(ev.second, s);
+    c->ev_used.push_back(ev);
+}
+
+static bool is_float_metric(int m) { return m == B200_METRIC_L2 || m == B200_METRIC_IP || m == B200_METRIC_COSINE; }
+static bool is_bin_metric(int m) { return m == B200_METRIC_HAMMING || m == B200_METRIC_JACCARD; }
+
+static int pad_for(int dtype, int d) {
+    if (dtype == B200_DTYPE_BF16) return (int)round_up(d, 64);  // 128-byte TMA/UMMA swizzle rows
+    if (dtype == B200_DTYPE_F32) return (int)round_up(d, 4);    // 16-byte vector loads
+    return d / 8;                                                // binary: bytes
+}
+
+extern "C" const char *b200_last_error(void) { return g_error.c_str(); }
+extern "C" const char *b200_version(void) { return "b200search 0.1 (sm_100a)"; }
+
+extern "C" int b200_device_count(int *out_n) {
+    if (!out_n) return fail(B200_ERR_INVALID, "out_n is null");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    *out_n = n;
+    return B200_OK;
+}
+
+extern "C" int b200_set_device(int device) {
+    B200_TRY(ensure_device());
+    B200_CUDA_OK(cudaSetDevice(device));
+    return B200_OK;
+}
+
+extern "C" int64_t b200_launch_count(int reset) {
+    int64_t v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+extern "C" int b200_corpus_create(int metric, int dtype, int d, int64_t capacity_rows, b200_corpus **out) {
+    if (!out) return fail(B200_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (d <= 0 || capacity_rows < 0) return fail(B200_ERR_INVALID, "bad d / capacity");
+    if (dtype == B200_DTYPE_BIN) {
+        if (!is_bin_metric(metric)) return fail(B200_ERR_INVALID, "binary corpus needs HAMMING or JACCARD");
+        if (d % 8) return fail(B200_ERR_INVALID, "binary dimension must be a multiple of 8 bits");
+    } else if (dtype == B200_DTYPE_F32 || dtype == B200_DTYPE_BF16) {
+        if (!is_float_metric(metric)) return fail(B200_ERR_INVALID, "float corpus needs L2, IP or COSINE");
+    } else {
+        return fail(B200_ERR_INVALID, "unknown dtype");
+    }
+    B200_TRY(ensure_device());
+    b200_corpus *c = new b200_corpus();
+    c->metric = metric;
+    c->dtype = dtype;
+    c->d = d;
+    c->d_pad = pad_for(dtype, d);
+    c->row_bytes = dtype == B200_DTYPE_BIN ? c->d_pad : (int64_t)c->d_pad * (dtype == B200_DTYPE_BF16 ? 2 : 4);
+    c->cap = capacity_rows;
+    cudaGetDevice(&c->device);
+    c->sms = num_sms();
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete c;
+        return fail(B200_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    }
+    *out = c;
+    return B200_OK;
+}
+
+static int corpus_alloc(b200_corpus *c, int64_t rows) {
+    if (c->data && c->owns && rows <= c->cap) return B200_OK;
+    if (c->data && !c->owns) return fail(B200_ERR_INVALID, "corpus adopted device memory; cannot append");
+    int64_t new_cap = std::max<int64_t>(rows, std::max<int64_t>(c->cap, 1));
+    void *nd = nullptr;
+    // +1 row of slack so that 16-byte vector loads of the last row never leave the allocation
+    cudaError_t e = cudaMalloc(&nd, (size_t)(new_cap + 1) * c->row_bytes + 256);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(B200_ERR_NOMEM, std::string("cudaMalloc corpus: ") + cudaGetErrorString(e));
+    }
+    float *ns = nullptr, *nb = nullptr;
+    if (c->metric == B200_METRIC_COSINE) cudaMalloc(&ns, (size_t)new_cap * 4 + 256);
+    if (c->metric == B200_METRIC_L2) cudaMalloc(&nb, (size_t)new_cap * 4 + 256);
+    if (c->data && c->n) {
+        cudaMemcpyAsync(nd, c->data, (size_t)c->n * c->row_bytes, cudaMemcpyDeviceToDevice, c->stream);
+        if (ns) cudaMemcpyAsync(ns, c->row_scale, (size_t)c->n * 4, cudaMemcpyDeviceToDevice, c->stream);
+        if (nb) cudaMemcpyAsync(nb, c->row_bias, (size_t)c->n * 4, cudaMemcpyDeviceToDevice, c->stream);
+        cudaStreamSynchronize(c->stream);
+    }
+    if (c->data) cudaFree(c->data);
+    if (c->row_scale) cudaFree(c->row_scale);
+    if (c->row_bias) cudaFree(c->row_bias);
+    c->data = nd;
+    c->row_scale = ns;
+    c->row_bias = nb;
+    c->cap = new_cap;
+    c->owns = true;
+    return B200_OK;
+}
+
+static int corpus_norms(b200_corpus *c, int64_t first, int64_t n) {
+    const char *rows = reinterpret_cast<const char *>(c->data) + first * c->row_bytes;
+    if (c->metric == B200_METRIC_COSINE)
+        B200_CUDA_OK(launch_row_norms(rows, c->dtype == B200_DTYPE_BF16, c->d_pad, n, 1, c->row_scale + first, c->stream));
+    if (c->metric == B200_METRIC_L2)
+        B200_CUDA_OK(launch_row_norms(rows, c->dtype == B200_DTYPE_BF16, c->d_pad, n, 0, c->row_bias + first, c->stream));
+    return B200_OK;
+}
+
+extern "C" int b200_corpus_append(b200_corpus *c, const void *rows, int64_t n) {
+    if (!c || (!rows && n > 0) || n < 0) return fail(B200_ERR_INVALID, "bad arguments");
+    if (n == 0) return B200_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    B200_CUDA_OK(cudaSetDevice(c->device));
+    if (c->n + n > c->cap || !c->data) B200_TRY(corpus_alloc(c, std::max(c->n + n, c->cap)));
+    char *dst = reinterpret_cast<char *>(c->data) + c->n * c->row_bytes;
+    if (c->dtype == B200_DTYPE_BIN) {
+        B200_CUDA_OK(cudaMemcpyAsync(dst, rows, (size_t)n * c->row_bytes, cudaMemcpyHostToDevice, c->stream));
+    } else if (c->dtype == B200_DTYPE_F32 && c->d == c->d_pad) {
+        B200_CUDA_OK(cudaMemcpyAsync(dst, rows, (size_t)n * c->row_bytes, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        // stage raw fp32 rows in chunks, then pad / convert on device
+        const int64_t chunk = std::max<int64_t>(1, (int64_t)(256ll << 20) / ((int64_t)c->d * 4));
+        for (int64_t off = 0; off < n; off += chunk) {
+            const int64_t m = std::min(chunk, n - off);
+            B200_TRY(c->w_raw.reserve((size_t)m * c->d * 4));
+            B200_CUDA_OK(cudaMemcpyAsync(c->w_raw.p, reinterpret_cast<const float *>(rows) + off * c->d, (size_t)m * c->d * 4,
+                                         cudaMemcpyHostToDevice, c->stream));
+            char *dd = dst + off * c->row_bytes;
+            if (c->dtype == B200_DTYPE_BF16)
+                B200_CUDA_OK(launch_f32_to_bf16_rows(c->w_raw.as<float>(), c->d, dd, c->d_pad, m, c->stream));
+            else
+                B200_CUDA_OK(launch_pad_rows_f32(c->w_raw.as<float>(), c->d, reinterpret_cast<float *>(dd), c->d_pad, m, c->stream));
+            B200_CUDA_OK(cudaStreamSynchronize(c->stream));  // w_raw is reused
+        }
+    }
+    if (c->dtype != B200_DTYPE_BIN) B200_TRY(corpus_norms(c, c->n, n));
+    B200_CUDA_OK(cudaStreamSynchronize(c->stream));
+    c->n += n;
+    return B200_OK;
+}
+
+extern "C" int b200_corpus_adopt_device(b200_corpus *c, const void *device_rows, int64_t n) {
+    if (!c || !device_rows || n < 0) return fail(B200_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (c->data) return fail(B200_ERR_INVALID, "corpus already holds data");
+    if (c->dtype != B200_DTYPE_BIN && c->d != c->d_pad)
+        return fail(B200_ERR_INVALID, "adopted rows must already be padded (d % 64 == 0 for bf16, d % 4 == 0 for f32)");
+    B200_CUDA_OK(cudaSetDevice(c->device));
+    c->data = const_cast<void *>(device_rows);
+    c->owns = false;
+    c->n = n;
+    c->cap = n;
+    if (c->metric == B200_METRIC_COSINE) B200_CUDA_OK(cudaMalloc(&c->row_scale, (size_t)n * 4 + 256));
+    if (c->metric == B200_METRIC_L2) B200_CUDA_OK(cudaMalloc(&c->row_bias, (size_t)n * 4 + 256));
+    if (c->dtype != B200_DTYPE_BIN) B200_TRY(corpus_norms(c, 0, n));
+    B200_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return B200_OK;
+}
+
+extern "C" int b200_corpus_size(const b200_corpus *c, int64_t *out_rows) {
+    if (!c || !out_rows) return fail(B200_ERR_INVALID, "null argument");
+    *out_rows = c->n;
+    return B200_OK;
+}
+
+extern "C" int b200_corpus_set_path(b200_corpus *c, int path) {
+    if (!c || path < 0 || path > 2) return fail(B200_ERR_INVALID, "path must be 0, 1 or 2");
+    c->path = path;
+    return B200_OK;
+}
+
+extern "C" int b200_corpus_enable_timing(b200_corpus *c, int on) {
+    if (!c) return fail(B200_ERR_INVALID, "null corpus");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->timing = on != 0;
+    return B200_OK;
+}
+
+extern "C" int b200_corpus_kernel_time(b200_corpus *c, int reset, double *out_total_ms, int64_t *out_launches) {
+    if (!c || !out_total_ms || !out_launches) return fail(B200_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    B200_CUDA_OK(cudaSetDevice(c->device));
+    for (auto &ev : c->ev_used) {
+        B200_CUDA_OK(cudaEventSynchronize(ev.second));
+        float ms = 0;
+        B200_CUDA_OK(cudaEventElapsedTime(&ms, ev.first, ev.second));
+        c->timed_ms += ms;
+        c->timed_launches++;
+        c->ev_free.push_back(ev);
+    }
+    c->ev_used.clear();
+    *out_total_ms = c->timed_ms;
+    *out_launches = c->timed_launches;
+    if (reset) {
+        c->timed_ms = 0;
+        c->timed_launches = 0;
+    }
+    return B200_OK;
+}
+
+extern "C" int b200_corpus_free(b200_corpus *c) {
+    if (!c) return B200_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->data && c->owns) cudaFree(c->data);
+    if (c->row_scale) cudaFree(c->row_scale);
+    if (c->row_bias) cudaFree(c->row_bias);
+    for (DevBuf *b : {&c->w_raw, &c->w_q32, &c->w_qbf, &c->w_qnorm, &c->w_pk, &c->w_pi, &c->w_lk, &c->w_li, &c->w_alive,
+                      &c->w_odis, &c->w_oids, &c->w_stage})
+        b->release();
+    for (auto *v : {&c->ev_used, &c->ev_free})
+        for (auto &ev : *v) {
+            cudaEventDestroy(ev.first);
+            cudaEventDestroy(ev.second);
+        }
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// search core: everything on device, asynchronous on `s`
+// d_queries: raw device fp32 [nq][d] (or bytes [nq][d/8] for binary corpora)
+// ------------------------------------------------------------------------------------
+static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k, const uint8_t *d_alive, int64_t id_offset,
+                       int ip_min_quirk, float *d_out_dis, int64_t *d_out_ids, cudaStream_t s) {
+    if (k <= 0) return fail(B200_ERR_INVALID, "k must be positive");
+    if (nq == 0) return B200_OK;
+    if (c->n >= (int64_t)0xffffffffll) return fail(B200_ERR_UNSUPPORTED, "corpus shards are limited to 2^32 - 1 rows");
+    const int sms = c->sms;
+
+    if (c->dtype == B200_DTYPE_BIN) {
+        if (k > 1024) return fail(B200_ERR_UNSUPPORTED, "k > 1024 not supported on the binary scan path");
+        int blocks_x = (int)std::min<int64_t>(std::max<int64_t>(1, ceil_div(c->n, 256)), std::max<int64_t>(1, (2 * sms) / std::max<int64_t>(1, std::min<int64_t>(nq, 2 * sms))));
+        B200_TRY(c->w_pk.reserve((size_t)nq * blocks_x * k * 4));
+        B200_TRY(c->w_pi.reserve((size_t)nq * blocks_x * k * 4));
+        BinaryScanParams bp{};
+        bp.corpus = reinterpret_cast<const uint8_t *>(c->data);
+        bp.queries = reinterpret_cast<const uint8_t *>(d_queries);
+        bp.alive = d_alive;
+        bp.part_keys = c->w_pk.as<float>();
+        bp.part_ids = c->w_pi.as<uint32_t>();
+        bp.n = c->n;
+        bp.nq = nq;
+        bp.nbytes = c->d_pad;
+        bp.k = k;
+        bp.jaccard = c->metric == B200_METRIC_JACCARD;
+        B200_CUDA_OK(launch_binary_scan(bp, blocks_x, s));
+        MergeParams mp{};
+        mp.in_keys = bp.part_keys;
+        mp.in_ids = bp.part_ids;
+        mp.list_stride = k;
+        mp.q_stride = (int64_t)blocks_x * k;
+        mp.n_lists = blocks_x;
+        mp.k_in = k;
+        mp.k = k;
+        mp.nq = nq;
+        mp.out_mode = kOutKey;
+        mp.id_offset = id_offset;
+        mp.out_dis = d_out_dis;
+        mp.out_ids = d_out_ids;
+        B200_CUDA_OK(launch_topk_merge(mp, false, s));
+        return B200_OK;
+    }
+
+    // ---- stage queries: pad to d_pad fp32, cosine -> normalise (VIWithDataPart.h:354-360)
+    B200_TRY(c->w_q32.reserve((size_t)nq * c->d_pad * 4));
+    float *q32 = c->w_q32.as<float>();
+    B200_CUDA_OK(launch_pad_rows_f32(reinterpret_cast<const float *>(d_queries), c->d, q32, c->d_pad, nq, s));
+    if (c->metric == B200_METRIC_COSINE) B200_CUDA_OK(launch_normalize_rows_f32(q32, c->d_pad, nq, s));
+
+    int path = c->path;
+    if (path == 0) path = (c->dtype == B200_DTYPE_BF16 && nq >= 16) ? 2 : 1;
+    if (path == 2 && c->dtype != B200_DTYPE_BF16)
+        return fail(B200_ERR_UNSUPPORTED, "the tcgen05 GEMM path needs a bf16 corpus");
+
+    const int out_mode_scan = c->metric == B200_METRIC_L2 ? kOutKey : c->metric == B200_METRIC_IP ? kOutNeg : kOutOnePlus;
+
+    if (path == 1) {
+        if (k > 2048) return fail(B200_ERR_UNSUPPORTED, "k > 2048 not supported on the scan path");
+        int qt = nq == 1 ? 1 : nq <= 4 ? 4 : 8;
+        while (qt > 1 && scan_smem_bytes(qt, c->d_pad, k) > 100 * 1024) qt = qt == 8 ? 4 : 1;
+        if (scan_smem_bytes(qt, c->d_pad, k) > 200 * 1024)
+            return fail(B200_ERR_UNSUPPORTED, "d * 4 + 64 * k exceeds the shared-memory budget of the scan kernel");
+        const int elems = c->dtype == B200_DTYPE_BF16 ? 8 : 4;
+        const int chunks = c->d_pad / elems;
+        int group = 1;
+        while (group < 32 && group < chunks) group <<= 1;
+        const int64_t y_tiles = ceil_div(nq, qt);
+        const int64_t rows_per_block_step = 8 * (32 / group);
+        int64_t bx = std::max<int64_t>(1, (2 * sms) / std::min<int64_t>(y_tiles, 2 * sms));
+        bx = std::min<int64_t>(bx, std::max<int64_t>(1, ceil_div(c->n, rows_per_block_step)));
+        const int blocks_x = (int)bx;
+        B200_TRY(c->w_pk.reserve((size_t)nq * blocks_x * k * 4));
+        B200_TRY(c->w_pi.reserve((size_t)nq * blocks_x * k * 4));
+        ScanParams sp{};
+        sp.corpus = c->data;
+        sp.queries = q32;
+        sp.row_scale = c->metric == B200_METRIC_COSINE ? c->row_scale : nullptr;
+        sp.alive = d_alive;
+        sp.part_keys = c->w_pk.as<float>();
+        sp.part_ids = c->w_pi.as<uint32_t>();
+        sp.n = c->n;
+        sp.nq = nq;
+        sp.row_bytes = c->row_bytes;
+        sp.d_pad = c->d_pad;
+        sp.k = k;
+        sp.group = group;
+        sp.l2 = c->metric == B200_METRIC_L2;
+        sp.bf16 = c->dtype == B200_DTYPE_BF16;
+        std::pair<cudaEvent_t, cudaEvent_t> ev;
+        timing_begin(c, s, ev);
+        B200_CUDA_OK(launch_flat_scan(sp, qt, blocks_x, s));
+        timing_end(c, s, ev);
+        MergeParams mp{};
+        mp.in_keys = sp.part_keys;
+        mp.in_ids = sp.part_ids;
+        mp.list_stride = k;
+        mp.q_stride = (int64_t)blocks_x * k;
+        mp.n_lists = blocks_x;
+        mp.k_in = k;
+        mp.k = k;
+        mp.nq = nq;
+        mp.out_mode = out_mode_scan;
+        mp.ip_min_quirk = ip_min_quirk && c->metric == B200_METRIC_IP;
+        mp.id_offset = id_offset;
+        mp.out_dis = d_out_dis;
+        mp.out_ids = d_out_ids;
+        B200_CUDA_OK(launch_topk_merge(mp, false, s));
+        return B200_OK;
+    }
+
+    // ---- path 2: tcgen05 GEMM with fused top-k, <= 1024 queries (8 query tiles) per launch
+    if (k > 1024) return fail(B200_ERR_UNSUPPORTED, "k > 1024 not supported on the GEMM path");
+    const int64_t QCHUNK = 1024;
+    for (int64_t qb = 0; qb < nq; qb += QCHUNK) {
+        const int64_t nq_c = std::min(QCHUNK, nq - qb);
+        const int nq_pad = (int)round_up(nq_c, 128);
+        const int q_tiles = nq_pad / 128;
+        B200_TRY(c->w_qbf.reserve((size_t)nq_pad * c->d_pad * 2));
+        B200_CUDA_OK(cudaMemsetAsync(c->w_qbf.p, 0, (size_t)nq_pad * c->d_pad * 2, s));
+        B200_CUDA_OK(launch_f32_to_bf16_rows(q32 + qb * c->d_pad, c->d_pad, c->w_qbf.p, c->d_pad, nq_c, s));
+        const float *q_add = nullptr;
+        if (c->metric == B200_METRIC_L2) {
+            B200_TRY(c->w_qnorm.reserve((size_t)nq_pad * 4));
+            B200_CUDA_OK(launch_row_norms(c->w_qbf.p, 1, c->d_pad, nq_c, 0, c->w_qnorm.as<float>(), s));
+            q_add = c->w_qnorm.as<float>();
+        }
+        int grid = gemm_topk_grid(q_tiles, c->n, sms);
+        grid = (grid / q_tiles) * q_tiles;
+        if (grid < q_tiles) grid = q_tiles;
+        B200_TRY(c->w_pk.reserve((size_t)grid * 128 * k * 4));
+        B200_TRY(c->w_pi.reserve((size_t)grid * 128 * k * 4));
+        GemmTopkParams gp{};
+        gp.corpus_bf16 = c->data;
+        gp.queries_bf16 = c->w_qbf.p;
+        gp.row_scale = c->metric == B200_METRIC_COSINE ? c->row_scale : nullptr;
+        gp.scale_const = c->metric == B200_METRIC_L2 ? -2.f : -1.f;
+        gp.row_bias = c->metric == B200_METRIC_L2 ? c->row_bias : nullptr;
+        gp.alive = d_alive;
+        gp.part_keys = c->w_pk.as<float>();
+        gp.part_ids = c->w_pi.as<uint32_t>();
+        if (k > kGemmSmemK) {
+            B200_TRY(c->w_lk.reserve((size_t)grid * 128 * k * 4));
+            B200_TRY(c->w_li.reserve((size_t)grid * 128 * k * 4));
+            gp.list_keys_gmem = c->w_lk.as<float>();
+            gp.list_ids_gmem = c->w_li.as<uint32_t>();
+        }
+        gp.n = c->n;
+        gp.nq_pad = nq_pad;
+        gp.d_pad = c->d_pad;
+        gp.k = k;
+        gp.q_tiles = q_tiles;
+        const char *detail = nullptr;
+        std::pair<cudaEvent_t, cudaEvent_t> ev;
+        timing_begin(c, s, ev);
+        cudaError_t e = launch_gemm_topk(gp, grid, s, &detail);
+        timing_end(c, s, ev);
+        if (e != cudaSuccess)
+            return fail(B200_ERR_CUDA, std::string("gemm_topk launch: ") + (detail ? detail : cudaGetErrorString(e)));
+        MergeParams mp{};
+        mp.in_keys = gp.part_keys;
+        mp.in_ids = gp.part_ids;
+        mp.list_stride = (int64_t)nq_pad * k;
+        mp.q_stride = k;
+        mp.n_lists = grid / q_tiles;
+        mp.k_in = k;
+        mp.k = k;
+        mp.nq = nq_c;
+        mp.out_mode = c->metric == B200_METRIC_L2 ? kOutAddQ : c->metric == B200_METRIC_IP ? kOutNeg : kOutOnePlus;
+        mp.q_add = q_add;
+        mp.ip_min_quirk = ip_min_quirk && c->metric == B200_METRIC_IP;
+        mp.id_offset = id_offset;
+        mp.out_dis = d_out_dis + qb * k;
+        mp.out_ids = d_out_ids + qb * k;
+        B200_CUDA_OK(launch_topk_merge(mp, false, s));
+    }
+    return B200_OK;
+}
+
+extern "C" int b200_corpus_search_device(b200_corpus *c, const float *d_queries, int64_t nq, int k,
+                                         const uint8_t *d_alive_bits, int64_t id_offset, float *d_out_dis,
+                                         int64_t *d_out_ids, void *stream) {
+    if (!c || (!d_queries && nq > 0) || !d_out_dis || !d_out_ids || nq < 0)
+        return fail(B200_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> lk(c->mu);
+    B200_CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : c->stream;
+    B200_TRY(search_core(c, d_queries, nq, k, d_alive_bits, id_offset, 0, d_out_dis, d_out_ids, s));
+    if (!stream) B200_CUDA_OK(cudaStreamSynchronize(s));
+    return B200_OK;
+}
+
+static int search_host(b200_corpus *c, const void *queries, int64_t nq, int k, const uint8_t *alive_bits, int ip_min_quirk,
+                       float *out_dis, int64_t *out_ids) {
+    if (!c || (!queries && nq > 0) || !out_dis || !out_ids || nq < 0 || k <= 0)
+        return fail(B200_ERR_INVALID, "bad arguments");
+    if (nq == 0) return B200_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    B200_CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const size_t q_bytes = c->dtype == B200_DTYPE_BIN ? (size_t)nq * c->d_pad : (size_t)nq * c->d * 4;
+    B200_TRY(c->w_stage.reserve(q_bytes));
+    B200_TRY(c->w_odis.reserve((size_t)nq * k * 4));
+    B200_TRY(c->w_oids.reserve((size_t)nq * k * 8));
+    B200_CUDA_OK(cudaMemcpyAsync(c->w_stage.p, queries, q_bytes, cudaMemcpyHostToDevice, s));
+    const uint8_t *d_alive = nullptr;
+    if (alive_bits) {
+        const size_t ab = (size_t)ceil_div(c->n, 8);
+        B200_TRY(c->w_alive.reserve(ab + 16));
+        B200_CUDA_OK(cudaMemcpyAsync(c->w_alive.p, alive_bits, ab, cudaMemcpyHostToDevice, s));
+        d_alive = c->w_alive.as<uint8_t>();
+    }
+    B200_TRY(search_core(c, c->w_stage.p, nq, k, d_alive, 0, ip_min_quirk, c->w_odis.as<float>(), c->w_oids.as<int64_t>(), s));
+    B200_CUDA_OK(cudaMemcpyAsync(out_dis, c->w_odis.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaMemcpyAsync(out_ids, c->w_oids.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    return B200_OK;
+}
+
+extern "C" int b200_corpus_search(b200_corpus *c, const float *queries, int64_t nq, int k, const uint8_t *alive_bits,
+                                  float *out_dis, int64_t *out_ids) {
+    return search_host(c, queries, nq, k, alive_bits, 0, out_dis, out_ids);
+}
+
+static void fill_empty(int metric, int64_t n, float *dis, int64_t *ids, int quirk) {
+    for (int64_t i = 0; i < n; i++) {
+        ids[i] = -1;
+        dis[i] = quirk ? FLT_MIN : (metric == B200_METRIC_IP ? -FLT_MAX : FLT_MAX);
+    }
+}
+
+extern "C" int b200_flat_knn(int metric, const float *x, int64_t nx, const float *y, int64_t ny, int d, int k,
+                             const uint8_t *alive_bits, float *out_dis, int64_t *out_ids) {
+    if (!is_float_metric(metric)) return fail(B200_ERR_INVALID, "b200_flat_knn: metric must be L2, IP or COSINE");
+    if (nx < 0 || ny < 0 || d <= 0 || k <= 0 || !out_dis || !out_ids) return fail(B200_ERR_INVALID, "bad arguments");
+    B200_TRY(ensure_device());
+    if (nx == 0) return B200_OK;
+    if (ny == 0) {
+        fill_empty(metric, nx * k, out_dis, out_ids, 0);
+        return B200_OK;
+    }
+    b200_corpus *c = nullptr;
+    B200_TRY(b200_corpus_create(metric, B200_DTYPE_F32, d, ny, &c));
+    int rc = b200_corpus_append(c, y, ny);
+    if (rc == B200_OK) rc = search_host(c, x, nx, k, alive_bits, 0, out_dis, out_ids);
+    std::string keep = g_error;
+    b200_corpus_free(c);
+    g_error = keep;
+    return rc;
+}
+
+extern "C" int b200_binary_knn(int metric, const uint8_t *x, int64_t nx, const uint8_t *y, int64_t ny, int nbytes, int k,
+                               const uint8_t *alive_bits, float *out_dis, int64_t *out_ids) {
+    if (!is_bin_metric(metric)) return fail(B200_ERR_INVALID, "b200_binary_knn: metric must be HAMMING or JACCARD");
+    if (nx < 0 || ny < 0 || nbytes <= 0 || k <= 0 || !out_dis || !out_ids) return fail(B200_ERR_INVALID, "bad arguments");
+    B200_TRY(ensure_device());
+    if (nx == 0) return B200_OK;
+    if (ny == 0) {
+        fill_empty(metric, nx * k, out_dis, out_ids, 0);
+        return B200_OK;
+    }
+    b200_corpus *c = nullptr;
+    B200_TRY(b200_corpus_create(metric, B200_DTYPE_BIN, nbytes * 8, ny, &c));
+    int rc = b200_corpus_append(c, y, ny);
+    if (rc == B200_OK) rc = search_host(c, x, nx, k, alive_bits, 0, out_dis, out_ids);
+    std::string keep = g_error;
+    b200_corpus_free(c);
+    g_error = keep;
+    return rc;
+}
+
+extern "C" int b200_part_scan(int metric, const void *x, int64_t nx, const void *y, int64_t ny, int d, int k,
+                              int64_t block_rows, const uint8_t *row_exists, const uint8_t *filter_bits, float *out_dis,
+                              int64_t *out_ids) {
+    (void)block_rows;
+    if (nx < 0 || ny < 0 || d <= 0 || k <= 0 || !out_dis || !out_ids) return fail(B200_ERR_INVALID, "bad arguments");
+    if (!is_float_metric(metric) && !is_bin_metric(metric)) return fail(B200_ERR_INVALID, "unknown metric");
+    B200_TRY(ensure_device());
+    if (nx == 0) return B200_OK;
+    const int quirk = metric == B200_METRIC_IP;
+    if (ny == 0) {
+        fill_empty(metric, nx * k, out_dis, out_ids, quirk);
+        return B200_OK;
+    }
+    // alive = filter (which already folds the lightweight-delete mask, MergeTreeVSManager.cpp:1040)
+    // or, without filter, the _row_exists column
+    std::vector<uint8_t> alive;
+    const uint8_t *alive_ptr = filter_bits;
+    if (!filter_bits && row_exists) {
+        alive.assign((size_t)ceil_div(ny, 8), 0);
+        for (int64_t i = 0; i < ny; i++)
+            if (row_exists[i]) alive[i >> 3] |= (uint8_t)(1u << (i & 7));
+        alive_ptr = alive.data();
+    }
+    b200_corpus *c = nullptr;
+    const bool bin = is_bin_metric(metric);
+    B200_TRY(b200_corpus_create(metric, bin ? B200_DTYPE_BIN : B200_DTYPE_F32, d, ny, &c));
+    int rc = b200_corpus_append(c, y, ny);
+    if (rc == B200_OK) rc = search_host(c, x, nx, k, alive_ptr, quirk, out_dis, out_ids);
+    std::string keep = g_error;
+    b200_corpus_free(c);
+    g_error = keep;
+    return rc;
+}
+
+extern "C" int b200_topk_merge_device(const float *d_dis, const int64_t *d_ids, int n_lists, int64_t nq, int k,
+                                      int descending, float *d_out_dis, int64_t *d_out_ids, void *stream) {
+    if (!d_dis || !d_ids || !d_out_dis || !d_out_ids || n_lists <= 0 || nq < 0 || k <= 0)
+        return fail(B200_ERR_INVALID, "bad arguments");
+    if (k > 2048) return fail(B200_ERR_UNSUPPORTED, "k > 2048 not supported by the merge kernel");
+    B200_TRY(ensure_device());
+    if (nq == 0) return B200_OK;
+    MergeParams mp{};
+    mp.in_keys = d_dis;
+    mp.in_ids = d_ids;
+    mp.list_stride = nq * k;
+    mp.q_stride = k;
+    mp.n_lists = n_lists;
+    mp.k_in = k;
+    mp.k = k;
+    mp.nq = nq;
+    mp.descending = descending;
+    mp.out_mode = descending ? kOutNeg : kOutKey;
+    mp.out_dis = d_out_dis;
+    mp.out_ids = d_out_ids;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    B200_CUDA_OK(launch_topk_merge(mp, true, s));
+    if (!stream) B200_CUDA_OK(cudaStreamSynchronize(s));
+    return B200_OK;
+}

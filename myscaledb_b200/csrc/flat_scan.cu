@@ -1,0 +1,402 @@
+// flat_scan.cu -- memory-bound FLAT scan kernels (K1/K3/K4) and the k-way merge (K7).
+//
+// K1/K3  flat_scan_kernel : squared-L2 / inner-product / cosine of <= 8 queries per pass
+//        against a row-major corpus (fp32 or bf16) with 128-bit streaming loads,
+//        sub-warp groups per row, warp-shuffle reduction and a fused per-warp top-k.
+//        Replaces faiss::knn_L2sqr / knn_inner_product as called from
+//        tryBruteForceSearch (reference: VectorIndex/Common/BruteForceSearch.h:77-88).
+//        HBM-bound: algorithmic bytes = n * d * sizeof(elem) per pass.
+// K4     binary_scan_kernel : Hamming / Jaccard via __popc (BruteForceSearch.h:96-105).
+// K7     topk_merge_kernel : merges P sorted lists per query; replaces the running merge
+//        in searchWrapper (MergeTreeVSManager.cpp:1652-1678) and the multimap merge in
+//        getTotalTopSearchResultImpl (MergeTreeBaseSearchManager.cpp:207-299).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200 {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanWarps = kScanThreads / 32;
+
+// ------------------------------------------------------------------------------------
+template <int N>
+struct QChunk {
+    float v[N];
+};
+
+template <bool BF16>
+struct ChunkTraits;
+template <>
+struct ChunkTraits<false> {
+    static constexpr int kElems = 4;
+    __device__ static __forceinline__ void unpack(const uint4 &r, float (&f)[4]) {
+        f[0] = __uint_as_float(r.x);
+        f[1] = __uint_as_float(r.y);
+        f[2] = __uint_as_float(r.z);
+        f[3] = __uint_as_float(r.w);
+    }
+};
+template <>
+struct ChunkTraits<true> {
+    static constexpr int kElems = 8;
+    __device__ static __forceinline__ void unpack(const uint4 &r, float (&f)[8]) {
+        f[0] = __uint_as_float(r.x << 16);
+        f[1] = __uint_as_float(r.x & 0xffff0000u);
+        f[2] = __uint_as_float(r.y << 16);
+        f[3] = __uint_as_float(r.y & 0xffff0000u);
+        f[4] = __uint_as_float(r.z << 16);
+        f[5] = __uint_as_float(r.z & 0xffff0000u);
+        f[6] = __uint_as_float(r.w << 16);
+        f[7] = __uint_as_float(r.w & 0xffff0000u);
+    }
+};
+
+// QT queries per pass, U rows in flight per group, L2 = squared-L2 vs inner product
+// (cosine = inner product scaled by the stored inverse row norm).
+template <int QT, int U, bool L2, bool BF16>
+__global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanParams p) {
+    using CT = ChunkTraits<BF16>;
+    constexpr int E = CT::kElems;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *qs = reinterpret_cast<float *>(smem_raw);                        // [QT][d_pad]
+    float *lk = qs + (size_t)QT * p.d_pad;                                   // [warps][QT][k]
+    uint32_t *li = reinterpret_cast<uint32_t *>(lk + (size_t)kScanWarps * QT * p.k);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t q0 = (int64_t)blockIdx.y * QT;
+    const int nq_here = (int)min((int64_t)QT, p.nq - q0);
+
+    // stage queries (zero-padded) in shared memory
+    for (int i = threadIdx.x; i < QT * p.d_pad; i += kScanThreads) {
+        const int q = i / p.d_pad, j = i - q * p.d_pad;
+        qs[i] = (q < nq_here) ? p.queries[(q0 + q) * p.d_pad + j] : 0.f;
+    }
+    WarpTopK lists[QT];
+#pragma unroll
+    for (int q = 0; q < QT; q++)
+    {
+        lists[q].init(lk + ((size_t)warp * QT + q) * p.k, li + ((size_t)warp * QT + q) * p.k, p.k);
+        for (int j = lane; j < p.k; j += 32) lists[q].keys[j] = FLT_MAX;  // sentinel for the block merge
+    }
+    __syncthreads();
+
+    const int G = p.group;           // lanes per row (power of two)
+    const int R = 32 / G;            // rows per warp step
+    const int sub = lane / G, gl = lane - sub * G;
+    const int64_t total_groups = (int64_t)gridDim.x * kScanWarps * R;
+    const int64_t gidx = ((int64_t)blockIdx.x * kScanWarps + warp) * R + sub;
+    const int chunks = p.d_pad / E;
+    const unsigned char *base = reinterpret_cast<const unsigned char *>(p.corpus);
+
+    for (int64_t it = 0;; it++) {
+        const int64_t row0 = gidx + it * U * total_groups;
+        // warp-uniform exit: the smallest row of this step over the warp is for sub == 0
+        if (row0 - sub >= p.n) break;
+        float acc[U][QT];
+        bool valid[U];
+        const uint4 *rp[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t row = row0 + (int64_t)u * total_groups;
+            valid[u] = row < p.n;
+            if (valid[u] && p.alive) valid[u] = (p.alive[row >> 3] >> (row & 7)) & 1;
+            rp[u] = reinterpret_cast<const uint4 *>(base + (size_t)(valid[u] ? row : 0) * p.row_bytes);
+#pragma unroll
+            for (int q = 0; q < QT; q++) acc[u][q] = 0.f;
+        }
+        for (int c = gl; c < chunks; c += G) {
+            uint4 raw[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) raw[u] = valid[u] ? ldg_stream(rp[u] + c) : make_uint4(0, 0, 0, 0);
+            float y[U][E];
+#pragma unroll
+            for (int u = 0; u < U; u++) CT::unpack(raw[u], y[u]);
+#pragma unroll
+            for (int q = 0; q < QT; q++) {
+                float x[E];
+                const float4 *qp = reinterpret_cast<const float4 *>(qs + (size_t)q * p.d_pad + (size_t)c * E);
+#pragma unroll
+                for (int e4 = 0; e4 < E / 4; e4++) {
+                    const float4 t = qp[e4];
+                    x[e4 * 4 + 0] = t.x;
+                    x[e4 * 4 + 1] = t.y;
+                    x[e4 * 4 + 2] = t.z;
+                    x[e4 * 4 + 3] = t.w;
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+#pragma unroll
+                    for (int e = 0; e < E; e++) {
+                        if (L2) {
+                            const float t = x[e] - y[u][e];
+                            acc[u][q] = fmaf(t, t, acc[u][q]);
+                        } else {
+                            acc[u][q] = fmaf(x[e], y[u][e], acc[u][q]);
+                        }
+                    }
+                }
+            }
+        }
+        // reduce over the G lanes of each group
+        for (int o = G >> 1; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < U; u++)
+#pragma unroll
+                for (int q = 0; q < QT; q++) acc[u][q] += __shfl_xor_sync(0xffffffffu, acc[u][q], o);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t row = row0 + (int64_t)u * total_groups;
+            float scale = 1.f;
+            if (!L2) scale = (p.row_scale && valid[u]) ? p.row_scale[row] : -1.f;
+#pragma unroll
+            for (int q = 0; q < QT; q++) {
+                const float key = L2 ? acc[u][q] : acc[u][q] * scale;
+                const bool cand = valid[u] && gl == 0 && q < nq_here && lists[q].passes(key, (uint32_t)row);
+                unsigned m = __ballot_sync(0xffffffffu, cand);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float ck = __shfl_sync(0xffffffffu, key, src);
+                    const uint32_t ci = __shfl_sync(0xffffffffu, (uint32_t)row, src);
+                    lists[q].insert(ck, ci);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // block merge: warp 0 absorbs the lists of warps 1..7, then writes the partial
+    if (warp == 0) {
+#pragma unroll
+        for (int q = 0; q < QT; q++) {
+            if (q >= nq_here) break;
+            for (int w = 1; w < kScanWarps; w++) {
+                const float *wk = lk + ((size_t)w * QT + q) * p.k;
+                const uint32_t *wi = li + ((size_t)w * QT + q) * p.k;
+                // slots beyond a warp's n hold the FLT_MAX sentinel
+                for (int j = 0; j < p.k; j++) {
+                    const float ck = wk[j];
+                    if (!(ck < FLT_MAX)) break;
+                    lists[q].insert(ck, wi[j]);
+                }
+            }
+            float *ok = p.part_keys + ((q0 + q) * (int64_t)gridDim.x + blockIdx.x) * p.k;
+            uint32_t *oi = p.part_ids + ((q0 + q) * (int64_t)gridDim.x + blockIdx.x) * p.k;
+            for (int j = lane; j < p.k; j += 32) {
+                ok[j] = j < lists[q].n ? lists[q].keys[j] : FLT_MAX;
+                oi[j] = j < lists[q].n ? lists[q].ids[j] : kNoId;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K4: binary vectors.  One thread per row, grid.y = query.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kScanThreads) binary_scan_kernel(const BinaryScanParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint8_t *qb = smem_raw;                                                         // [nbytes] (padded to 16)
+    float *lk = reinterpret_cast<float *>(smem_raw + round_up(p.nbytes, 16));       // [warps][k]
+    uint32_t *li = reinterpret_cast<uint32_t *>(lk + (size_t)kScanWarps * p.k);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t q = blockIdx.y;
+    for (int i = threadIdx.x; i < p.nbytes; i += kScanThreads) qb[i] = p.queries[q * p.nbytes + i];
+    WarpTopK list;
+    list.init(lk + (size_t)warp * p.k, li + (size_t)warp * p.k, p.k);
+    for (int j = lane; j < p.k; j += 32) list.keys[j] = FLT_MAX;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * kScanThreads;
+    for (int64_t row0 = (int64_t)blockIdx.x * kScanThreads + warp * 32; row0 < p.n; row0 += stride) {
+        const int64_t row = row0 + lane;
+        bool valid = row < p.n;
+        if (valid && p.alive) valid = (p.alive[row >> 3] >> (row & 7)) & 1;
+        float key = FLT_MAX;
+        if (valid) {
+            const uint8_t *y = p.corpus + (size_t)row * p.nbytes;
+            int x_or = 0, x_and = 0, x_xor = 0;
+            if ((p.nbytes & 3) == 0) {
+                const uint32_t *yw = reinterpret_cast<const uint32_t *>(y);
+                const uint32_t *qw = reinterpret_cast<const uint32_t *>(qb);
+                for (int j = 0; j < p.nbytes / 4; j++) {
+                    const uint32_t a = qw[j], b = yw[j];
+                    x_xor += __popc(a ^ b);
+                    x_and += __popc(a & b);
+                    x_or += __popc(a | b);
+                }
+            } else {
+                for (int j = 0; j < p.nbytes; j++) {
+                    const uint32_t a = qb[j], b = y[j];
+                    x_xor += __popc(a ^ b);
+                    x_and += __popc(a & b);
+                    x_or += __popc(a | b);
+                }
+            }
+            key = p.jaccard ? (x_or == 0 ? 0.f : (float)(x_or - x_and) / (float)x_or) : (float)x_xor;
+        }
+        const bool cand = valid && list.passes(key, (uint32_t)row);
+        unsigned m = __ballot_sync(0xffffffffu, cand);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            list.insert(__shfl_sync(0xffffffffu, key, src), __shfl_sync(0xffffffffu, (uint32_t)row, src));
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        for (int w = 1; w < kScanWarps; w++)
+            for (int j = 0; j < p.k; j++) {
+                const float ck = lk[(size_t)w * p.k + j];
+                if (!(ck < FLT_MAX)) break;
+                list.insert(ck, li[(size_t)w * p.k + j]);
+            }
+        float *ok = p.part_keys + (q * (int64_t)gridDim.x + blockIdx.x) * p.k;
+        uint32_t *oi = p.part_ids + (q * (int64_t)gridDim.x + blockIdx.x) * p.k;
+        for (int j = lane; j < p.k; j += 32) {
+            ok[j] = j < list.n ? list.keys[j] : FLT_MAX;
+            oi[j] = j < list.n ? list.ids[j] : kNoId;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K7: merge.  One block per query; 8 warps filter slices of the candidate set into warp
+// lists, warp 0 merges them and writes the final, converted result.
+// ------------------------------------------------------------------------------------
+template <typename IdT, bool EXTERNAL>
+__global__ void __launch_bounds__(kScanThreads) topk_merge_kernel(const MergeParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *lk = reinterpret_cast<float *>(smem_raw);
+    uint32_t *li = reinterpret_cast<uint32_t *>(lk + (size_t)kScanWarps * p.k);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t q = blockIdx.x;
+    WarpTopK list;
+    list.init(lk + (size_t)warp * p.k, li + (size_t)warp * p.k, p.k);
+    for (int j = lane; j < p.k; j += 32) list.keys[j] = FLT_MAX;
+    __syncwarp();
+    const float *keys = reinterpret_cast<const float *>(p.in_keys);
+    const IdT *ids = reinterpret_cast<const IdT *>(p.in_ids);
+    const int64_t ncand = (int64_t)p.n_lists * p.k_in;
+    for (int64_t c0 = (int64_t)warp * 32; c0 < ncand; c0 += kScanThreads) {
+        const int64_t c = c0 + lane;
+        float key = FLT_MAX;
+        uint32_t id = kNoId;
+        bool cand = false;
+        if (c < ncand) {
+            const int64_t l = c / p.k_in, j = c - l * p.k_in;
+            const int64_t off = l * p.list_stride + q * p.q_stride + j;
+            const float v = keys[off];
+            if (EXTERNAL) {
+                // external lists carry 64-bit ids (negative = empty slot); row ids are
+                // UInt32 labels in the reference (ColumnUInt32, MergeTreeVSManager.cpp:469),
+                // shard offsets keep them < 2^32 - 1
+                const int64_t full = (int64_t)ids[off];
+                if (full >= 0) {
+                    key = p.descending ? -v : v;
+                    id = (uint32_t)full;
+                    cand = list.passes(key, id);
+                }
+            } else {
+                id = (uint32_t)ids[off];
+                key = v;
+                cand = id != kNoId && list.passes(key, id);
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, cand);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            list.insert(__shfl_sync(0xffffffffu, key, src), __shfl_sync(0xffffffffu, id, src));
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        for (int w = 1; w < kScanWarps; w++)
+            for (int j = 0; j < p.k; j++) {
+                const float ck = lk[(size_t)w * p.k + j];
+                if (!(ck < FLT_MAX)) break;
+                list.insert(ck, li[(size_t)w * p.k + j]);
+            }
+        for (int j = lane; j < p.k; j += 32) {
+            float dis;
+            int64_t id;
+            if (j < list.n) {
+                const float key = list.keys[j];
+                id = (int64_t)list.ids[j] + p.id_offset;
+                switch (p.out_mode) {
+                    case kOutKey: dis = key; break;
+                    case kOutNeg: dis = -key; break;
+                    case kOutOnePlus: dis = 1.f + key; break;
+                    default: dis = fmaxf(key + p.q_add[q], 0.f); break;  // kOutAddQ
+                }
+                if (p.ip_min_quirk && !(dis > FLT_MIN)) {
+                    // vectorScanWithoutIndex IP init = numeric_limits<float>::min() (smallest positive)
+                    id = -1;
+                    dis = FLT_MIN;
+                }
+            } else {
+                id = -1;
+                dis = (p.out_mode == kOutNeg) ? -FLT_MAX : FLT_MAX;
+                if (p.ip_min_quirk) dis = FLT_MIN;
+            }
+            p.out_dis[q * p.k + j] = dis;
+            p.out_ids[q * p.k + j] = id;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------
+template <int QT, int U>
+static cudaError_t launch_scan_qt(const ScanParams &p, dim3 grid, size_t smem, cudaStream_t s) {
+    auto go = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, kScanThreads, smem, s>>>(p);
+        g_launches++;
+        return cudaGetLastError();
+    };
+    if (p.l2) return p.bf16 ? go(flat_scan_kernel<QT, U, true, true>) : go(flat_scan_kernel<QT, U, true, false>);
+    return p.bf16 ? go(flat_scan_kernel<QT, U, false, true>) : go(flat_scan_kernel<QT, U, false, false>);
+}
+
+size_t scan_smem_bytes(int qt, int d_pad, int k) {
+    return (size_t)qt * d_pad * 4 + (size_t)kScanWarps * qt * k * 8;
+}
+
+cudaError_t launch_flat_scan(const ScanParams &p, int qt, int blocks_x, cudaStream_t s) {
+    const dim3 grid(blocks_x, (unsigned)ceil_div(p.nq, qt));
+    const size_t smem = scan_smem_bytes(qt, p.d_pad, p.k);
+    const int elems = p.bf16 ? 8 : 4;
+    const int chunks_per_lane = (int)ceil_div(p.d_pad / elems, p.group);
+    const bool u4 = chunks_per_lane <= 2;
+    switch (qt) {
+        case 1: return u4 ? launch_scan_qt<1, 4>(p, grid, smem, s) : launch_scan_qt<1, 2>(p, grid, smem, s);
+        case 4: return u4 ? launch_scan_qt<4, 4>(p, grid, smem, s) : launch_scan_qt<4, 2>(p, grid, smem, s);
+        default: return u4 ? launch_scan_qt<8, 4>(p, grid, smem, s) : launch_scan_qt<8, 2>(p, grid, smem, s);
+    }
+}
+
+cudaError_t launch_binary_scan(const BinaryScanParams &p, int blocks_x, cudaStream_t s) {
+    const dim3 grid(blocks_x, (unsigned)p.nq);
+    const size_t smem = round_up(p.nbytes, 16) + (size_t)kScanWarps * p.k * 8;
+    cudaError_t e = cudaFuncSetAttribute(binary_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    binary_scan_kernel<<<grid, kScanThreads, smem, s>>>(p);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_topk_merge(const MergeParams &p, bool external, cudaStream_t s) {
+    const size_t smem = (size_t)kScanWarps * p.k * 8;
+    auto go = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)p.nq, kScanThreads, smem, s>>>(p);
+        g_launches++;
+        return cudaGetLastError();
+    };
+    return external ? go(topk_merge_kernel<int64_t, true>) : go(topk_merge_kernel<uint32_t, false>);
+}
+
+}  // namespace b200

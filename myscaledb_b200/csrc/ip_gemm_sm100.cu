@@ -1,0 +1,405 @@
+// ip_gemm_sm100.cu -- K2: batched multi-query x corpus inner product as a dense bf16 GEMM
+// on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA),
+// with the top-k selection FUSED into the epilogue: the [nq x N] score matrix is never
+// written to memory.
+//
+// Replaces faiss::knn_inner_product / knn_L2sqr for nx >= 20 (the BLAS sgemm path) reached
+// from tryBruteForceSearch (reference: VectorIndex/Common/BruteForceSearch.h:77-88) and the
+// FLAT Search::VectorIndex::search scan (VectorIndex/Common/VIWithDataPart.cpp:926).
+//
+// Shape of one CTA tile: D[128 queries (TMEM lanes) x 256 corpus rows (TMEM columns)],
+// K-loop over d in blocks of 64 bf16 (= one 128-byte swizzle atom row).
+//   warp 0      : TMA producer (one lane)        -- A = query tile, B = corpus tile
+//   warp 1      : TMEM allocator + MMA issuer (one lane), tcgen05.mma cta_group::1 kind::f16
+//   warps 2..5  : epilogue; thread t owns TMEM lane t = one query, streams the 256 scores of
+//                 the tile through a register threshold test and keeps a private sorted
+//                 top-k in shared memory (k <= 30) or global scratch (larger k)
+// Pipelines: 4-stage smem ring (full/empty mbarriers), 2-stage TMEM accumulator ring.
+// Each CTA owns ONE query tile for its whole life (blockIdx % q_tiles) and walks the corpus
+// tiles worker, worker+W, ...; thresholds therefore live in registers for the whole kernel.
+// The key that is ranked is  acc * row_scale[j] + row_bias[j]  (smaller = better):
+//   IP: -acc | L2: ||y||^2 - 2 acc (+||q||^2 added at merge) | cosine: -acc / ||y||
+//   filtered / out-of-range rows: scale 0, bias +inf.
+//
+// Tensor-bound: 2 * 128 * 256 * d FLOP per tile; algorithmic HBM bytes = N * d * 2 once.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200 {
+namespace gemm {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int ACC_STAGES = 2;
+constexpr int UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2;           // 16 KB
+constexpr int B_BYTES = BN * BK * 2;           // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES; // 48 KB
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_THREADS = 128;
+constexpr int TMEM_COLS = 512;
+
+constexpr int OFF_A = 0;
+constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
+constexpr int OFF_SIDE = OFF_B + STAGES * B_BYTES;   // scale[256], bias[256]
+constexpr int OFF_BAR = OFF_SIDE + 2 * BN * 4;
+constexpr int OFF_LIST = OFF_BAR + 128;
+constexpr int SMEM_ALIGN_SLACK = 1024;
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    while (!mbar_try_wait(addr, parity)) {
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// K-major, 128-byte swizzled operand tile: rows of 64 bf16 (128 B), 8-row atoms of 1024 B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);  // start address
+    d |= (uint64_t)1 << 16;                      // leading byte offset (unused for SW128 K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset: 8 rows * 128 B
+    d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
+    return d;
+}
+
+// kind::f16, A = B = bf16 (K-major), D = f32, M = 128, N = 256
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// per-thread sorted list, element j at [j * EPI_THREADS] (bank-conflict free in smem,
+// coalesced in global scratch)
+struct ThreadTopK {
+    float *keys;
+    uint32_t *ids;
+    int k, n;
+    float thr_key;
+    uint32_t thr_id;
+};
+
+__device__ __noinline__ void list_insert(ThreadTopK &t, float key, uint32_t id) {
+    if (!better(key, id, t.thr_key, t.thr_id)) return;
+    int j = t.n < t.k ? t.n : t.k - 1;
+    while (j > 0) {
+        const float pk = t.keys[(j - 1) * EPI_THREADS];
+        const uint32_t pi = t.ids[(j - 1) * EPI_THREADS];
+        if (!better(key, id, pk, pi)) break;
+        t.keys[j * EPI_THREADS] = pk;
+        t.ids[j * EPI_THREADS] = pi;
+        j--;
+    }
+    t.keys[j * EPI_THREADS] = key;
+    t.ids[j * EPI_THREADS] = id;
+    if (t.n < t.k) t.n++;
+    if (t.n == t.k) {
+        t.thr_key = t.keys[(t.k - 1) * EPI_THREADS];
+        t.thr_id = t.ids[(t.k - 1) * EPI_THREADS];
+    }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
+                 const GemmTopkParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char *sA = smem + OFF_A;
+    unsigned char *sB = smem + OFF_B;
+    float *side_scale = reinterpret_cast<float *>(smem + OFF_SIDE);
+    float *side_bias = side_scale + BN;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tmem_full_bar = empty_bar + STAGES;
+    uint64_t *tmem_empty_bar = tmem_full_bar + ACC_STAGES;
+    uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // tile schedule: this CTA owns query tile qt and corpus tiles worker, worker + W, ...
+    const int qt = blockIdx.x % p.q_tiles;
+    const int worker = blockIdx.x / p.q_tiles;
+    const int W = (gridDim.x - qt + p.q_tiles - 1) / p.q_tiles;
+    const int64_t n_tiles = (p.n + BN - 1) / BN;
+    const int kb_count = p.d_pad / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_c)) : "memory");
+        for (int i = 0; i < STAGES; i++) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < ACC_STAGES; i++) {
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], EPI_THREADS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                     "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t t = worker; t < n_tiles; t += W) {
+                for (int kb = 0; kb < kb_count; kb++) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    tma_load_2d(&map_q, &full_bar[stage], sA + stage * A_BYTES, kb * BK, qt * BM);
+                    tma_load_2d(&map_c, &full_bar[stage], sB + stage * B_BYTES, kb * BK, (int)(t * BN));
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc();
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int64_t t = worker; t < n_tiles; t += W) {
+                mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < kb_count; kb++) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
+                    const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; k++) {
+                        const uint64_t adesc = make_smem_desc(a_addr + k * UMMA_K * 2);
+                        const uint64_t bdesc = make_smem_desc(b_addr + k * UMMA_K * 2);
+                        umma(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tmem_full_bar[as]);  // accumulator ready for the epilogue
+                if (++as == ACC_STAGES) {
+                    as = 0;
+                    aphase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: fused top-k =====================
+        const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
+        const int row = quarter * 32 + lane;          // query row inside the tile
+        const int et = threadIdx.x - 64;              // 0..127 among epilogue threads
+        const bool use_side = p.row_scale || p.row_bias || p.alive || p.scale_const != -1.f;
+        ThreadTopK list;
+        list.k = p.k;
+        list.n = 0;
+        list.thr_key = FLT_MAX;
+        list.thr_id = 0;
+        if (p.k <= kGemmSmemK) {
+            list.keys = reinterpret_cast<float *>(smem + OFF_LIST) + row;
+            list.ids = reinterpret_cast<uint32_t *>(smem + OFF_LIST + (size_t)p.k * EPI_THREADS * 4) + row;
+        } else {
+            list.keys = p.list_keys_gmem + (size_t)blockIdx.x * p.k * EPI_THREADS + row;
+            list.ids = p.list_ids_gmem + (size_t)blockIdx.x * p.k * EPI_THREADS + row;
+        }
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int64_t t = worker; t < n_tiles; t += W) {
+            const int64_t n0 = t * BN;
+            if (use_side) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers done
+                for (int c = et; c < BN; c += EPI_THREADS) {
+                    const int64_t r = n0 + c;
+                    bool ok = r < p.n;
+                    if (ok && p.alive) ok = (p.alive[r >> 3] >> (r & 7)) & 1;
+                    side_scale[c] = ok ? (p.row_scale ? p.row_scale[r] : p.scale_const) : 0.f;
+                    side_bias[c] = ok ? (p.row_bias ? p.row_bias[r] : 0.f) : __int_as_float(0x7f800000);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            mbar_wait(&tmem_full_bar[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+            for (int chunk = 0; chunk < BN / 32; chunk++) {
+                float v[32];
+                __syncwarp();
+                tmem_ld32(taddr + chunk * 32, v);
+                const uint32_t id0 = (uint32_t)(n0 + chunk * 32);
+                if (use_side) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float key = fmaf(v[j], side_scale[chunk * 32 + j], side_bias[chunk * 32 + j]);
+                        if (key <= list.thr_key) list_insert(list, key, id0 + j);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float key = -v[j];
+                        if (key <= list.thr_key && (int64_t)(id0 + j) < p.n) list_insert(list, key, id0 + j);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty_bar[as]);
+            if (++as == ACC_STAGES) {
+                as = 0;
+                aphase ^= 1;
+            }
+        }
+        // publish this CTA's per-query partial list
+        float *ok = p.part_keys + ((size_t)blockIdx.x * BM + row) * p.k;
+        uint32_t *oi = p.part_ids + ((size_t)blockIdx.x * BM + row) * p.k;
+        for (int j = 0; j < p.k; j++) {
+            ok[j] = j < list.n ? list.keys[j * EPI_THREADS] : FLT_MAX;
+            oi[j] = j < list.n ? list.ids[j * EPI_THREADS] : kNoId;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+static bool encode_rows_map(CUtensorMap *map, const void *base, int64_t rows, int d_pad, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)d_pad * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace gemm
+
+int gemm_topk_grid(int q_tiles, int64_t n, int num_sms) {
+    const int64_t n_tiles = ceil_div(n, gemm::BN);
+    int64_t g = (int64_t)q_tiles * (n_tiles < 1 ? 1 : n_tiles);
+    if (g > num_sms) g = num_sms;
+    if (g < q_tiles) g = q_tiles;
+    return (int)g;
+}
+
+cudaError_t launch_gemm_topk(const GemmTopkParams &p, int grid, cudaStream_t s, const char **err_detail) {
+    *err_detail = nullptr;
+    CUtensorMap map_q, map_c;
+    if (!gemm::encode_rows_map(&map_q, p.queries_bf16, p.nq_pad, p.d_pad, gemm::BM) ||
+        !gemm::encode_rows_map(&map_c, p.corpus_bf16, p.n, p.d_pad, gemm::BN)) {
+        *err_detail = "cuTensorMapEncodeTiled failed";
+        return cudaErrorInvalidValue;
+    }
+    size_t smem = gemm::OFF_LIST + gemm::SMEM_ALIGN_SLACK;
+    if (p.k <= kGemmSmemK) smem += (size_t)p.k * gemm::EPI_THREADS * 8;
+    cudaError_t e = cudaFuncSetAttribute(gemm::gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    gemm::gemm_topk_kernel<<<grid, gemm::NUM_THREADS, smem, s>>>(map_q, map_c, p);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace b200

@@ -1,0 +1,82 @@
+// kernels.h -- parameter blocks and host launchers shared between the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+struct ScanParams {
+    const void *corpus;      // [n][row_bytes]
+    const float *queries;    // device fp32 [nq][d_pad] (cosine: pre-normalised)
+    const float *row_scale;  // cosine: -1/||row|| (-1 for rows with sum sq < FLT_EPSILON), else null (= -1)
+    const uint8_t *alive;    // LSB-first bitmap or null
+    float *part_keys;        // [nq][gridDim.x][k]
+    uint32_t *part_ids;
+    int64_t n, nq;
+    int64_t row_bytes;
+    int d_pad, k, group;
+    int l2, bf16;
+};
+
+struct BinaryScanParams {
+    const uint8_t *corpus;   // [n][nbytes]
+    const uint8_t *queries;  // [nq][nbytes]
+    const uint8_t *alive;
+    float *part_keys;
+    uint32_t *part_ids;
+    int64_t n, nq;
+    int nbytes, k, jaccard;
+};
+
+enum { kOutKey = 0, kOutNeg = 1, kOutOnePlus = 2, kOutAddQ = 3 };
+
+struct MergeParams {
+    const void *in_keys;     // float
+    const void *in_ids;      // uint32 (internal partials) or int64 (external lists)
+    int64_t list_stride, q_stride;
+    int n_lists, k_in, k;
+    int64_t nq;
+    int descending;          // external only
+    int out_mode;            // kOut*
+    int ip_min_quirk;        // part-scan IP: drop scores <= FLT_MIN
+    const float *q_add;      // kOutAddQ: ||q||^2 per query
+    int64_t id_offset;
+    float *out_dis;
+    int64_t *out_ids;
+};
+
+size_t scan_smem_bytes(int qt, int d_pad, int k);
+cudaError_t launch_flat_scan(const ScanParams &p, int qt, int blocks_x, cudaStream_t s);
+cudaError_t launch_binary_scan(const BinaryScanParams &p, int blocks_x, cudaStream_t s);
+cudaError_t launch_topk_merge(const MergeParams &p, bool external, cudaStream_t s);
+
+// ---- tcgen05 bf16 GEMM + fused top-k (ip_gemm_sm100.cu) ---------------------------
+struct GemmTopkParams {
+    const void *corpus_bf16;   // [n][d_pad] bf16, d_pad % 64 == 0
+    const void *queries_bf16;  // [nq_pad][d_pad] bf16, nq_pad % 128 == 0
+    const float *row_scale;    // per corpus row multiplier a[j] or null (= scale_const)
+    float scale_const;         // -1 for IP, -2 for L2
+    const float *row_bias;     // per corpus row addend b[j] or null (=0)
+    const uint8_t *alive;      // LSB-first bitmap or null
+    float *part_keys;          // [gridDim.x][128][k]
+    uint32_t *part_ids;
+    float *list_keys_gmem;     // scratch for k > kGemmSmemK: [gridDim.x][k][128]
+    uint32_t *list_ids_gmem;
+    int64_t n;
+    int nq_pad, d_pad, k;
+    int q_tiles;               // nq_pad / 128
+};
+constexpr int kGemmSmemK = 30;
+int gemm_topk_grid(int q_tiles, int64_t n, int num_sms);
+// returns cudaSuccess or an error; tensor maps are encoded inside
+cudaError_t launch_gemm_topk(const GemmTopkParams &p, int grid, cudaStream_t s, const char **err_detail);
+
+// ---- elementwise prep kernels (prep.cu) --------------------------------------------
+cudaError_t launch_f32_to_bf16_rows(const float *src, int d, void *dst, int d_pad, int64_t n, cudaStream_t s);
+cudaError_t launch_pad_rows_f32(const float *src, int d, float *dst, int d_pad, int64_t n, cudaStream_t s);
+// per-row sum of squares (fp32 accumulate) of a [n][d_pad] corpus; mode 0: out = ss, mode 1: out = -(ss<eps ? 1 : 1/sqrt(ss))
+cudaError_t launch_row_norms(const void *rows, int bf16, int d_pad, int64_t n, int mode, float *out, cudaStream_t s);
+// normalise fp32 query rows in place (cosine), skipping rows with ss < FLT_EPSILON
+cudaError_t launch_normalize_rows_f32(float *rows, int d_pad, int64_t n, cudaStream_t s);
+
+}  // namespace b200

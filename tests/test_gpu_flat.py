@@ -1,0 +1,222 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI
+of libb200search.so (ctypes) and is checked against the CPU oracle / the reference goldens."""
+import numpy as np
+import pytest
+
+import myscaledb_b200 as b2
+import oracle as orc
+from myscaledb_b200 import search as S
+from tests.util import check_topk, to_bf16_values
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+def _nnn(lo, hi, d=3):
+    return np.repeat(np.arange(lo, hi, dtype=np.float32)[:, None], d, axis=1)
+
+
+# ------------------------------------------------------------------ reference goldens
+def test_golden_00001_flat_index(goldens):
+    g = goldens["00001_flat_l2"]
+    c = b2.Corpus(b2.L2, 3).append(_nnn(0, 100))
+    dis, ids = c.search(np.array([g["query"]], F32), g["k"])
+    assert ids[0].tolist() == [e[0] for e in g["expect"]]
+    np.testing.assert_allclose(dis[0], [e[1] for e in g["expect"]], rtol=1e-6)
+
+
+def test_golden_00012_part_scan_with_empty_rows(goldens):
+    g = goldens["00012_bruteforce_l2"]
+    y = _nnn(0, 10030)
+    y[10:30] = np.finfo(np.float32).max
+    dis, ids = b2.part_scan(b2.L2, np.array([g["query"]], F32), y, g["k"], block_rows=128)
+    assert ids[0].tolist() == [e[0] for e in g["expect"]]
+    np.testing.assert_allclose(dis[0], [e[1] for e in g["expect"]], rtol=1e-5)
+
+
+@pytest.mark.parametrize("name,metric", [("00002_batch_l2", b2.L2), ("00002_batch_ip", b2.IP)])
+def test_golden_00002_batch(goldens, name, metric):
+    g = goldens[name]
+    q = np.array(g["queries"], F32)
+    y = _nnn(0, 100)
+    dis, ids = b2.part_scan(metric, q, y, g["k"])
+    got = [[int(ids[qi, j]), qi, float(dis[qi, j])] for qi in range(3) for j in range(g["k"])]
+    exp = g["expect"]
+    assert [r[:2] for r in got] == [e[:2] for e in exp]
+    np.testing.assert_allclose([r[2] for r in got], [e[2] for e in exp], rtol=2e-6)
+
+
+def test_golden_00014_cosine(goldens):
+    g = goldens["00014_cosine_bruteforce"]
+    n = np.arange(1000, dtype=np.float32)
+    y = np.stack([n, n + 3, n + 1], axis=1)
+    dis, ids = b2.part_scan(b2.COSINE, np.array([g["query"]], F32), y, g["k"])
+    assert ids[0].tolist() == [e[0] for e in g["expect"]]
+    np.testing.assert_allclose(dis[0], [e[1] for e in g["expect"]], rtol=0, atol=2e-7)
+
+
+@pytest.mark.parametrize("metric,prefix", [(b2.HAMMING, "hamming"), (b2.JACCARD, "jaccard")])
+def test_golden_00038_binary(goldens, metric, prefix):
+    g = goldens["00038_binary"]
+    y = np.repeat((np.arange(1024) % 256).astype(np.uint8)[:, None], 4, axis=1)
+    q = np.array([g["query"]], np.uint8)
+    dis, ids = b2.part_scan(metric, q, y, 20)
+    exp = g[prefix + "_brute"]
+    assert ids[0].tolist() == [e[0] for e in exp]
+    assert dis[0].tolist() == [float(F32(e[1])) for e in exp]
+    mask = np.zeros(1024, bool); mask[101:120] = True
+    dis, ids = b2.part_scan(metric, q, y, 20, filter_bits=orc.pack_bits(mask))
+    exp = g[prefix + "_filter"]
+    assert ids[0][:len(exp)].tolist() == [e[0] for e in exp] and (ids[0][len(exp):] == -1).all()
+    bq = np.array(g["batch_queries"], np.uint8)
+    dis, ids = b2.part_scan(metric, bq, y, 10)
+    got = [[int(ids[qi, j]), qi, float(dis[qi, j])] for qi in range(3) for j in range(10)]
+    assert got == [[e[0], e[1], float(F32(e[2]))] for e in g[prefix + "_batch"]]
+    row_exists = np.ones(1024, np.uint8); row_exists[:200] = 0
+    if metric == b2.HAMMING:
+        dis, ids = b2.part_scan(metric, q, y, 10, row_exists=row_exists)
+        assert [[int(i), float(d)] for i, d in zip(ids[0], dis[0])] == g["hamming_after_lwd_lt200"]
+
+
+def test_golden_00028_768d_and_00035_ties(goldens):
+    g = goldens["00028_mstg_768"]
+    n = np.arange(1000, dtype=np.float64)[:, None]; x = np.arange(768, dtype=np.float64)[None, :]
+    y = (0.00001 * (n * 768 + x + 1) * np.where(x % 2 == 0, -1.0, 1.0)).astype(np.float32)
+    q = np.array([g["query"]], F32)
+    dis, ids = b2.flat_knn(b2.L2, q, y, 5)
+    assert ids[0].tolist() == [e[0] for e in g["expect_l2"]]
+    np.testing.assert_allclose(dis[0], [e[1] for e in g["expect_l2"]], rtol=1e-4)
+    dis, ids = b2.flat_knn(b2.COSINE, q, y, 5)
+    assert ids[0].tolist() == [e[0] for e in g["expect_cosine"]]
+    np.testing.assert_allclose(dis[0], [e[1] for e in g["expect_cosine"]], rtol=1e-4)
+    alive = np.ones(1000, bool); alive[0] = False; alive[2] = False
+    dis, ids = b2.flat_knn(b2.COSINE, q, y, 5, alive_bits=orc.pack_bits(alive))
+    assert ids[0].tolist() == [e[0] for e in g["expect_cosine_after_delete_id2"]]
+    t = goldens["00035_ties"]
+    idv = np.array([n for n in range(1001) if n != 1])
+    yy = np.repeat(idv.astype(np.float32)[:, None], 16, axis=1)
+    dis, ids = b2.part_scan(b2.L2, np.array([t["query"]], F32), yy, 10)
+    assert [[int(idv[i]), float(d)] for i, d in zip(ids[0], dis[0])] == t["expect_unfiltered"]
+    dis, ids = b2.part_scan(b2.L2, np.array([t["query"]], F32), yy, 10, filter_bits=orc.pack_bits(idv < 11))
+    assert [[int(idv[i]), float(d)] for i, d in zip(ids[0], dis[0])] == t["expect_filtered"]
+
+
+# ------------------------------------------------------------------ scan kernel vs oracle
+@pytest.mark.parametrize("metric", [b2.L2, b2.IP, b2.COSINE])
+@pytest.mark.parametrize("n,d,nq,k", [(10000, 128, 1, 10), (5003, 17, 3, 7), (20011, 768, 8, 30), (3001, 96, 13, 100),
+                                      (77, 5, 2, 100), (1, 8, 1, 3)])
+def test_scan_matches_oracle(metric, n, d, nq, k):
+    rng = np.random.default_rng(n + d + nq)
+    y = rng.standard_normal((n, d)).astype(F32)
+    x = rng.standard_normal((nq, d)).astype(F32)
+    dg, ig = b2.flat_knn(metric, x, y, k)
+    do, io = orc.search_without_index(metric, x, y, k)
+    check_topk(metric, x, y, dg, ig, do, io)
+
+
+def test_scan_alive_bitmap_and_ip_min_quirk():
+    rng = np.random.default_rng(5)
+    y = rng.standard_normal((9000, 64)).astype(F32)
+    x = rng.standard_normal((4, 64)).astype(F32)
+    alive = rng.random(9000) < 0.3
+    dg, ig = b2.flat_knn(b2.L2, x, y, 20, alive_bits=orc.pack_bits(alive))
+    do, io = orc.search_without_index(orc.L2, x, y, 20, alive=orc.pack_bits(alive))
+    check_topk(b2.L2, x, y, dg, ig, do, io)
+    assert alive[ig].all()
+    # vectorScanWithoutIndex IP quirk: scores <= FLT_MIN are never returned
+    yneg = -np.abs(y); xpos = np.abs(x)
+    dg, ig = b2.part_scan(b2.IP, xpos, yneg, 5)
+    do, io = orc.part_scan(orc.IP, xpos, yneg, 5)
+    assert (ig == -1).all() and (io == -1).all()
+    row_exists = (rng.random(9000) < 0.9).astype(np.uint8)
+    dg, ig = b2.part_scan(b2.IP, x, y, 10, row_exists=row_exists)
+    do, io = orc.part_scan(orc.IP, x, y, 10, block_rows=1024, row_exists=row_exists)
+    check_topk(b2.IP, x, y, dg, ig, do, io)
+
+
+def test_scan_bf16_corpus():
+    rng = np.random.default_rng(11)
+    y = to_bf16_values(rng.standard_normal((30000, 768)).astype(F32))
+    x = rng.standard_normal((5, 768)).astype(F32)
+    for metric in (b2.L2, b2.IP, b2.COSINE):
+        c = b2.Corpus(metric, 768, dtype=S.BF16).append(y)
+        c.set_path(1)
+        dg, ig = c.search(x, 10)
+        do, io = orc.search_without_index(metric, x, y, 10)
+        check_topk(metric, x, y, dg, ig, do, io)
+        c.close()
+
+
+# ------------------------------------------------------------------ tcgen05 GEMM path vs oracle
+@pytest.mark.parametrize("metric", [b2.IP, b2.L2, b2.COSINE])
+@pytest.mark.parametrize("n,d,nq,k", [(20000, 768, 128, 10), (5000, 64, 37, 30), (70001, 128, 300, 10), (1000, 96, 20, 50)])
+def test_gemm_path_matches_oracle(metric, n, d, nq, k):
+    rng = np.random.default_rng(n + d + nq + metric)
+    y = to_bf16_values(rng.standard_normal((n, d)).astype(F32))
+    x = to_bf16_values(rng.standard_normal((nq, d)).astype(F32))
+    c = b2.Corpus(metric, d, dtype=S.BF16).append(y)
+    c.set_path(2)
+    dg, ig = c.search(x, k)
+    c.close()
+    do, io = orc.knn_flat_parts(orc.IP if metric != orc.L2 else orc.L2, *( _prep_cos(x, y) if metric == b2.COSINE else (x, y)), k, 4)
+    if metric == b2.COSINE:
+        do = 1 - do
+    # fp32 tensor-core accumulation order differs from the CPU: near ties may swap
+    check_topk(metric, x, y, dg, ig, do, io, rtol=2e-4, atol=2e-4 if metric == b2.L2 else 2e-5, min_exact=0.99)
+
+
+def _prep_cos(x, y):
+    x = x.copy(); y = y.copy()
+    orc.lib().orc_normalize(x.ctypes.data_as(orc.C.POINTER(orc.C.c_float)), orc.C.c_int64(x.shape[0]), orc.C.c_int(x.shape[1]))
+    orc.lib().orc_normalize(y.ctypes.data_as(orc.C.POINTER(orc.C.c_float)), orc.C.c_int64(y.shape[0]), orc.C.c_int(y.shape[1]))
+    return x, y
+
+
+def test_gemm_path_alive_bitmap():
+    rng = np.random.default_rng(21)
+    y = to_bf16_values(rng.standard_normal((40000, 256)).astype(F32))
+    x = to_bf16_values(rng.standard_normal((64, 256)).astype(F32))
+    alive = rng.random(40000) < 0.5
+    c = b2.Corpus(b2.IP, 256, dtype=S.BF16).append(y)
+    c.set_path(2)
+    dg, ig = c.search(x, 10, alive_bits=orc.pack_bits(alive))
+    c.close()
+    do, io = orc.knn_flat(orc.IP, x, y, 10, alive=orc.pack_bits(alive))
+    check_topk(b2.IP, x, y, dg, ig, do, io, rtol=2e-4, atol=2e-5, min_exact=0.99)
+    assert alive[ig].all()
+
+
+def test_gemm_equals_scan_large_property():
+    """Size-independent property at a size the oracle cannot reach quickly: the two
+    independent GPU paths (fp32 FMA scan vs tcgen05 GEMM) must return the same ids."""
+    rng = np.random.default_rng(33)
+    y = to_bf16_values(rng.standard_normal((400000, 768)).astype(F32))
+    x = to_bf16_values(rng.standard_normal((256, 768)).astype(F32))
+    c = b2.Corpus(b2.IP, 768, dtype=S.BF16).append(y)
+    c.set_path(2); d2, i2 = c.search(x, 10)
+    c.set_path(1); d1, i1 = c.search(x, 10)
+    c.close()
+    check_topk(b2.IP, x, y, d2, i2, d1, i1, rtol=2e-4, atol=2e-5, min_exact=0.99)
+    assert (np.diff(d2, axis=1) <= 0).all()  # sorted best-first
+
+
+def test_topk_merge_device_matches_oracle_merge():
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(3)
+    L, nq, k = 8, 33, 10
+    dis = np.sort(rng.standard_normal((L, nq, k)).astype(F32), axis=2)
+    ids = rng.permutation(L * nq * k).reshape(L, nq, k).astype(np.int64)
+    ids[3, 5, 7:] = -1
+    for desc in (False, True):
+        d_in = dis[:, :, ::-1].copy() if desc else dis
+        td, ti = torch.tensor(d_in).cuda(), torch.tensor(ids).cuda()
+        od = torch.empty((nq, k), dtype=torch.float32, device="cuda"); oi = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        b2.topk_merge_device(td.data_ptr(), ti.data_ptr(), L, nq, k, desc, od.data_ptr(), oi.data_ptr())
+        torch.cuda.synchronize()
+        for q in range(nq):
+            m = ids[:, q, :].reshape(-1) >= 0
+            sc = d_in[:, q, :].reshape(-1)[m]; lab = ids[:, q, :].reshape(-1)[m]
+            order = np.lexsort((lab, -sc if desc else sc))[:k]
+            assert oi[q].cpu().numpy().tolist() == lab[order].tolist()
+            np.testing.assert_array_equal(od[q].cpu().numpy(), sc[order])
