@@ -393,10 +393,12 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
     B200_TRY(c->w_q32.reserve((size_t)nq * c->d_pad * 4));
     float *q32 = c->w_q32.as<float>();
     B200_CUDA_OK(launch_pad_rows_f32(reinterpret_cast<const float *>(d_queries), c->d, q32, c->d_pad, nq, s));
-    if (c->metric == B200_METRIC_COSINE) B200_CUDA_OK(launch_normalize_rows_f32(q32, c->d_pad, nq, s));
-
     int path = c->path;
     if (path == 0) path = (c->dtype == B200_DTYPE_BF16 && nq >= 16) ? 2 : 1;
+    // scan path: queries normalised in fp32 like the reference.  GEMM path: the bf16 operand
+    // keeps the caller's values (normalising first would add a bf16 rounding of the unit
+    // vector); the positive per-query factor 1/||q|| is applied when the result is emitted.
+    if (c->metric == B200_METRIC_COSINE && path == 1) B200_CUDA_OK(launch_normalize_rows_f32(q32, c->d_pad, nq, s));
     if (path == 2 && c->dtype != B200_DTYPE_BF16)
         return fail(B200_ERR_UNSUPPORTED, "the tcgen05 GEMM path needs a bf16 corpus");
 
@@ -467,9 +469,11 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
         B200_CUDA_OK(cudaMemsetAsync(c->w_qbf.p, 0, (size_t)nq_pad * c->d_pad * 2, s));
         B200_CUDA_OK(launch_f32_to_bf16_rows(q32 + qb * c->d_pad, c->d_pad, c->w_qbf.p, c->d_pad, nq_c, s));
         const float *q_add = nullptr;
-        if (c->metric == B200_METRIC_L2) {
+        if (c->metric == B200_METRIC_L2 || c->metric == B200_METRIC_COSINE) {
+            // L2: ||q||^2 of the bf16-rounded query; cosine: -(1/||q||) (mode 1 stores the negative)
             B200_TRY(c->w_qnorm.reserve((size_t)nq_pad * 4));
-            B200_CUDA_OK(launch_row_norms(c->w_qbf.p, 1, c->d_pad, nq_c, 0, c->w_qnorm.as<float>(), s));
+            B200_CUDA_OK(launch_row_norms(c->w_qbf.p, 1, c->d_pad, nq_c, c->metric == B200_METRIC_L2 ? 0 : 1,
+                                          c->w_qnorm.as<float>(), s));
             q_add = c->w_qnorm.as<float>();
         }
         int grid = gemm_topk_grid(q_tiles, c->n, sms);
@@ -513,7 +517,7 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
         mp.k_in = k;
         mp.k = k;
         mp.nq = nq_c;
-        mp.out_mode = c->metric == B200_METRIC_L2 ? kOutAddQ : c->metric == B200_METRIC_IP ? kOutNeg : kOutOnePlus;
+        mp.out_mode = c->metric == B200_METRIC_L2 ? kOutAddQ : c->metric == B200_METRIC_IP ? kOutNeg : kOutCosQ;
         mp.q_add = q_add;
         mp.ip_min_quirk = ip_min_quirk && c->metric == B200_METRIC_IP;
         mp.id_offset = id_offset;

@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(kScanThreads) topk_merge_kernel(const MergePar
                     case kOutKey: dis = key; break;
                     case kOutNeg: dis = -key; break;
                     case kOutOnePlus: dis = 1.f + key; break;
+                    case kOutCosQ: dis = 1.f - key * p.q_add[q]; break;  // key = -ip/||y||, q_add = -1/||q||
                     default: dis = fmaxf(key + p.q_add[q], 0.f); break;  // kOutAddQ
                 }
                 if (p.ip_min_quirk && !(dis > FLT_MIN)) {

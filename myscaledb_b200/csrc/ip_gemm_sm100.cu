@@ -119,21 +119,20 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+          "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]),
+          "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]),
+          "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+        : "r"(taddr)
+        : "memory");
 }
+// all tcgen05.ld issued by this thread have landed in their registers
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // per-thread sorted list, element j at [j * EPI_THREADS] (bank-conflict free in smem,
 // coalesced in global scratch)
@@ -162,6 +161,37 @@ __device__ __noinline__ void list_insert(ThreadTopK &t, float key, uint32_t id) 
     if (t.n == t.k) {
         t.thr_key = t.keys[(t.k - 1) * EPI_THREADS];
         t.thr_id = t.ids[(t.k - 1) * EPI_THREADS];
+    }
+}
+
+// Filter one chunk of 32 accumulator columns of this thread's query row.
+__device__ __forceinline__ void epilogue_chunk(ThreadTopK &list, float (&v)[32], bool use_side, const float *scale,
+                                               const float *bias, uint32_t id0, bool tail, int64_t n) {
+    float thr = list.thr_key;
+    if (use_side) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = fmaf(v[j], scale[j], bias[j]);  // broadcast LDS
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = -v[j];
+    }
+    float m0 = fminf(v[0], v[1]), m1 = fminf(v[2], v[3]), m2 = fminf(v[4], v[5]), m3 = fminf(v[6], v[7]);
+#pragma unroll
+    for (int j = 8; j < 32; j += 8) {
+        m0 = fminf(m0, fminf(v[j], v[j + 1]));
+        m1 = fminf(m1, fminf(v[j + 2], v[j + 3]));
+        m2 = fminf(m2, fminf(v[j + 4], v[j + 5]));
+        m3 = fminf(m3, fminf(v[j + 6], v[j + 7]));
+    }
+    const float best = fminf(fminf(m0, m1), fminf(m2, m3));
+    if (best <= thr) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            if (v[j] <= thr && (use_side || !tail || (int64_t)(id0 + j) < n)) {
+                list_insert(list, v[j], id0 + j);
+                thr = list.thr_key;
+            }
+        }
     }
 }
 
@@ -301,25 +331,26 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             mbar_wait(&tmem_full_bar[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
+            // Chunks of 32 columns; the TMEM load of chunk c+1 is in flight while chunk c is
+            // filtered.  A chunk is first reduced to its best key (31 FMNMX); the per-element
+            // test only runs for the rare chunk that can beat the current k-th key.
+            const bool tail = n0 + BN > p.n;
+            float va[32], vb[32];
+            __syncwarp();
+            tmem_ld32_issue(taddr, va);
+            tmem_ld_wait();
 #pragma unroll 1
-            for (int chunk = 0; chunk < BN / 32; chunk++) {
-                float v[32];
+            for (int chunk = 0; chunk < BN / 32; chunk += 2) {
                 __syncwarp();
-                tmem_ld32(taddr + chunk * 32, v);
-                const uint32_t id0 = (uint32_t)(n0 + chunk * 32);
-                if (use_side) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float key = fmaf(v[j], side_scale[chunk * 32 + j], side_bias[chunk * 32 + j]);
-                        if (key <= list.thr_key) list_insert(list, key, id0 + j);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float key = -v[j];
-                        if (key <= list.thr_key && (int64_t)(id0 + j) < p.n) list_insert(list, key, id0 + j);
-                    }
-                }
+                tmem_ld32_issue(taddr + (chunk + 1) * 32, vb);
+                epilogue_chunk(list, va, use_side, side_scale + chunk * 32, side_bias + chunk * 32,
+                               (uint32_t)(n0 + chunk * 32), tail, p.n);
+                tmem_ld_wait();
+                __syncwarp();
+                if (chunk + 2 < BN / 32) tmem_ld32_issue(taddr + (chunk + 2) * 32, va);
+                epilogue_chunk(list, vb, use_side, side_scale + (chunk + 1) * 32, side_bias + (chunk + 1) * 32,
+                               (uint32_t)(n0 + (chunk + 1) * 32), tail, p.n);
+                tmem_ld_wait();
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty_bar[as]);

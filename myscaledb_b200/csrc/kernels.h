@@ -28,7 +28,7 @@ struct BinaryScanParams {
     int nbytes, k, jaccard;
 };
 
-enum { kOutKey = 0, kOutNeg = 1, kOutOnePlus = 2, kOutAddQ = 3 };
+enum { kOutKey = 0, kOutNeg = 1, kOutOnePlus = 2, kOutAddQ = 3, kOutCosQ = 4 };
 
 struct MergeParams {
     const void *in_keys;     // float
@@ -39,7 +39,7 @@ struct MergeParams {
     int descending;          // external only
     int out_mode;            // kOut*
     int ip_min_quirk;        // part-scan IP: drop scores <= FLT_MIN
-    const float *q_add;      // kOutAddQ: ||q||^2 per query
+    const float *q_add;      // kOutAddQ: ||q||^2 per query; kOutCosQ: -(1/||q||) per query
     int64_t id_offset;
     float *out_dis;
     int64_t *out_ids;
