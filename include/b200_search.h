@@ -110,7 +110,8 @@ int b200_corpus_search(b200_corpus *c, const float *queries, int64_t nq, int k, 
 int b200_corpus_search_device(b200_corpus *c, const float *d_queries, int64_t nq, int k,
                               const uint8_t *d_alive_bits /*nullable*/, int64_t id_offset, float *d_out_dis,
                               int64_t *d_out_ids, void *stream);
-/* Force a search path: 0 = auto, 1 = memory-bound scan kernel, 2 = tcgen05 bf16 GEMM. */
+/* Force a search path: 0 = auto, 1 = memory-bound scan kernel, 2 = tcgen05 bf16 GEMM
+ * (CTA pairs when there are >= 2 query tiles), 3 = tcgen05 GEMM restricted to single-CTA MMAs. */
 int b200_corpus_set_path(b200_corpus *c, int path);
 /* CUDA-event timing of the dominant kernel (scan or GEMM) of every search on this corpus,
  * recorded on the launching stream; used by bench.py for the roofline report. */

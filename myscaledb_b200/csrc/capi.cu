@@ -97,6 +97,7 @@ struct b200_corpus {
     float *row_bias = nullptr;   // L2: ||y||^2 (GEMM path)
     int device = 0;
     int path = 0;
+    int gemm_cta_group = 0;  // 0 auto, 1 force single-CTA MMA (A/B experiments)
     int sms = 148;
     cudaStream_t stream = nullptr;
     std::mutex mu;
@@ -290,8 +291,9 @@ extern "C" int b200_corpus_size(const b200_corpus *c, int64_t *out_rows) {
 }
 
 extern "C" int b200_corpus_set_path(b200_corpus *c, int path) {
-    if (!c || path < 0 || path > 2) return fail(B200_ERR_INVALID, "path must be 0, 1 or 2");
-    c->path = path;
+    if (!c || path < 0 || path > 3) return fail(B200_ERR_INVALID, "path must be 0, 1, 2 or 3");
+    c->path = path == 3 ? 2 : path;
+    c->gemm_cta_group = path == 3 ? 1 : 0;
     return B200_OK;
 }
 
@@ -463,7 +465,9 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
     const int64_t QCHUNK = 1024;
     for (int64_t qb = 0; qb < nq; qb += QCHUNK) {
         const int64_t nq_c = std::min(QCHUNK, nq - qb);
-        const int nq_pad = (int)round_up(nq_c, 128);
+        // >= 2 query tiles: CTA pairs (tcgen05 cta_group::2), query tiles padded to an even count
+        const int cta_group = (nq_c > 128 && c->gemm_cta_group != 1) ? 2 : 1;
+        const int nq_pad = (int)round_up(nq_c, 128 * cta_group);
         const int q_tiles = nq_pad / 128;
         B200_TRY(c->w_qbf.reserve((size_t)nq_pad * c->d_pad * 2));
         B200_CUDA_OK(cudaMemsetAsync(c->w_qbf.p, 0, (size_t)nq_pad * c->d_pad * 2, s));
@@ -501,6 +505,7 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
         gp.d_pad = c->d_pad;
         gp.k = k;
         gp.q_tiles = q_tiles;
+        gp.cta_group = cta_group;
         const char *detail = nullptr;
         std::pair<cudaEvent_t, cudaEvent_t> ev;
         timing_begin(c, s, ev);

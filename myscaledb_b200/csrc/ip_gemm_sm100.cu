@@ -14,7 +14,14 @@
 //   warps 2..5  : epilogue; thread t owns TMEM lane t = one query, streams the 256 scores of
 //                 the tile through a register threshold test and keeps a private sorted
 //                 top-k in shared memory (k <= 30) or global scratch (larger k)
-// Pipelines: 4-stage smem ring (full/empty mbarriers), 2-stage TMEM accumulator ring.
+// Pipelines: smem ring (full/empty mbarriers, 4 stages of 48 KB), 2-stage TMEM accumulator ring.
+// CG = 2 variant (used whenever there are >= 2 query tiles): a CTA PAIR (cluster of 2,
+// tcgen05.mma cta_group::2) computes D[256 queries x 256 rows]; each CTA stages its own 128
+// queries and HALF of the corpus tile (6 stages of 32 KB), which takes the operand traffic
+// through shared memory from 192 B/clk (the measured 67 % tensor-pipe ceiling of the 1-CTA
+// form, profiles/r01_gemm_topk_cg1.md) to 128 B/clk per SM and the L2->SM traffic from 48 KB
+// to 32 KB per k-block.  The leader CTA issues the MMAs; both CTAs run a TMA producer and the
+// top-k epilogue for their own 128 TMEM lanes.
 // Each CTA owns ONE query tile for its whole life (blockIdx % q_tiles) and walks the corpus
 // tiles worker, worker+W, ...; thresholds therefore live in registers for the whole kernel.
 // The key that is ranked is  acc * row_scale[j] + row_bias[j]  (smaller = better):
@@ -33,22 +40,29 @@ namespace gemm {
 constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
 constexpr int ACC_STAGES = 2;
 constexpr int UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;           // 16 KB
-constexpr int B_BYTES = BN * BK * 2;           // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES; // 48 KB
 constexpr int NUM_THREADS = 192;
 constexpr int EPI_THREADS = 128;
 constexpr int TMEM_COLS = 512;
-
-constexpr int OFF_A = 0;
-constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
-constexpr int OFF_SIDE = OFF_B + STAGES * B_BYTES;   // scale[256], bias[256]
-constexpr int OFF_BAR = OFF_SIDE + 2 * BN * 4;
-constexpr int OFF_LIST = OFF_BAR + 128;
 constexpr int SMEM_ALIGN_SLACK = 1024;
+constexpr int MAX_STAGES = 6;
+
+// CG = CTAs per MMA (cta_group): 1 or 2
+template <int CG>
+struct Cfg {
+    static constexpr int B_ROWS = BN / CG;                 // corpus rows staged by one CTA
+    static constexpr int B_BYTES = B_ROWS * BK * 2;        // 32 KB / 16 KB
+    static constexpr int STAGES = CG == 1 ? 4 : 6;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // per CTA
+    static constexpr int TX_BYTES = STAGE_BYTES * CG;      // what the (leader's) full barrier expects
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
+    static constexpr int OFF_SIDE = OFF_B + STAGES * B_BYTES;  // scale[256], bias[256]
+    static constexpr int OFF_BAR = OFF_SIDE + 2 * BN * 4;
+    static constexpr int OFF_LIST = OFF_BAR + 256;
+};
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -86,6 +100,32 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *ba
         : "memory");
 }
 
+// 2-CTA form: dst in this CTA, completion signalled on the LEADER CTA's mbarrier (the shared
+// window address carries the CTA rank in bit 24; clearing it names the even CTA of the pair).
+__device__ __forceinline__ void tma_load_2d_cg2(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
 // K-major, 128-byte swizzled operand tile: rows of 64 bf16 (128 B), 8-row atoms of 1024 B.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -97,9 +137,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     return d;
 }
 
-// kind::f16, A = B = bf16 (K-major), D = f32, M = 128, N = 256
-__device__ __forceinline__ constexpr uint32_t make_idesc() {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::f16, A = B = bf16 (K-major), D = f32, M = 128 * CG, N = 256
+__device__ __forceinline__ constexpr uint32_t make_idesc(int cg) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * cg) >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
@@ -115,6 +155,25 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
+}
+__device__ __forceinline__ void umma_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// arrive (once all prior MMAs retire) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_cg2(uint64_t *bar) {
+    const uint16_t mask = 3;
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(mask)
+        : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -195,27 +254,33 @@ __device__ __forceinline__ void epilogue_chunk(ThreadTopK &list, float (&v)[32],
     }
 }
 
+template <int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
                  const GemmTopkParams p) {
+    using C = Cfg<CG>;
+    constexpr int STAGES = C::STAGES;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    unsigned char *sA = smem + OFF_A;
-    unsigned char *sB = smem + OFF_B;
-    float *side_scale = reinterpret_cast<float *>(smem + OFF_SIDE);
+    unsigned char *sA = smem + C::OFF_A;
+    unsigned char *sB = smem + C::OFF_B;
+    float *side_scale = reinterpret_cast<float *>(smem + C::OFF_SIDE);
     float *side_bias = side_scale + BN;
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
-    uint64_t *empty_bar = full_bar + STAGES;
-    uint64_t *tmem_full_bar = empty_bar + STAGES;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
+    uint64_t *empty_bar = full_bar + MAX_STAGES;
+    uint64_t *tmem_full_bar = empty_bar + MAX_STAGES;
     uint64_t *tmem_empty_bar = tmem_full_bar + ACC_STAGES;
     uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + ACC_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;
+    const bool is_leader = cta_rank == 0;
 
-    // tile schedule: this CTA owns query tile qt and corpus tiles worker, worker + W, ...
+    // tile schedule: a CTA (CG=1) or CTA pair (CG=2) owns CG query tiles for its whole life and
+    // walks the corpus tiles worker, worker + W, ...  (blockIdx = worker * q_tiles + qt)
     const int qt = blockIdx.x % p.q_tiles;
     const int worker = blockIdx.x / p.q_tiles;
-    const int W = (gridDim.x - qt + p.q_tiles - 1) / p.q_tiles;
+    const int W = gridDim.x / p.q_tiles;  // the host launches a multiple of q_tiles CTAs
     const int64_t n_tiles = (p.n + BN - 1) / BN;
     const int kb_count = p.d_pad / BK;
 
@@ -228,32 +293,46 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         }
         for (int i = 0; i < ACC_STAGES; i++) {
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], EPI_THREADS);
+            mbar_init(&tmem_empty_bar[i], EPI_THREADS * CG);  // leader's: both CTAs' epilogue threads
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
-                     "n"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                         "n"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                         "n"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (both CTAs of a pair) =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             for (int64_t t = worker; t < n_tiles; t += W) {
                 for (int kb = 0; kb < kb_count; kb++) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-                    tma_load_2d(&map_q, &full_bar[stage], sA + stage * A_BYTES, kb * BK, qt * BM);
-                    tma_load_2d(&map_c, &full_bar[stage], sB + stage * B_BYTES, kb * BK, (int)(t * BN));
+                    if (CG == 1) {
+                        mbar_arrive_expect_tx(&full_bar[stage], C::TX_BYTES);
+                        tma_load_2d(&map_q, &full_bar[stage], sA + stage * A_BYTES, kb * BK, qt * BM);
+                        tma_load_2d(&map_c, &full_bar[stage], sB + stage * C::B_BYTES, kb * BK, (int)(t * BN));
+                    } else {
+                        if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], C::TX_BYTES);
+                        tma_load_2d_cg2(&map_q, &full_bar[stage], sA + stage * A_BYTES, kb * BK, qt * BM);
+                        tma_load_2d_cg2(&map_c, &full_bar[stage], sB + stage * C::B_BYTES, kb * BK,
+                                        (int)(t * BN + cta_rank * C::B_ROWS));
+                    }
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -262,9 +341,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc();
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (lane == 0 && is_leader) {
+            constexpr uint32_t idesc = make_idesc(CG);
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0;
             for (int64_t t = worker; t < n_tiles; t += W) {
@@ -275,20 +354,23 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
-                    const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
+                    const uint32_t b_addr = smem_u32(sB + stage * C::B_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; k++) {
                         const uint64_t adesc = make_smem_desc(a_addr + k * UMMA_K * 2);
                         const uint64_t bdesc = make_smem_desc(b_addr + k * UMMA_K * 2);
-                        umma(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (CG == 1) umma(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else umma_cg2(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
+                    // smem slot free (in both CTAs) once these MMAs retire
+                    if (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_cg2(&empty_bar[stage]);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit(&tmem_full_bar[as]);  // accumulator ready for the epilogue
+                // accumulator ready for the epilogue (of both CTAs)
+                if (CG == 1) umma_commit(&tmem_full_bar[as]); else umma_commit_cg2(&tmem_full_bar[as]);
                 if (++as == ACC_STAGES) {
                     as = 0;
                     aphase ^= 1;
@@ -307,8 +389,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         list.thr_key = FLT_MAX;
         list.thr_id = 0;
         if (p.k <= kGemmSmemK) {
-            list.keys = reinterpret_cast<float *>(smem + OFF_LIST) + row;
-            list.ids = reinterpret_cast<uint32_t *>(smem + OFF_LIST + (size_t)p.k * EPI_THREADS * 4) + row;
+            list.keys = reinterpret_cast<float *>(smem + C::OFF_LIST) + row;
+            list.ids = reinterpret_cast<uint32_t *>(smem + C::OFF_LIST + (size_t)p.k * EPI_THREADS * 4) + row;
         } else {
             list.keys = p.list_keys_gmem + (size_t)blockIdx.x * p.k * EPI_THREADS + row;
             list.ids = p.list_ids_gmem + (size_t)blockIdx.x * p.k * EPI_THREADS + row;
@@ -353,7 +435,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 tmem_ld_wait();
             }
             tc_fence_before();
-            mbar_arrive(&tmem_empty_bar[as]);
+            if (CG == 1 || is_leader) mbar_arrive(&tmem_empty_bar[as]);
+            else mbar_arrive_remote(&tmem_empty_bar[as], 0);
             if (++as == ACC_STAGES) {
                 as = 0;
                 aphase ^= 1;
@@ -369,10 +452,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();  // nobody leaves while the peer may still signal us
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        if (CG == 1)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
 }
 
@@ -406,6 +492,30 @@ static bool encode_rows_map(CUtensorMap *map, const void *base, int64_t rows, in
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+template <int CG>
+static cudaError_t launch_cg(const CUtensorMap &map_q, const CUtensorMap &map_c, const GemmTopkParams &p, int grid,
+                             cudaStream_t s) {
+    size_t smem = Cfg<CG>::OFF_LIST + SMEM_ALIGN_SLACK;
+    if (p.k <= kGemmSmemK) smem += (size_t)p.k * EPI_THREADS * 8;
+    cudaError_t e = cudaFuncSetAttribute(gemm_topk_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, gemm_topk_kernel<CG>, map_q, map_c, p);
+    g_launches++;
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
 }  // namespace gemm
 
 int gemm_topk_grid(int q_tiles, int64_t n, int num_sms) {
@@ -418,19 +528,18 @@ int gemm_topk_grid(int q_tiles, int64_t n, int num_sms) {
 
 cudaError_t launch_gemm_topk(const GemmTopkParams &p, int grid, cudaStream_t s, const char **err_detail) {
     *err_detail = nullptr;
+    const int cg = p.cta_group == 2 ? 2 : 1;
+    if (grid % p.q_tiles != 0 || (cg == 2 && (p.q_tiles % 2 != 0))) {
+        *err_detail = "grid must be a multiple of q_tiles (and q_tiles even for cta_group 2)";
+        return cudaErrorInvalidValue;
+    }
     CUtensorMap map_q, map_c;
     if (!gemm::encode_rows_map(&map_q, p.queries_bf16, p.nq_pad, p.d_pad, gemm::BM) ||
-        !gemm::encode_rows_map(&map_c, p.corpus_bf16, p.n, p.d_pad, gemm::BN)) {
+        !gemm::encode_rows_map(&map_c, p.corpus_bf16, p.n, p.d_pad, gemm::BN / cg)) {
         *err_detail = "cuTensorMapEncodeTiled failed";
         return cudaErrorInvalidValue;
     }
-    size_t smem = gemm::OFF_LIST + gemm::SMEM_ALIGN_SLACK;
-    if (p.k <= kGemmSmemK) smem += (size_t)p.k * gemm::EPI_THREADS * 8;
-    cudaError_t e = cudaFuncSetAttribute(gemm::gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    gemm::gemm_topk_kernel<<<grid, gemm::NUM_THREADS, smem, s>>>(map_q, map_c, p);
-    g_launches++;
-    return cudaGetLastError();
+    return cg == 2 ? gemm::launch_cg<2>(map_q, map_c, p, grid, s) : gemm::launch_cg<1>(map_q, map_c, p, grid, s);
 }
 
 }  // namespace b200

@@ -65,6 +65,7 @@ struct GemmTopkParams {
     int64_t n;
     int nq_pad, d_pad, k;
     int q_tiles;               // nq_pad / 128
+    int cta_group;             // 1: one CTA per MMA; 2: CTA pairs (cluster of 2), q_tiles must be even
 };
 constexpr int kGemmSmemK = 30;
 int gemm_topk_grid(int q_tiles, int64_t n, int num_sms);

@@ -149,13 +149,16 @@ def test_scan_bf16_corpus():
 
 # ------------------------------------------------------------------ tcgen05 GEMM path vs oracle
 @pytest.mark.parametrize("metric", [b2.IP, b2.L2, b2.COSINE])
-@pytest.mark.parametrize("n,d,nq,k", [(20000, 768, 128, 10), (5000, 64, 37, 30), (70001, 128, 300, 10), (1000, 96, 20, 50)])
-def test_gemm_path_matches_oracle(metric, n, d, nq, k):
+@pytest.mark.parametrize("n,d,nq,k,path", [(20000, 768, 128, 10, 2), (5000, 64, 37, 30, 2), (70001, 128, 300, 10, 2),
+                                           (70001, 128, 300, 10, 3), (1000, 96, 20, 50, 2), (33333, 768, 1024, 10, 2),
+                                           (257, 64, 129, 5, 2)])
+def test_gemm_path_matches_oracle(metric, n, d, nq, k, path):
+    """path 2 = CTA pairs (cta_group::2) when nq > 128, path 3 = single-CTA MMAs only."""
     rng = np.random.default_rng(n + d + nq + metric)
     y = to_bf16_values(rng.standard_normal((n, d)).astype(F32))
     x = to_bf16_values(rng.standard_normal((nq, d)).astype(F32))
     c = b2.Corpus(metric, d, dtype=S.BF16).append(y)
-    c.set_path(2)
+    c.set_path(path)
     dg, ig = c.search(x, k)
     c.close()
     do, io = orc.knn_flat_parts(orc.IP if metric != orc.L2 else orc.L2, *( _prep_cos(x, y) if metric == b2.COSINE else (x, y)), k, 4)

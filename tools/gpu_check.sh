@@ -2,14 +2,15 @@
 # One gpurun call = many checks, each under its own timeout, all output kept in gpurun_out/.
 mkdir -p gpurun_out
 exec > >(tee gpurun_out/gpu_check.log) 2>&1
-nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv
-lscpu | grep -E "Model name|^CPU\(s\)|Thread|Socket|Flags" | cut -c1-400
-echo "=== gpu tests"
-timeout 900 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -25
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv,noheader
+echo "=== gemm tests first (new code)"
+timeout 600 python -m pytest tests/test_gpu_flat.py -m gpu -q -k "gemm" --timeout 200 -x 2>&1 | tail -25
+echo "=== all gpu tests"
+timeout 900 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -8
 echo "=== smoke"
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 echo "=== bench"
-timeout 900 python bench.py --steps 10 --warmup 3 2>&1 | tail -3
+timeout 900 python bench.py --steps 10 --warmup 3 $BENCH_ARGS 2>&1 | tail -3
 if [ "$1" == "ncu" ]; then
 echo "=== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench1.log 2>&1
