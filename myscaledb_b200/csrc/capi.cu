@@ -5,6 +5,7 @@
 // There is deliberately no CPU compute path in this file: every entry point either runs
 // CUDA kernels on an sm_100 device or fails with B200_ERR_NO_DEVICE / B200_ERR_CUDA.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -102,7 +103,8 @@ struct b200_corpus {
     cudaStream_t stream = nullptr;
     std::mutex mu;
     // workspaces
-    DevBuf w_raw, w_q32, w_qbf, w_qnorm, w_pk, w_pi, w_lk, w_li, w_alive, w_odis, w_oids, w_stage;
+    DevBuf w_raw, w_q32, w_qbf, w_qnorm, w_pk, w_pi, w_lk, w_li, w_alive, w_odis, w_oids, w_stage, w_prog;
+    int sync_slack = 2;
     // optional CUDA-event timing of the dominant kernel (scan or GEMM) for the roofline report
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_used, ev_free;
@@ -184,6 +186,7 @@ extern "C" int b200_corpus_create(int metric, int dtype, int d, int64_t capacity
     c->cap = capacity_rows;
     cudaGetDevice(&c->device);
     c->sms = num_sms();
+    if (const char *ev = getenv("B200_GEMM_SYNC_SLACK")) c->sync_slack = atoi(ev);
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete c;
@@ -334,7 +337,7 @@ extern "C" int b200_corpus_free(b200_corpus *c) {
     if (c->row_scale) cudaFree(c->row_scale);
     if (c->row_bias) cudaFree(c->row_bias);
     for (DevBuf *b : {&c->w_raw, &c->w_q32, &c->w_qbf, &c->w_qnorm, &c->w_pk, &c->w_pi, &c->w_lk, &c->w_li, &c->w_alive,
-                      &c->w_odis, &c->w_oids, &c->w_stage})
+                      &c->w_odis, &c->w_oids, &c->w_stage, &c->w_prog})
         b->release();
     for (auto *v : {&c->ev_used, &c->ev_free})
         for (auto &ev : *v) {
@@ -506,6 +509,12 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
         gp.k = k;
         gp.q_tiles = q_tiles;
         gp.cta_group = cta_group;
+        if (q_tiles > cta_group && c->sync_slack > 0) {
+            B200_TRY(c->w_prog.reserve((size_t)grid * 4));
+            B200_CUDA_OK(cudaMemsetAsync(c->w_prog.p, 0, (size_t)grid * 4, s));
+            gp.progress = c->w_prog.as<int>();
+            gp.sync_slack = c->sync_slack;
+        }
         const char *detail = nullptr;
         std::pair<cudaEvent_t, cudaEvent_t> ev;
         timing_begin(c, s, ev);

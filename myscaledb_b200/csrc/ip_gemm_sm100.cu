@@ -121,9 +121,27 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 // arrive on the mbarrier at the same offset in CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t cta) {
-    uint32_t remote;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 remote;\n\t"
+        "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [remote];\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(cta)
+        : "memory");
+}
+// one lane of a converged warp (keeps the surrounding control flow warp-uniform, so the
+// compiler holds descriptors / barrier addresses in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 
 // K-major, 128-byte swizzled operand tile: rows of 64 bf16 (128 B), 8-row atoms of 1024 B.
@@ -293,7 +311,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         }
         for (int i = 0; i < ACC_STAGES; i++) {
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], EPI_THREADS * CG);  // leader's: both CTAs' epilogue threads
+            mbar_init(&tmem_empty_bar[i], 4 * CG);  // leader's: one arrival per epilogue warp of both CTAs
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -317,12 +335,38 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs of a pair) =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int64_t t = worker; t < n_tiles; t += W) {
-                for (int kb = 0; kb < kb_count; kb++) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+        // the whole warp walks the loop (uniform control flow); one elected lane issues
+        int stage = 0;
+        uint32_t phase = 0;
+        int ordinal = 0;
+        bool pacing = p.progress != nullptr;
+        for (int64_t t = worker; t < n_tiles; t += W, ordinal++) {
+            // Pacing: the CTAs (pairs) that stream the SAME corpus tiles for different query tiles
+            // stay within `sync_slack` tiles of each other, so a tile is fetched from HBM once and
+            // served to the others from L2 (without it ncu shows 2.9-3.6x the algorithmic DRAM
+            // bytes, profiles/r01_*).  Only pacing, no data dependency: plain volatile counters.
+            // Bounded wait (~50 us): if the sharers are not co-resident (another kernel holds SMs)
+            // pacing is dropped instead of risking a co-residency deadlock.
+            if (pacing && is_leader) {
+                int ok = 1;
+                if (lane == 0) {
+                    volatile int *prog = p.progress + (size_t)worker * p.q_tiles;
+                    prog[qt] = ordinal + 1;
+                    int spins = 0;
+                    for (int g = 0; g < p.q_tiles; g += CG)
+                        while (prog[g] < ordinal + 1 - p.sync_slack && spins < 256) {
+                            __nanosleep(200);
+                            spins++;
+                        }
+                    if (spins >= 256) prog[qt] = 0x7fffffff;  // never hold anybody back again
+                    ok = spins < 256;
+                }
+                pacing = __shfl_sync(0xffffffffu, ok, 0) != 0;
+            }
+            __syncwarp();
+            for (int kb = 0; kb < kb_count; kb++) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
                     if (CG == 1) {
                         mbar_arrive_expect_tx(&full_bar[stage], C::TX_BYTES);
                         tma_load_2d(&map_q, &full_bar[stage], sA + stage * A_BYTES, kb * BK, qt * BM);
@@ -333,17 +377,22 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         tma_load_2d_cg2(&map_c, &full_bar[stage], sB + stage * C::B_BYTES, kb * BK,
                                         (int)(t * BN + cta_rank * C::B_ROWS));
                     }
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                }
+                __syncwarp();
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
-        if (lane == 0 && is_leader) {
+        if (is_leader) {
             constexpr uint32_t idesc = make_idesc(CG);
+            // descriptors of stage 0; other stages / k-steps are plain adds on the 14-bit
+            // (address >> 4) field, which cannot carry: shared addresses stay below 2^18
+            const uint64_t adesc0 = make_smem_desc(smem_u32(sA));
+            const uint64_t bdesc0 = make_smem_desc(smem_u32(sB));
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0;
             for (int64_t t = worker; t < n_tiles; t += W) {
@@ -353,24 +402,28 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 for (int kb = 0; kb < kb_count; kb++) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
-                    const uint32_t b_addr = smem_u32(sB + stage * C::B_BYTES);
+                    if (elect_one()) {
+                        const uint64_t adesc = adesc0 + (uint64_t)(stage * (A_BYTES >> 4));
+                        const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (C::B_BYTES >> 4));
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; k++) {
-                        const uint64_t adesc = make_smem_desc(a_addr + k * UMMA_K * 2);
-                        const uint64_t bdesc = make_smem_desc(b_addr + k * UMMA_K * 2);
-                        if (CG == 1) umma(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-                        else umma_cg2(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BK / UMMA_K; k++) {
+                            const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+                            if (CG == 1) umma(tmem_d, adesc + k * (UMMA_K * 2 >> 4), bdesc + k * (UMMA_K * 2 >> 4), idesc, acc);
+                            else umma_cg2(tmem_d, adesc + k * (UMMA_K * 2 >> 4), bdesc + k * (UMMA_K * 2 >> 4), idesc, acc);
+                        }
+                        // smem slot free (in both CTAs) once these MMAs retire
+                        if (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_cg2(&empty_bar[stage]);
+                        // accumulator ready for the epilogue (of both CTAs)
+                        if (kb == kb_count - 1) {
+                            if (CG == 1) umma_commit(&tmem_full_bar[as]); else umma_commit_cg2(&tmem_full_bar[as]);
+                        }
                     }
-                    // smem slot free (in both CTAs) once these MMAs retire
-                    if (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_cg2(&empty_bar[stage]);
+                    __syncwarp();
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                // accumulator ready for the epilogue (of both CTAs)
-                if (CG == 1) umma_commit(&tmem_full_bar[as]); else umma_commit_cg2(&tmem_full_bar[as]);
                 if (++as == ACC_STAGES) {
                     as = 0;
                     aphase ^= 1;
@@ -435,8 +488,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 tmem_ld_wait();
             }
             tc_fence_before();
-            if (CG == 1 || is_leader) mbar_arrive(&tmem_empty_bar[as]);
-            else mbar_arrive_remote(&tmem_empty_bar[as], 0);
+            __syncwarp();
+            if (lane == 0) {
+                if (CG == 1 || is_leader) mbar_arrive(&tmem_empty_bar[as]);
+                else mbar_arrive_remote(&tmem_empty_bar[as], 0);
+            }
             if (++as == ACC_STAGES) {
                 as = 0;
                 aphase ^= 1;

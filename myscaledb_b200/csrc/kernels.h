@@ -66,6 +66,8 @@ struct GemmTopkParams {
     int nq_pad, d_pad, k;
     int q_tiles;               // nq_pad / 128
     int cta_group;             // 1: one CTA per MMA; 2: CTA pairs (cluster of 2), q_tiles must be even
+    int *progress;             // [grid / q_tiles][q_tiles] zeroed pacing counters, or null
+    int sync_slack;            // tiles a CTA may run ahead of the slowest sharer of its corpus tiles
 };
 constexpr int kGemmSmemK = 30;
 int gemm_topk_grid(int q_tiles, int64_t n, int num_sms);
