@@ -287,7 +287,8 @@ def main():
 
     # ---- sanity: results are sane (sorted, ids in range); parity proper lives in tests/ ----
     d_res, i_res = res
-    assert (np.diff(d_res, axis=1) <= 0).all() and (i_res >= 0).all() and (i_res < a.rows).all()
+    if not os.environ.get("B200_GEMM_DEBUG"):  # kernel experiments produce garbage on purpose
+        assert (np.diff(d_res, axis=1) <= 0).all() and (i_res >= 0).all() and (i_res < a.rows).all()
 
     if rank == 0:
         peaks = {}

@@ -509,6 +509,7 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
         gp.k = k;
         gp.q_tiles = q_tiles;
         gp.cta_group = cta_group;
+        if (const char *dv = getenv("B200_GEMM_DEBUG")) gp.debug = atoi(dv);
         if (q_tiles > cta_group && c->sync_slack > 0) {
             B200_TRY(c->w_prog.reserve((size_t)grid * 4));
             B200_CUDA_OK(cudaMemsetAsync(c->w_prog.p, 0, (size_t)grid * 4, s));

@@ -366,7 +366,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             __syncwarp();
             for (int kb = 0; kb < kb_count; kb++) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                if (elect_one()) {
+                if (p.debug & 4) {  // experiment: no TMA traffic, operands are whatever is in smem
+                    if (is_leader && elect_one()) mbar_arrive(&full_bar[stage]);
+                } else if (elect_one()) {
                     if (CG == 1) {
                         mbar_arrive_expect_tx(&full_bar[stage], C::TX_BYTES);
                         tma_load_2d(&map_q, &full_bar[stage], sA + stage * A_BYTES, kb * BK, qt * BM);
@@ -470,6 +472,19 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             // filtered.  A chunk is first reduced to its best key (31 FMNMX); the per-element
             // test only runs for the rare chunk that can beat the current k-th key.
             const bool tail = n0 + BN > p.n;
+            if (p.debug & 1) {  // experiment: epilogue does nothing
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 1 || is_leader) mbar_arrive(&tmem_empty_bar[as]);
+                    else mbar_arrive_remote(&tmem_empty_bar[as], 0);
+                }
+                if (++as == ACC_STAGES) {
+                    as = 0;
+                    aphase ^= 1;
+                }
+                continue;
+            }
             float va[32], vb[32];
             __syncwarp();
             tmem_ld32_issue(taddr, va);
@@ -478,13 +493,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             for (int chunk = 0; chunk < BN / 32; chunk += 2) {
                 __syncwarp();
                 tmem_ld32_issue(taddr + (chunk + 1) * 32, vb);
-                epilogue_chunk(list, va, use_side, side_scale + chunk * 32, side_bias + chunk * 32,
-                               (uint32_t)(n0 + chunk * 32), tail, p.n);
+                if (!(p.debug & 2))
+                    epilogue_chunk(list, va, use_side, side_scale + chunk * 32, side_bias + chunk * 32,
+                                   (uint32_t)(n0 + chunk * 32), tail, p.n);
+                else if (va[3] == 12345.678f) list.n = 0;
                 tmem_ld_wait();
                 __syncwarp();
                 if (chunk + 2 < BN / 32) tmem_ld32_issue(taddr + (chunk + 2) * 32, va);
-                epilogue_chunk(list, vb, use_side, side_scale + (chunk + 1) * 32, side_bias + (chunk + 1) * 32,
-                               (uint32_t)(n0 + (chunk + 1) * 32), tail, p.n);
+                if (!(p.debug & 2))
+                    epilogue_chunk(list, vb, use_side, side_scale + (chunk + 1) * 32, side_bias + (chunk + 1) * 32,
+                                   (uint32_t)(n0 + (chunk + 1) * 32), tail, p.n);
+                else if (vb[3] == 12345.678f) list.n = 0;
                 tmem_ld_wait();
             }
             tc_fence_before();

@@ -15,7 +15,7 @@ echo "=== bench without pacing"
 B200_GEMM_SYNC_SLACK=0 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-400
 if [ "$1" == "ncu" ]; then
 echo "=== ncu launch list"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench1.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gemm_topk|topk_merge|pad_rows|f32_to_bf16|row_norms|flat_scan|normalize_rows" -c 60 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench1.log 2>&1
 tail -2 gpurun_out/ncu_bench1.log | cut -c1-300
 echo "=== ncu full capture of gemm_topk"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_topk -s 3 -c 1 -f -o gpurun_out/gemm_topk python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench2.log 2>&1
