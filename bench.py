@@ -193,8 +193,9 @@ def main():
     assert a.rows % (N * CHUNK) == 0 or N == 1, "rows must split into 250k-row chunks per rank"
 
     # ---- synthetic corpus shard, generated in HBM (seeded per global 250k-row chunk) ----
-    shard_rows = a.rows // N
-    row0 = rank * shard_rows
+    from myscaledb_b200.sharding import shard_range
+    row0, row1 = shard_range(a.rows, N, rank, CHUNK)
+    shard_rows = row1 - row0
     corpus = torch.empty((shard_rows, a.dim), dtype=torch.bfloat16, device=dev)
     off = 0
     while off < shard_rows:
