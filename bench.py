@@ -212,10 +212,12 @@ def main():
     index.enable_timing(True)
 
     k, nq = a.k, a.nq
-    o_dis = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    o_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
-    g_dis = torch.empty((N, nq, k), dtype=torch.float32, device=dev)
-    g_ids = torch.empty((N, nq, k), dtype=torch.int64, device=dev)
+    # one packed record per rank {float dis[nq*k]; int64 ids[nq*k]} -> a single NCCL all-gather
+    rec = nq * k * 12
+    packed = torch.empty(rec, dtype=torch.uint8, device=dev)
+    gathered = torch.empty(N * rec, dtype=torch.uint8, device=dev)
+    o_dis = packed[:nq * k * 4].view(torch.float32).view(nq, k)
+    o_ids = packed[nq * k * 4:].view(torch.int64).view(nq, k)
     f_dis = torch.empty((nq, k), dtype=torch.float32, device=dev)
     f_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
     h_dis = torch.empty((nq, k), dtype=torch.float32).pin_memory()
@@ -225,10 +227,9 @@ def main():
         s = torch.cuda.current_stream().cuda_stream
         index.search_device(q_dev.data_ptr(), nq, k, o_dis.data_ptr(), o_ids.data_ptr(), id_offset=row0, stream=s)
         if N > 1:
-            dist.all_gather_into_tensor(g_dis, o_dis)
-            dist.all_gather_into_tensor(g_ids, o_ids)
-            b2.topk_merge_device(g_dis.data_ptr(), g_ids.data_ptr(), N, nq, k, True, f_dis.data_ptr(), f_ids.data_ptr(),
-                                 stream=s)
+            dist.all_gather_into_tensor(gathered, packed)
+            S.topk_merge_device_strided(gathered.data_ptr(), gathered.data_ptr() + nq * k * 4, N, rec // 4, rec // 8, nq, k,
+                                        True, f_dis.data_ptr(), f_ids.data_ptr(), stream=s)
 
     def step_e2e():
         if N == 1:

@@ -111,7 +111,8 @@ int b200_corpus_search_device(b200_corpus *c, const float *d_queries, int64_t nq
                               const uint8_t *d_alive_bits /*nullable*/, int64_t id_offset, float *d_out_dis,
                               int64_t *d_out_ids, void *stream);
 /* Force a search path: 0 = auto, 1 = memory-bound scan kernel, 2 = tcgen05 bf16 GEMM
- * (CTA pairs when there are >= 2 query tiles), 3 = tcgen05 GEMM restricted to single-CTA MMAs. */
+ * (CTA pairs when there are >= 2 query tiles; queries stationary in TMEM when d <= 768),
+ * 3 = tcgen05 GEMM restricted to single-CTA MMAs, 4 = CTA pairs with both operands streamed. */
 int b200_corpus_set_path(b200_corpus *c, int path);
 /* CUDA-event timing of the dominant kernel (scan or GEMM) of every search on this corpus,
  * recorded on the launching stream; used by bench.py for the roofline report. */
@@ -127,6 +128,13 @@ int64_t b200_launch_count(int reset);
  * descending = 1 for IP / BM25. */
 int b200_topk_merge_device(const float *d_dis, const int64_t *d_ids, int n_lists, int64_t nq, int k, int descending,
                            float *d_out_dis, int64_t *d_out_ids, void *stream);
+
+/* Same, for a packed all-gather buffer: list l starts at d_dis + l * dis_list_stride (floats) and
+ * d_ids + l * ids_list_stride (int64s), so that one NCCL all-gather of
+ * {float dis[nq*k]; int64 ids[nq*k]} per rank feeds the merge directly. */
+int b200_topk_merge_device_strided(const float *d_dis, const int64_t *d_ids, int n_lists, int64_t dis_list_stride,
+                                   int64_t ids_list_stride, int64_t nq, int k, int descending, float *d_out_dis,
+                                   int64_t *d_out_ids, void *stream);
 
 #ifdef __cplusplus
 }

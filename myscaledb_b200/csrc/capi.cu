@@ -105,6 +105,7 @@ struct b200_corpus {
     // workspaces
     DevBuf w_raw, w_q32, w_qbf, w_qnorm, w_pk, w_pi, w_lk, w_li, w_alive, w_odis, w_oids, w_stage, w_prog;
     int sync_slack = 2;
+    int gemm_ts = 1;  // queries stationary in TMEM when the shape allows (B200_GEMM_TS=0 disables)
     // optional CUDA-event timing of the dominant kernel (scan or GEMM) for the roofline report
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_used, ev_free;
@@ -187,6 +188,7 @@ extern "C" int b200_corpus_create(int metric, int dtype, int d, int64_t capacity
     cudaGetDevice(&c->device);
     c->sms = num_sms();
     if (const char *ev = getenv("B200_GEMM_SYNC_SLACK")) c->sync_slack = atoi(ev);
+    if (const char *ev = getenv("B200_GEMM_TS")) c->gemm_ts = atoi(ev);
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete c;
@@ -294,9 +296,11 @@ extern "C" int b200_corpus_size(const b200_corpus *c, int64_t *out_rows) {
 }
 
 extern "C" int b200_corpus_set_path(b200_corpus *c, int path) {
-    if (!c || path < 0 || path > 3) return fail(B200_ERR_INVALID, "path must be 0, 1, 2 or 3");
-    c->path = path == 3 ? 2 : path;
+    if (!c || path < 0 || path > 4) return fail(B200_ERR_INVALID, "path must be 0..4");
+    c->path = path >= 3 ? 2 : path;
     c->gemm_cta_group = path == 3 ? 1 : 0;
+    if (path == 4) c->gemm_ts = 0;
+    if (path == 2) c->gemm_ts = 2;
     return B200_OK;
 }
 
@@ -519,7 +523,12 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
         const char *detail = nullptr;
         std::pair<cudaEvent_t, cudaEvent_t> ev;
         timing_begin(c, s, ev);
-        cudaError_t e = launch_gemm_topk(gp, grid, s, &detail);
+        // TS (queries stationary in TMEM): measured slower than streaming at d = 768 (N = 64 MMAs are bound
+        // by the 64 B/clk TMEM->tensor-core operand path: 75 vs 32 cycles per MMA); auto-enabled only
+        // where a 2 x 128-column accumulator ring fits (d_pad <= 512); gemm_ts = 2 forces it.
+        const bool use_ts = cta_group == 2 && gemm_topk_ts_supported(c->d_pad, q_tiles) &&
+                            (c->gemm_ts == 2 || (c->gemm_ts == 1 && c->d_pad <= 512));
+        cudaError_t e = use_ts ? launch_gemm_topk_ts(gp, grid, s, &detail) : launch_gemm_topk(gp, grid, s, &detail);
         timing_end(c, s, ev);
         if (e != cudaSuccess)
             return fail(B200_ERR_CUDA, std::string("gemm_topk launch: ") + (detail ? detail : cudaGetErrorString(e)));
@@ -671,6 +680,13 @@ extern "C" int b200_part_scan(int metric, const void *x, int64_t nx, const void 
 
 extern "C" int b200_topk_merge_device(const float *d_dis, const int64_t *d_ids, int n_lists, int64_t nq, int k,
                                       int descending, float *d_out_dis, int64_t *d_out_ids, void *stream) {
+    return b200_topk_merge_device_strided(d_dis, d_ids, n_lists, nq * k, nq * k, nq, k, descending, d_out_dis, d_out_ids,
+                                          stream);
+}
+
+extern "C" int b200_topk_merge_device_strided(const float *d_dis, const int64_t *d_ids, int n_lists,
+                                              int64_t dis_list_stride, int64_t ids_list_stride, int64_t nq, int k,
+                                              int descending, float *d_out_dis, int64_t *d_out_ids, void *stream) {
     if (!d_dis || !d_ids || !d_out_dis || !d_out_ids || n_lists <= 0 || nq < 0 || k <= 0)
         return fail(B200_ERR_INVALID, "bad arguments");
     if (k > 2048) return fail(B200_ERR_UNSUPPORTED, "k > 2048 not supported by the merge kernel");
@@ -679,7 +695,8 @@ extern "C" int b200_topk_merge_device(const float *d_dis, const int64_t *d_ids, 
     MergeParams mp{};
     mp.in_keys = d_dis;
     mp.in_ids = d_ids;
-    mp.list_stride = nq * k;
+    mp.list_stride = dis_list_stride;
+    mp.id_list_stride = ids_list_stride;
     mp.q_stride = k;
     mp.n_lists = n_lists;
     mp.k_in = k;

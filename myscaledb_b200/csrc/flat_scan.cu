@@ -284,19 +284,20 @@ __global__ void __launch_bounds__(kScanThreads) topk_merge_kernel(const MergePar
         if (c < ncand) {
             const int64_t l = c / p.k_in, j = c - l * p.k_in;
             const int64_t off = l * p.list_stride + q * p.q_stride + j;
+            const int64_t ioff = l * (p.id_list_stride ? p.id_list_stride : p.list_stride) + q * p.q_stride + j;
             const float v = keys[off];
             if (EXTERNAL) {
                 // external lists carry 64-bit ids (negative = empty slot); row ids are
                 // UInt32 labels in the reference (ColumnUInt32, MergeTreeVSManager.cpp:469),
                 // shard offsets keep them < 2^32 - 1
-                const int64_t full = (int64_t)ids[off];
+                const int64_t full = (int64_t)ids[ioff];
                 if (full >= 0) {
                     key = p.descending ? -v : v;
                     id = (uint32_t)full;
                     cand = list.passes(key, id);
                 }
             } else {
-                id = (uint32_t)ids[off];
+                id = (uint32_t)ids[ioff];
                 key = v;
                 cand = id != kNoId && list.passes(key, id);
             }

@@ -29,248 +29,10 @@
 //   filtered / out-of-range rows: scale 0, bias +inf.
 //
 // Tensor-bound: 2 * 128 * 256 * d FLOP per tile; algorithmic HBM bytes = N * d * 2 once.
-#include <cuda.h>
-
-#include "common.cuh"
-#include "kernels.h"
+#include "gemm_common.cuh"
 
 namespace b200 {
 namespace gemm {
-
-constexpr int BM = 128;
-constexpr int BN = 256;
-constexpr int BK = 64;
-constexpr int ACC_STAGES = 2;
-constexpr int UMMA_K = 16;
-constexpr int A_BYTES = BM * BK * 2;           // 16 KB
-constexpr int NUM_THREADS = 192;
-constexpr int EPI_THREADS = 128;
-constexpr int TMEM_COLS = 512;
-constexpr int SMEM_ALIGN_SLACK = 1024;
-constexpr int MAX_STAGES = 6;
-
-// CG = CTAs per MMA (cta_group): 1 or 2
-template <int CG>
-struct Cfg {
-    static constexpr int B_ROWS = BN / CG;                 // corpus rows staged by one CTA
-    static constexpr int B_BYTES = B_ROWS * BK * 2;        // 32 KB / 16 KB
-    static constexpr int STAGES = CG == 1 ? 4 : 6;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // per CTA
-    static constexpr int TX_BYTES = STAGE_BYTES * CG;      // what the (leader's) full barrier expects
-    static constexpr int OFF_A = 0;
-    static constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
-    static constexpr int OFF_SIDE = OFF_B + STAGES * B_BYTES;  // scale[256], bias[256]
-    static constexpr int OFF_BAR = OFF_SIDE + 2 * BN * 4;
-    static constexpr int OFF_LIST = OFF_BAR + 256;
-};
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    while (!mbar_try_wait(addr, parity)) {
-    }
-}
-
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-
-// 2-CTA form: dst in this CTA, completion signalled on the LEADER CTA's mbarrier (the shared
-// window address carries the CTA rank in bit 24; clearing it names the even CTA of the pair).
-__device__ __forceinline__ void tma_load_2d_cg2(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
-        "[%2];" ::"r"(smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
-        : "memory");
-}
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the mbarrier at the same offset in CTA `cta` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t cta) {
-    asm volatile(
-        "{\n\t"
-        ".reg .b32 remote;\n\t"
-        "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
-        "mbarrier.arrive.shared::cluster.b64 _, [remote];\n\t"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(cta)
-        : "memory");
-}
-// one lane of a converged warp (keeps the surrounding control flow warp-uniform, so the
-// compiler holds descriptors / barrier addresses in uniform registers)
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P;\n\t"
-        "elect.sync _|P, 0xffffffff;\n\t"
-        "selp.b32 %0, 1, 0, P;\n\t"
-        "}\n"
-        : "=r"(pred));
-    return pred != 0;
-}
-
-// K-major, 128-byte swizzled operand tile: rows of 64 bf16 (128 B), 8-row atoms of 1024 B.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);  // start address
-    d |= (uint64_t)1 << 16;                      // leading byte offset (unused for SW128 K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset: 8 rows * 128 B
-    d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
-    return d;
-}
-
-// kind::f16, A = B = bf16 (K-major), D = f32, M = 128 * CG, N = 256
-__device__ __forceinline__ constexpr uint32_t make_idesc(int cg) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * cg) >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void umma_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-}
-// arrive (once all prior MMAs retire) on the barrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_cg2(uint64_t *bar) {
-    const uint16_t mask = 3;
-    asm volatile(
-        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-            smem_u32(bar)),
-        "h"(mask)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
-          "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]),
-          "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]),
-          "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-// all tcgen05.ld issued by this thread have landed in their registers
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// per-thread sorted list, element j at [j * EPI_THREADS] (bank-conflict free in smem,
-// coalesced in global scratch)
-struct ThreadTopK {
-    float *keys;
-    uint32_t *ids;
-    int k, n;
-    float thr_key;
-    uint32_t thr_id;
-};
-
-__device__ __noinline__ void list_insert(ThreadTopK &t, float key, uint32_t id) {
-    if (!better(key, id, t.thr_key, t.thr_id)) return;
-    int j = t.n < t.k ? t.n : t.k - 1;
-    while (j > 0) {
-        const float pk = t.keys[(j - 1) * EPI_THREADS];
-        const uint32_t pi = t.ids[(j - 1) * EPI_THREADS];
-        if (!better(key, id, pk, pi)) break;
-        t.keys[j * EPI_THREADS] = pk;
-        t.ids[j * EPI_THREADS] = pi;
-        j--;
-    }
-    t.keys[j * EPI_THREADS] = key;
-    t.ids[j * EPI_THREADS] = id;
-    if (t.n < t.k) t.n++;
-    if (t.n == t.k) {
-        t.thr_key = t.keys[(t.k - 1) * EPI_THREADS];
-        t.thr_id = t.ids[(t.k - 1) * EPI_THREADS];
-    }
-}
-
-// Filter one chunk of 32 accumulator columns of this thread's query row.
-__device__ __forceinline__ void epilogue_chunk(ThreadTopK &list, float (&v)[32], bool use_side, const float *scale,
-                                               const float *bias, uint32_t id0, bool tail, int64_t n) {
-    float thr = list.thr_key;
-    if (use_side) {
-#pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = fmaf(v[j], scale[j], bias[j]);  // broadcast LDS
-    } else {
-#pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = -v[j];
-    }
-    float m0 = fminf(v[0], v[1]), m1 = fminf(v[2], v[3]), m2 = fminf(v[4], v[5]), m3 = fminf(v[6], v[7]);
-#pragma unroll
-    for (int j = 8; j < 32; j += 8) {
-        m0 = fminf(m0, fminf(v[j], v[j + 1]));
-        m1 = fminf(m1, fminf(v[j + 2], v[j + 3]));
-        m2 = fminf(m2, fminf(v[j + 4], v[j + 5]));
-        m3 = fminf(m3, fminf(v[j + 6], v[j + 7]));
-    }
-    const float best = fminf(fminf(m0, m1), fminf(m2, m3));
-    if (best <= thr) {
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-            if (v[j] <= thr && (use_side || !tail || (int64_t)(id0 + j) < n)) {
-                list_insert(list, v[j], id0 + j);
-                thr = list.thr_key;
-            }
-        }
-    }
-}
 
 template <int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -535,36 +297,6 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         else
             asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void *ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-    return fn;
-}
-
-static bool encode_rows_map(CUtensorMap *map, const void *base, int64_t rows, int d_pad, int box_rows) {
-    EncodeTiledFn fn = get_encode_fn();
-    if (!fn) return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)d_pad * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int CG>

@@ -34,6 +34,7 @@ struct MergeParams {
     const void *in_keys;     // float
     const void *in_ids;      // uint32 (internal partials) or int64 (external lists)
     int64_t list_stride, q_stride;
+    int64_t id_list_stride;  // 0 = same as list_stride (element units of the id type)
     int n_lists, k_in, k;
     int64_t nq;
     int descending;          // external only
@@ -74,6 +75,10 @@ constexpr int kGemmSmemK = 30;
 int gemm_topk_grid(int q_tiles, int64_t n, int num_sms);
 // returns cudaSuccess or an error; tensor maps are encoded inside
 cudaError_t launch_gemm_topk(const GemmTopkParams &p, int grid, cudaStream_t s, const char **err_detail);
+// queries-stationary-in-TMEM form (ip_gemm_ts_sm100.cu): CTA pairs, d_pad <= 768, even q_tiles
+bool gemm_topk_ts_supported(int d_pad, int q_tiles);
+int gemm_topk_ts_tile_rows(int d_pad);
+cudaError_t launch_gemm_topk_ts(const GemmTopkParams &p, int grid, cudaStream_t s, const char **err_detail);
 
 // ---- elementwise prep kernels (prep.cu) --------------------------------------------
 cudaError_t launch_f32_to_bf16_rows(const float *src, int d, void *dst, int d_pad, int64_t n, cudaStream_t s);

@@ -162,5 +162,13 @@ def topk_merge_device(dis_ptr, ids_ptr, n_lists, nq, k, descending, out_dis_ptr,
                                         C.c_void_p(out_ids_ptr), C.c_void_p(stream or None)))
 
 
+def topk_merge_device_strided(dis_ptr, ids_ptr, n_lists, dis_stride, ids_stride, nq, k, descending, out_dis_ptr,
+                              out_ids_ptr, stream=0):
+    _check(lib().b200_topk_merge_device_strided(C.c_void_p(dis_ptr), C.c_void_p(ids_ptr), C.c_int(n_lists),
+                                                C.c_int64(dis_stride), C.c_int64(ids_stride), C.c_int64(nq), C.c_int(k),
+                                                C.c_int(1 if descending else 0), C.c_void_p(out_dis_ptr),
+                                                C.c_void_p(out_ids_ptr), C.c_void_p(stream or None)))
+
+
 def launch_count(reset=False) -> int:
     return int(lib().b200_launch_count(C.c_int(1 if reset else 0)))

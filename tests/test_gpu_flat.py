@@ -150,10 +150,12 @@ def test_scan_bf16_corpus():
 # ------------------------------------------------------------------ tcgen05 GEMM path vs oracle
 @pytest.mark.parametrize("metric", [b2.IP, b2.L2, b2.COSINE])
 @pytest.mark.parametrize("n,d,nq,k,path", [(20000, 768, 128, 10, 2), (5000, 64, 37, 30, 2), (70001, 128, 300, 10, 2),
-                                           (70001, 128, 300, 10, 3), (1000, 96, 20, 50, 2), (33333, 768, 1024, 10, 2),
-                                           (257, 64, 129, 5, 2)])
+                                           (70001, 128, 300, 10, 3), (70001, 128, 300, 10, 4), (1000, 96, 20, 50, 2),
+                                           (33333, 768, 1024, 10, 2), (33333, 768, 1024, 10, 4), (257, 64, 129, 5, 2),
+                                           (9000, 512, 256, 10, 2), (9000, 832, 256, 10, 2)])
 def test_gemm_path_matches_oracle(metric, n, d, nq, k, path):
-    """path 2 = CTA pairs (cta_group::2) when nq > 128, path 3 = single-CTA MMAs only."""
+    """path 2 = auto (CTA pairs, queries stationary in TMEM when d <= 768), 3 = single-CTA MMAs only,
+    4 = CTA pairs with both operands streamed through shared memory."""
     rng = np.random.default_rng(n + d + nq + metric)
     y = to_bf16_values(rng.standard_normal((n, d)).astype(F32))
     x = to_bf16_values(rng.standard_normal((nq, d)).astype(F32))

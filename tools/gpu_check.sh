@@ -11,8 +11,8 @@ echo "=== smoke"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 echo "=== bench"
 timeout 900 python bench.py --steps 10 --warmup 3 $BENCH_ARGS 2>&1 | tail -3
-echo "=== bench without pacing"
-B200_GEMM_SYNC_SLACK=0 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-400
+echo "=== bench TS off"
+B200_GEMM_TS=0 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-400
 if [ "$1" == "ncu" ]; then
 echo "=== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gemm_topk|topk_merge|pad_rows|f32_to_bf16|row_norms|flat_scan|normalize_rows" -c 60 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench1.log 2>&1

@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 mkdir -p gpurun_out
 exec > >(tee gpurun_out/gpu_exp.log) 2>&1
-for dbg in 0 1 2 4 5; do
+for dbg in 0 1; do
   echo "=== B200_GEMM_DEBUG=$dbg"
   B200_GEMM_DEBUG=$dbg timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
 import json,sys
@@ -10,3 +10,5 @@ try:
 except Exception as e: print('ERR',e)
 "
 done
+echo "=== streaming pairs (B200_GEMM_TS=0)"
+B200_GEMM_TS=0 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-330
