@@ -25,6 +25,7 @@
 #ifndef B200_SEARCH_H
 #define B200_SEARCH_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -135,6 +136,53 @@ int b200_topk_merge_device(const float *d_dis, const int64_t *d_ids, int n_lists
 int b200_topk_merge_device_strided(const float *d_dis, const int64_t *d_ids, int n_lists, int64_t dis_list_stride,
                                    int64_t ids_list_stride, int64_t nq, int k, int descending, float *d_out_dis,
                                    int64_t *d_out_ids, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * BM25 full-text search (Boundary B).  Replaces the TANTIVY::ffi_* calls of TantivyIndexStore
+ * (Storages/MergeTree/TantivyIndexStore.cpp): ffi_index_multi_column_docs :742,
+ * ffi_index_writer_commit :824, ffi_bm25_search :908/:939, ffi_get_doc_freq :962,
+ * ffi_get_total_num_docs :974, ffi_get_total_num_tokens :986.  One index per part, resident
+ * in HBM; tantivy-0.21 BM25 and "default" tokenizer semantics; results are score-descending,
+ * ties to the smaller doc (tantivy TopDocs).
+ * ---------------------------------------------------------------------------------- */
+typedef struct b200_bm25 b200_bm25;
+int b200_bm25_create(uint32_t n_fields, b200_bm25 **out);
+int b200_bm25_free(b200_bm25 *ix);
+/* one row: add_doc(row_id) then add_text(field, text) per value (several per field for Array(String)) */
+int b200_bm25_add_doc(b200_bm25 *ix, uint64_t row_id);
+int b200_bm25_add_text(b200_bm25 *ix, uint32_t field, const char *text);
+int b200_bm25_commit(b200_bm25 *ix);
+int b200_bm25_total_docs(const b200_bm25 *ix, uint64_t *out);
+int b200_bm25_total_tokens(const b200_bm25 *ix, uint32_t field, uint64_t *out);
+int b200_bm25_doc_freq(const b200_bm25 *ix, uint32_t field, const char *term, uint64_t *out);
+/* distinct lowercase terms of a sentence, NUL-separated, in tokenisation order */
+int b200_bm25_query_terms(const char *sentence, char *buf, size_t buf_len, uint32_t *out_n);
+/* stat_*: table-wide statistics (ReadWithHybridSearch::getStatisticForTextSearch,
+ * VectorIndex/Processors/ReadWithHybridSearch.cpp:89-209), used iff stat_total_docs > 0:
+ * stat_total_tokens[n_fields of the index], stat_doc_freq[q][fq * 64 + term_index]. */
+int b200_bm25_search(b200_bm25 *ix, const char *sentence, const uint32_t *fields, uint32_t n_fields_q, uint32_t topk,
+                     const uint8_t *alive_bits /*over row ids*/, int use_filter, int operator_or, uint64_t stat_total_docs,
+                     const uint64_t *stat_total_tokens, const uint64_t *stat_doc_freq, uint64_t *out_rows,
+                     float *out_scores, uint32_t *out_n);
+int b200_bm25_search_batch(b200_bm25 *ix, const char *const *sentences, int64_t nq, const uint32_t *fields,
+                           uint32_t n_fields_q, uint32_t topk, const uint8_t *alive_bits, int use_filter, int operator_or,
+                           uint64_t stat_total_docs, const uint64_t *stat_total_tokens, const uint64_t *stat_doc_freq,
+                           uint64_t *out_rows /*[nq][topk]*/, float *out_scores, uint32_t *out_counts /*[nq]*/);
+
+/* ------------------------------------------------------------------------------------
+ * Hybrid-search fusion, batched.  Replaces RankFusion / RelativeScoreFusion
+ * (VectorIndex/Utils/HybridSearchUtils.cpp:164-274) + the final ordering of
+ * MergeTreeHybridSearchManager::hybridSearch (VectorIndex/Storages/MergeTreeHybridSearchManager.cpp:108-171).
+ * fusion_type 0 = RSF (fusion_weight, vector_scan_direction 1 asc / -1 desc), 1 = RRF (fusion_k).
+ * Candidate lists are [nq][stride] arrays (already globally ordered) with per-query counts;
+ * outputs [nq][top_k], fused score descending, ties in ascending (shard, part, label) order.
+ * ---------------------------------------------------------------------------------- */
+int b200_hybrid_fusion_batch(int fusion_type, int64_t nq, const uint32_t *vec_shard, const uint64_t *vec_part,
+                             const uint64_t *vec_label, const float *vec_score, const uint32_t *vec_count, int64_t vec_stride,
+                             const uint32_t *txt_shard, const uint64_t *txt_part, const uint64_t *txt_label,
+                             const float *txt_score, const uint32_t *txt_count, int64_t txt_stride, float fusion_weight,
+                             uint64_t fusion_k, int vector_scan_direction, uint32_t top_k, uint32_t *out_shard,
+                             uint64_t *out_part, uint64_t *out_label, float *out_score, uint32_t *out_count);
 
 #ifdef __cplusplus
 }

@@ -105,7 +105,7 @@ struct b200_corpus {
     // workspaces
     DevBuf w_raw, w_q32, w_qbf, w_qnorm, w_pk, w_pi, w_lk, w_li, w_alive, w_odis, w_oids, w_stage, w_prog;
     int sync_slack = 2;
-    int gemm_ts = 1;  // queries stationary in TMEM when the shape allows (B200_GEMM_TS=0 disables)
+    int gemm_ts = 0;  // 0 streaming (default: faster at every measured d), 1 TS when d_pad <= 512, 2 TS whenever it fits
     // optional CUDA-event timing of the dominant kernel (scan or GEMM) for the roofline report
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_used, ev_free;

@@ -172,3 +172,121 @@ def topk_merge_device_strided(dis_ptr, ids_ptr, n_lists, dis_stride, ids_stride,
 
 def launch_count(reset=False) -> int:
     return int(lib().b200_launch_count(C.c_int(1 if reset else 0)))
+
+
+class BM25Index:
+    """Per-part BM25 index resident in HBM (mirror of the TantivyIndexStore calls,
+    src/Storages/MergeTree/TantivyIndexStore.cpp:742-998)."""
+
+    def __init__(self, n_fields: int = 1):
+        self._h = C.c_void_p()
+        self.n_fields = n_fields
+        _check(lib().b200_bm25_create(C.c_uint32(n_fields), C.byref(self._h)))
+
+    def add_doc(self, row_id: int, texts):
+        """texts: per field a str or a list[str] (Array(String) column)."""
+        _check(lib().b200_bm25_add_doc(self._h, C.c_uint64(row_id)))
+        if isinstance(texts, str):
+            texts = [texts]
+        for f, t in enumerate(texts):
+            for piece in ([t] if isinstance(t, str) else t):
+                _check(lib().b200_bm25_add_text(self._h, C.c_uint32(f), piece.encode()))
+
+    def commit(self):
+        _check(lib().b200_bm25_commit(self._h))
+        return self
+
+    @property
+    def total_docs(self):
+        v = C.c_uint64()
+        _check(lib().b200_bm25_total_docs(self._h, C.byref(v)))
+        return v.value
+
+    def total_tokens(self, field=0):
+        v = C.c_uint64()
+        _check(lib().b200_bm25_total_tokens(self._h, C.c_uint32(field), C.byref(v)))
+        return v.value
+
+    def doc_freq(self, term, field=0):
+        v = C.c_uint64()
+        _check(lib().b200_bm25_doc_freq(self._h, C.c_uint32(field), term.encode(), C.byref(v)))
+        return v.value
+
+    @staticmethod
+    def query_terms(sentence):
+        buf = C.create_string_buffer(4096)
+        n = C.c_uint32()
+        _check(lib().b200_bm25_query_terms(sentence.encode(), buf, C.c_size_t(4096), C.byref(n)))
+        return [t.decode() for t in buf.raw.split(b"\0")[:n.value]]
+
+    def search_batch(self, sentences, topk, fields=(0,), alive_bits=None, operator_or=True, stats=None):
+        nq = len(sentences)
+        arr = (C.c_char_p * nq)(*[s.encode() for s in sentences])
+        f = np.array(fields, np.uint32)
+        rows = np.empty((nq, topk), np.uint64)
+        scores = np.empty((nq, topk), np.float32)
+        counts = np.zeros(nq, np.uint32)
+        st_docs, st_tok, st_df = 0, None, None
+        if stats is not None:
+            st_docs = int(stats["total_docs"])
+            st_tok = np.zeros(self.n_fields, np.uint64)
+            for fi, v in stats["total_tokens"].items():
+                st_tok[fi] = v
+            st_df = np.zeros((nq, len(fields), 64), np.uint64)
+            for qi, sent in enumerate(sentences):
+                for ti, t in enumerate(self.query_terms(sent)[:64]):
+                    for fi, fld in enumerate(fields):
+                        st_df[qi, fi, ti] = stats["doc_freq"].get((fld, t), 0)
+        ab = _bits(alive_bits)
+        _check(lib().b200_bm25_search_batch(self._h, arr, C.c_int64(nq), _p(f, C.c_uint32), C.c_uint32(len(fields)),
+                                            C.c_uint32(topk), _p(ab, C.c_uint8), C.c_int(0 if ab is None else 1),
+                                            C.c_int(1 if operator_or else 0), C.c_uint64(st_docs), _p(st_tok, C.c_uint64),
+                                            _p(st_df, C.c_uint64), _p(rows, C.c_uint64), _p(scores, C.c_float),
+                                            _p(counts, C.c_uint32)))
+        return [(rows[q, :counts[q]].copy(), scores[q, :counts[q]].copy()) for q in range(nq)]
+
+    def search(self, sentence, topk, **kw):
+        return self.search_batch([sentence], topk, **kw)[0]
+
+    def close(self):
+        if self._h:
+            lib().b200_bm25_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def hybrid_fusion_batch(fusion_type, vec_lists, txt_lists, top_k, fusion_weight=0.5, fusion_k=60, vector_scan_direction=1):
+    """vec_lists / txt_lists: per query a list of (shard, part, label, score), globally ordered.
+    Returns per query a list of (shard, part, label, fused_score)."""
+    nq = len(vec_lists)
+    assert len(txt_lists) == nq
+    vs = max([len(v) for v in vec_lists] + [1])
+    ts = max([len(t) for t in txt_lists] + [1])
+
+    def pack(lists, stride):
+        sh = np.zeros((nq, stride), np.uint32); pa = np.zeros((nq, stride), np.uint64)
+        la = np.zeros((nq, stride), np.uint64); sc = np.zeros((nq, stride), np.float32)
+        cnt = np.zeros(nq, np.uint32)
+        for q, lst in enumerate(lists):
+            cnt[q] = len(lst)
+            for i, (a, b, c, d) in enumerate(lst):
+                sh[q, i], pa[q, i], la[q, i], sc[q, i] = a, b, c, d
+        return sh, pa, la, sc, cnt
+    v = pack(vec_lists, vs)
+    t = pack(txt_lists, ts)
+    o_sh = np.zeros((nq, top_k), np.uint32); o_pa = np.zeros((nq, top_k), np.uint64)
+    o_la = np.zeros((nq, top_k), np.uint64); o_sc = np.zeros((nq, top_k), np.float32); o_cnt = np.zeros(nq, np.uint32)
+    ft = {"rsf": 0, "rrf": 1}[fusion_type.lower()]
+    _check(lib().b200_hybrid_fusion_batch(
+        C.c_int(ft), C.c_int64(nq), _p(v[0], C.c_uint32), _p(v[1], C.c_uint64), _p(v[2], C.c_uint64), _p(v[3], C.c_float),
+        _p(v[4], C.c_uint32), C.c_int64(vs), _p(t[0], C.c_uint32), _p(t[1], C.c_uint64), _p(t[2], C.c_uint64),
+        _p(t[3], C.c_float), _p(t[4], C.c_uint32), C.c_int64(ts), C.c_float(fusion_weight), C.c_uint64(fusion_k),
+        C.c_int(vector_scan_direction), C.c_uint32(top_k), _p(o_sh, C.c_uint32), _p(o_pa, C.c_uint64), _p(o_la, C.c_uint64),
+        _p(o_sc, C.c_float), _p(o_cnt, C.c_uint32)))
+    return [[(int(o_sh[q, i]), int(o_pa[q, i]), int(o_la[q, i]), float(o_sc[q, i])) for i in range(o_cnt[q])]
+            for q in range(nq)]

@@ -1,0 +1,62 @@
+"""HybridSearch on the GPU: vector scan + BM25 + fusion through the C ABI reproduce the reference's
+goldens (fed 5 candidates per modality, see SURVEY.md 8c stale-golden caveat) and the oracle on
+random lists."""
+import numpy as np
+import pytest
+
+import myscaledb_b200 as b2
+import oracle as orc
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+def _lists_5_gpu(goldens):
+    g = goldens["00040_hybrid"]
+    ix = b2.BM25Index(1)
+    for rid, _, doc in g["docs"]:
+        ix.add_doc(rid, [doc])
+    ix.commit()
+    rows, sc = ix.search("Ancient", 5)
+    txt = [(0, 0, int(r), float(s)) for r, s in zip(rows, sc)]
+    y = np.repeat(np.arange(20, dtype=np.float32)[:, None], 3, axis=1)
+    dis, ids = b2.part_scan(b2.L2, np.array([[1, 1, 1]], F32), y, 5)
+    vec = [(0, 0, int(i), float(d)) for i, d in zip(ids[0], dis[0])]
+    return vec, txt
+
+
+def _order(res, k=5):
+    return sorted(((r[2], float(F32(r[3]))) for r in res), key=lambda t: (-t[1], t[0]))[:k]
+
+
+def test_goldens_rsf_rrf_end_to_end_on_gpu(goldens):
+    g = goldens["00040_hybrid"]
+    vec, txt = _lists_5_gpu(goldens)
+    rsf, rrf = (b2.hybrid_fusion_batch(ft, [vec], [txt], 10, fusion_weight=0.5, fusion_k=60, vector_scan_direction=1)[0]
+                for ft in ("rsf", "rrf"))
+    assert [[i, s] for i, s in _order(rsf)] == [[e[0], float(F32(e[1]))] for e in g["rsf"]]
+    assert [[i, s] for i, s in _order(rrf)] == [[e[0], float(F32(e[1]))] for e in g["rrf"]]
+    assert [[i, s] for i, s in _order(rsf)] == [[e[0], float(F32(e[1]))] for e in goldens["00041_multi_parts"]["rsf_1part"]]
+
+
+@pytest.mark.parametrize("ft", ["rsf", "rrf"])
+@pytest.mark.parametrize("direction", [1, -1])
+def test_random_lists_match_oracle_bitexact(ft, direction):
+    rng = np.random.default_rng(17)
+    vecs, txts = [], []
+    for q in range(64):
+        nv, nt = int(rng.integers(0, 31)), int(rng.integers(0, 31))
+        labels = rng.permutation(80)
+        vs = np.sort(rng.random(nv).astype(F32))
+        if direction == -1:
+            vs = vs[::-1]
+        if q % 7 == 0 and nv:
+            vs[:] = vs[0]  # all-equal scores -> normalised to 1.0
+        ts = np.sort(rng.random(nt).astype(F32))[::-1]
+        vecs.append([(int(l % 2), int(l % 3), int(l), float(s)) for l, s in zip(labels[:nv], vs)])
+        txts.append([(int(l % 2), int(l % 3), int(l), float(s)) for l, s in zip(rng.permutation(80)[:nt], ts)])
+    got = b2.hybrid_fusion_batch(ft, vecs, txts, 20, fusion_weight=0.3, fusion_k=60, vector_scan_direction=direction)
+    for q in range(64):
+        exp = orc.hybrid_fusion(ft, vecs[q], txts[q], 20, fusion_weight=0.3, fusion_k=60, vector_scan_direction=direction) \
+            if (vecs[q] or txts[q]) else []
+        assert [(a, b, c, float(F32(d))) for a, b, c, d in got[q]] == [(a, b, c, float(F32(d))) for a, b, c, d in exp], q
