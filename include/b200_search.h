@@ -138,6 +138,28 @@ int b200_topk_merge_device_strided(const float *d_dis, const int64_t *d_ids, int
                                    int64_t *d_out_ids, void *stream);
 
 /* ------------------------------------------------------------------------------------
+ * Vector indexes.  Replaces Search::createVectorIndex / VectorIndex::{build, search,
+ * computeTopDistanceSubset} (VectorIndex/Common/VIWithDataPart.cpp:416-430, :131, :926, :838-856).
+ * type: "FLAT", "IVFFLAT", "IVFPQ", "MSTG" (MSTG is closed source upstream; here it names our
+ * two-stage index: IVFPQ first stage + exact fp32 re-rank).  params: the
+ * reference's key=value / JSON parameter string ("ncentroids=1024, M=32", "nprobe=64",
+ * "refine_factor=8").  Parts smaller than max(2000, 8 * nlist) rows are served by an exact FLAT
+ * scan (the reference's fallback_to_flat, test 00029).
+ * ---------------------------------------------------------------------------------- */
+typedef struct b200_index b200_index;
+int b200_index_create(const char *type, int metric, int d, const char *params, b200_index **out);
+int b200_index_build(b200_index *ix, const float *rows, int64_t n);
+int b200_index_info(const b200_index *ix, int64_t *n, int *nlist, int *m, int *uses_ivf);
+/* first_stage_only (MSTG): return the first-stage candidates with approximate distances;
+ * out_num_candidates receives the width the first stage ran with (SearchResult::getNumCandidates). */
+int b200_index_search(b200_index *ix, const float *queries, int64_t nq, int k, const char *params, int first_stage_only,
+                      const uint8_t *alive_bits /*nullable*/, float *out_dis, int64_t *out_ids, int64_t *out_num_candidates);
+/* computeTopDistanceSubset: exact distances of candidate ids [nq][ncand] (negative = unused) -> top-k */
+int b200_index_refine(b200_index *ix, const float *queries, int64_t nq, const int64_t *cand_ids, int64_t ncand, int k,
+                      float *out_dis, int64_t *out_ids);
+int b200_index_free(b200_index *ix);
+
+/* ------------------------------------------------------------------------------------
  * BM25 full-text search (Boundary B).  Replaces the TANTIVY::ffi_* calls of TantivyIndexStore
  * (Storages/MergeTree/TantivyIndexStore.cpp): ffi_index_multi_column_docs :742,
  * ffi_index_writer_commit :824, ffi_bm25_search :908/:939, ffi_get_doc_freq :962,

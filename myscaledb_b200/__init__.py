@@ -8,9 +8,9 @@ anywhere, computing needs an sm_100 GPU and the built library.
 """
 from . import _lib  # noqa: F401
 from .search import (  # noqa: F401
-    COSINE, HAMMING, IP, JACCARD, L2, METRIC_NAMES, B200Error, BM25Index, Corpus, binary_knn, flat_knn, hybrid_fusion_batch, part_scan,
+    COSINE, HAMMING, IP, JACCARD, L2, METRIC_NAMES, B200Error, BM25Index, Corpus, VectorIndex, binary_knn, flat_knn, hybrid_fusion_batch, part_scan,
     topk_merge_device,
 )
 
-__all__ = ["Corpus", "BM25Index", "hybrid_fusion_batch", "flat_knn", "binary_knn", "part_scan", "topk_merge_device", "B200Error", "L2", "IP", "COSINE",
+__all__ = ["Corpus", "VectorIndex", "BM25Index", "hybrid_fusion_batch", "flat_knn", "binary_knn", "part_scan", "topk_merge_device", "B200Error", "L2", "IP", "COSINE",
            "HAMMING", "JACCARD", "METRIC_NAMES"]

@@ -130,6 +130,18 @@ static void timing_end(b200_corpus *c, cudaStream_t s, std::pair<cudaEvent_t, cu
     c->ev_used.push_back(ev);
 }
 
+namespace b200 {
+// hooks for the index layer (ivf.cu): device view of the rows / in-place row normalisation
+const void *corpus_device_rows(const b200_corpus *c) { return c->data; }
+int corpus_normalize_rows(b200_corpus *c) {
+    if (c->dtype != B200_DTYPE_F32) return fail(B200_ERR_UNSUPPORTED, "normalise: fp32 corpora only");
+    B200_CUDA_OK(cudaSetDevice(c->device));
+    B200_CUDA_OK(launch_normalize_rows_f32(reinterpret_cast<float *>(c->data), c->d_pad, c->n, c->stream));
+    B200_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return B200_OK;
+}
+}  // namespace b200
+
 static bool is_float_metric(int m) { return m == B200_METRIC_L2 || m == B200_METRIC_IP || m == B200_METRIC_COSINE; }
 static bool is_bin_metric(int m) { return m == B200_METRIC_HAMMING || m == B200_METRIC_JACCARD; }
 

@@ -290,3 +290,57 @@ def hybrid_fusion_batch(fusion_type, vec_lists, txt_lists, top_k, fusion_weight=
         _p(o_sc, C.c_float), _p(o_cnt, C.c_uint32)))
     return [[(int(o_sh[q, i]), int(o_pa[q, i]), int(o_la[q, i]), float(o_sc[q, i])) for i in range(o_cnt[q])]
             for q in range(nq)]
+
+
+class VectorIndex:
+    """Mirror of Search::VectorIndex as driven by VIWithColumnInPart (build / search / computeTopDistanceSubset,
+    src/VectorIndex/Common/VIWithDataPart.cpp:131, :926, :838-856).  type: FLAT, IVFFLAT, IVFPQ, MSTG."""
+
+    def __init__(self, index_type, metric, d, params=""):
+        self._h = C.c_void_p()
+        self.d = d
+        _check(lib().b200_index_create(index_type.encode(), C.c_int(metric), C.c_int(d), params.encode(), C.byref(self._h)))
+
+    def build(self, rows):
+        rows = np.ascontiguousarray(rows, np.float32)
+        _check(lib().b200_index_build(self._h, _p(rows, C.c_float), C.c_int64(rows.shape[0])))
+        return self
+
+    def info(self):
+        n, nl, m, ivf = C.c_int64(), C.c_int(), C.c_int(), C.c_int()
+        _check(lib().b200_index_info(self._h, C.byref(n), C.byref(nl), C.byref(m), C.byref(ivf)))
+        return dict(n=n.value, nlist=nl.value, m=m.value, uses_ivf=bool(ivf.value))
+
+    def search(self, queries, k, params="", first_stage_only=False, alive_bits=None):
+        q = np.ascontiguousarray(queries, np.float32)
+        nq = q.shape[0]
+        dis = np.empty((nq, k), np.float32)
+        ids = np.empty((nq, k), np.int64)
+        nc = C.c_int64()
+        ab = _bits(alive_bits)
+        _check(lib().b200_index_search(self._h, _p(q, C.c_float), C.c_int64(nq), C.c_int(k), params.encode(),
+                                       C.c_int(1 if first_stage_only else 0), _p(ab, C.c_uint8), _p(dis, C.c_float),
+                                       _p(ids, C.c_int64), C.byref(nc)))
+        self.last_num_candidates = nc.value
+        return dis, ids
+
+    def refine(self, queries, cand_ids, k):
+        q = np.ascontiguousarray(queries, np.float32)
+        c = np.ascontiguousarray(cand_ids, np.int64)
+        nq = q.shape[0]
+        dis = np.empty((nq, k), np.float32)
+        ids = np.empty((nq, k), np.int64)
+        _check(lib().b200_index_refine(self._h, _p(q, C.c_float), C.c_int64(nq), _p(c, C.c_int64), C.c_int64(c.shape[1]),
+                                       C.c_int(k), _p(dis, C.c_float), _p(ids, C.c_int64)))
+        return dis, ids
+
+    def close(self):
+        if self._h:
+            lib().b200_index_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,117 @@
+"""IVFFLAT / IVFPQ / two-stage (MSTG-type) indexes and computeTopDistanceSubset on the GPU.
+There is no runnable reference for ANN behaviour (closed / un-vendored libraries): "parity unpinned"
+for large-N recall; the contract is recall vs the exact FLAT answer (validated against the oracle)
+and exact refined distances.  Small-N goldens (00028) are pinned exactly via the FLAT fallback."""
+import numpy as np
+import pytest
+
+import myscaledb_b200 as b2
+import oracle as orc
+from tests.util import check_topk
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+def _clustered(n, d, n_centres, seed, spread=0.3):
+    rng = np.random.default_rng(seed)
+    centres = rng.standard_normal((n_centres, d)).astype(F32)
+    y = centres[rng.integers(0, n_centres, n)] + spread * rng.standard_normal((n, d)).astype(F32)
+    q = centres[rng.integers(0, n_centres, 64)] + spread * rng.standard_normal((64, d)).astype(F32)
+    return y.astype(F32), q.astype(F32)
+
+
+def _recall(ids, truth):
+    return np.mean([len(set(a.tolist()) & set(b.tolist())) / len(b) for a, b in zip(ids, truth)])
+
+
+@pytest.mark.parametrize("metric", [b2.L2, b2.IP, b2.COSINE])
+def test_ivfflat_all_lists_equals_exact(metric):
+    y, q = _clustered(30000, 64, 200, 1)
+    ix = b2.VectorIndex("IVFFLAT", metric, 64, "ncentroids=64").build(y)
+    assert ix.info()["uses_ivf"]
+    dg, ig = ix.search(q, 10, "nprobe=64")
+    do, io = orc.search_without_index(metric, q, y, 10)
+    check_topk(metric, q, y, dg, ig, do, io, rtol=2e-4, atol=2e-5, min_exact=0.995)
+    # a few lists only: recall drops but stays high on clustered data
+    d2, i2 = ix.search(q, 10, "nprobe=8")
+    assert _recall(i2, io) > 0.8
+
+
+def test_ivfflat_alive_bitmap():
+    y, q = _clustered(20000, 32, 100, 2)
+    alive = np.random.default_rng(3).random(20000) < 0.5
+    ix = b2.VectorIndex("IVFFLAT", b2.L2, 32, "ncentroids=32").build(y)
+    dg, ig = ix.search(q, 10, "nprobe=32", alive_bits=orc.pack_bits(alive))
+    do, io = orc.search_without_index(orc.L2, q, y, 10, alive=orc.pack_bits(alive))
+    check_topk(b2.L2, q, y, dg, ig, do, io, rtol=2e-4, atol=2e-5, min_exact=0.995)
+
+
+@pytest.mark.parametrize("metric", [b2.L2, b2.COSINE])
+def test_two_stage_mstg_recall_and_exact_distances(metric):
+    y, q = _clustered(60000, 96, 500, 5)
+    ix = b2.VectorIndex("MSTG", metric, 96, "ncentroids=128, M=24").build(y)
+    info = ix.info()
+    assert info["uses_ivf"] and info["m"] == 24
+    do, io = orc.search_without_index(metric, q, y, 10)
+    dg, ig = ix.search(q, 10, "nprobe=32, refine_factor=16")
+    assert ix.last_num_candidates == 160
+    rec = _recall(ig, io)
+    assert rec >= 0.95, rec
+    # refined distances are EXACT fp32 distances of the returned ids
+    for qi in range(len(q)):
+        for j in range(10):
+            t = orc.search_without_index(metric, q[qi:qi + 1], y[ig[qi, j]:ig[qi, j] + 1], 1)[0][0, 0]
+            assert abs(dg[qi, j] - t) <= 1e-4 * max(1.0, abs(t))
+    assert (np.diff(dg, axis=1) >= -1e-6).all()
+    # first stage only: approximate (ADC) distances, wider candidate list semantics of the reference
+    d1, i1 = ix.search(q, 160, "nprobe=32", first_stage_only=True)
+    assert (i1 >= 0).all() and (np.diff(d1, axis=1) >= -1e-6).all()
+    # the 160 first-stage candidates must already contain (almost) all true top-10 -- that is what stage 2 re-ranks
+    assert np.mean([len(set(a.tolist()) & set(b.tolist())) / 10 for a, b in zip(i1, io)]) >= 0.95
+
+
+def test_ivfpq_ip_adc_recall():
+    y, q = _clustered(40000, 64, 300, 8)
+    ix = b2.VectorIndex("IVFPQ", b2.IP, 64, "ncentroids=64, M=32").build(y)
+    do, io = orc.search_without_index(orc.IP, q, y, 10)
+    dg, ig = ix.search(q, 10, "nprobe=64")
+    assert _recall(ig, io) >= 0.6
+    # ADC scores approximate the true inner products
+    true = np.array([[float(q[a] @ y[ig[a, j]]) for j in range(10)] for a in range(len(q))])
+    assert np.abs(dg - true).max() < 0.15 * np.abs(true).max()
+
+
+def test_compute_top_distance_subset_matches_oracle():
+    rng = np.random.default_rng(4)
+    y = rng.standard_normal((5000, 100)).astype(F32)
+    q = rng.standard_normal((7, 100)).astype(F32)
+    for metric in (b2.L2, b2.IP, b2.COSINE):
+        ix = b2.VectorIndex("FLAT", metric, 100).build(y)
+        cand = np.stack([rng.permutation(5000)[:50] for _ in range(7)]).astype(np.int64)
+        cand[2, 40:] = -1
+        dg, ig = ix.refine(q, cand, 8)
+        for qi in range(7):
+            c = cand[qi][cand[qi] >= 0]
+            do, io = orc.search_without_index(metric, q[qi:qi + 1], y[c], 8)
+            assert ig[qi].tolist() == c[io[0]].tolist()
+            np.testing.assert_allclose(dg[qi], do[0], rtol=1e-4, atol=1e-5)
+
+
+def test_golden_00028_mstg_small_part_falls_back_to_exact(goldens):
+    g = goldens["00028_mstg_768"]
+    n = np.arange(1000, dtype=np.float64)[:, None]; x = np.arange(768, dtype=np.float64)[None, :]
+    y = (0.00001 * (n * 768 + x + 1) * np.where(x % 2 == 0, -1.0, 1.0)).astype(F32)
+    q = np.array([g["query"]], F32)
+    ix = b2.VectorIndex("MSTG", b2.L2, 768, "disk_mode=1").build(y)
+    assert not ix.info()["uses_ivf"]
+    dis, ids = ix.search(q, 5)
+    assert ids[0].tolist() == [e[0] for e in g["expect_l2"]]
+    np.testing.assert_allclose(dis[0], [e[1] for e in g["expect_l2"]], rtol=1e-4)
+    ic = b2.VectorIndex("MSTG", b2.COSINE, 768, "metric_type=Cosine").build(y)
+    dis, ids = ic.search(q, 5)
+    assert ids[0].tolist() == [e[0] for e in g["expect_cosine"]]
+    np.testing.assert_allclose(dis[0], [e[1] for e in g["expect_cosine"]], rtol=1e-4)
+    alive = np.ones(1000, bool); alive[0] = False; alive[2] = False
+    dis, ids = ic.search(q, 5, alive_bits=orc.pack_bits(alive))
+    assert ids[0].tolist() == [e[0] for e in g["expect_cosine_after_delete_id2"]]
