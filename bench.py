@@ -114,7 +114,8 @@ def run_cpu_sample(a, q_np, y_np, threads):
     """Times the oracle's threaded brute force (the reference's CPU algorithm) on y_np."""
     import oracle as orc
     t0 = time.perf_counter()
-    orc.knn_flat_parts(orc.IP, q_np, y_np, a.k, threads)
+    if orc.knn_flat_parts_blas(orc.IP, q_np, y_np, a.k, threads) is None:   # Faiss BLAS form (preferred)
+        orc.knn_flat_parts(orc.IP, q_np, y_np, a.k, threads)               # portable SIMD loops
     return time.perf_counter() - t0
 
 
@@ -132,7 +133,8 @@ def cpu_baseline(a, q_np, sample_fn):
     qps = a.nq / (t * (a.rows / rows))
     return {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
             "sample": f"{a.nq} queries x {rows} of {a.rows} rows (fp32 copies of the bf16 values), "
-                      f"{t:.2f} s on {threads} threads, one thread per part, scaled linearly to {a.rows} rows"}
+                      f"{t:.2f} s on {threads} threads, one single-threaded OpenBLAS sgemm stream per part "
+                      f"(Faiss BLAS form; oracle/cpu_baseline.c), scaled linearly to {a.rows} rows"}
 
 
 def reference_arm(a):
@@ -162,7 +164,7 @@ def reference_arm(a):
     qps = a.nq / t_step
     cb = {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
           "sample": f"each step = {a.nq} queries x {rows} of {a.rows} rows, scaled linearly; oracle/cpu_baseline.c, "
-                    "one thread per part (reference threading model)"}
+                    "one single-threaded OpenBLAS sgemm stream per part (Faiss BLAS form, reference threading model)"}
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": a.gpus,
                       "steps": a.steps, "warmup": a.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
                       "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -287,6 +289,27 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_qps = nq / (float(te.item()) / a.steps)
 
+    # ---- the memory-bound FLAT scan on the same resident shard (BASELINE metric: "brute-force GB/s vs HBM peak")
+    flat_scan = []
+    if rank == 0 or N > 1:
+        for nq_s in (1, 8):
+            index.set_path(1)
+            for _ in range(3):
+                index.search_device(q_dev.data_ptr(), nq_s, k, o_dis.data_ptr(), o_ids.data_ptr(), id_offset=row0,
+                                    stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            index.kernel_time(reset=True)
+            reps = 10
+            for _ in range(reps):
+                index.search_device(q_dev.data_ptr(), nq_s, k, o_dis.data_ptr(), o_ids.data_ptr(), id_offset=row0,
+                                    stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            kms, kn = index.kernel_time(reset=True)
+            gbs = shard_rows * a.dim * 2 / (kms / max(kn, 1) * 1e-3) / 1e9
+            flat_scan.append({"kernel": "flat_scan_kernel (bf16 rows, fp32 FMA)", "queries_per_pass": nq_s,
+                              "ms_per_launch": kms / max(kn, 1), "GB_per_s": gbs, "bytes_per_launch": shard_rows * a.dim * 2})
+        index.set_path(0)
+
     # ---- sanity: results are sane (sorted, ids in range); parity proper lives in tests/ ----
     d_res, i_res = res
     if not os.environ.get("B200_GEMM_DEBUG"):  # kernel experiments produce garbage on purpose
@@ -318,6 +341,11 @@ def main():
                          "launches_timed": int(kern_n), "peak_source": peak_src,
                          "hbm_algorithmic_bytes_per_launch": shard_rows * a.dim * 2},
         }
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        for fs in flat_scan:
+            fs["frac_of_hbm_peak"] = fs["GB_per_s"] / hbm
+            fs["hbm_peak_GB_per_s"] = hbm
+        out["flat_scan"] = flat_scan
         if N == 1 and not a.no_cpu_baseline:
             qn = q_host.numpy()
             out["cpu_baseline"] = cpu_baseline(a, qn, lambda rows: corpus[:rows].to(torch.float32).cpu().numpy())

@@ -176,6 +176,29 @@ def knn_flat_parts(metric, x, y, k, n_parts):
     return dis, ids
 
 
+def blas_path():
+    """OpenBLAS shipped inside numpy's wheel (numpy.libs/libscipy_openblas64_*.so), or None."""
+    import glob
+    hits = glob.glob(os.path.join(os.path.dirname(np.__file__), "..", "numpy.libs", "libscipy_openblas64_*.so"))
+    return hits[0] if hits else None
+
+
+def knn_flat_parts_blas(metric, x, y, k, n_parts):
+    """Timed CPU baseline, Faiss BLAS form: one single-threaded sgemm stream per part (cpu_baseline.c).
+    Returns None when no OpenBLAS could be loaded."""
+    p = blas_path()
+    if p is None or lib().orc_blas_load(p.encode()) != 0:
+        return None
+    x, y = _f32(x), _f32(y)
+    nx, d = x.shape
+    ny = y.shape[0]
+    dis = np.empty((nx, k), np.float32)
+    ids = np.empty((nx, k), np.int64)
+    rc = lib().orc_knn_flat_parts_blas(C.c_int(metric), _p(x, C.c_float), C.c_int64(nx), _p(y, C.c_float), C.c_int64(ny),
+                                       C.c_int(d), C.c_int(k), C.c_int(n_parts), _p(dis, C.c_float), _p(ids, C.c_int64))
+    return (dis, ids) if rc == 0 else None
+
+
 class BM25Index:
     """In-memory per-part inverted index with tantivy-0.21 BM25 semantics (bm25_oracle.c)."""
 

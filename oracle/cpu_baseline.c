@@ -220,3 +220,146 @@ void orc_knn_flat_parts(int metric, const float *x, int64_t nx, const float *y, 
     free(jobs);
     free(th);
 }
+
+/* ------------------------------------------------------------------------- */
+/* BLAS form of the same baseline.  Faiss routes knn_inner_product/knn_L2sqr  */
+/* with nx >= 20 through sgemm in blocks of 4096 queries x 1024 base rows     */
+/* (published behaviour of faiss/utils/distances.cpp); the reference reaches  */
+/* it from BruteForceSearch.h:77-88 with omp_set_num_threads(1), i.e. one     */
+/* single-threaded sgemm stream per part.  The sgemm comes from the OpenBLAS  */
+/* that numpy bundles (dlopen'ed; ILP64 cblas interface), so the CPU arm gets  */
+/* a vendor-tuned AVX-512/AMX kernel rather than this file's portable loops.  */
+/* ------------------------------------------------------------------------- */
+#include <dlfcn.h>
+
+typedef void (*sgemm_fn)(int order, int transa, int transb, int64_t m, int64_t n, int64_t k, float alpha, const float *a,
+                         int64_t lda, const float *b, int64_t ldb, float beta, float *c, int64_t ldc);
+typedef void (*setthr_fn)(int);
+static sgemm_fn g_sgemm = NULL;
+
+int orc_blas_load(const char *path) {
+    if (g_sgemm) return 0;
+    void *h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) return -1;
+    g_sgemm = (sgemm_fn)dlsym(h, "scipy_cblas_sgemm64_");
+    setthr_fn st = (setthr_fn)dlsym(h, "scipy_openblas_set_num_threads64_");
+    if (st) st(1); /* threads come from the parts, not from BLAS (omp_set_num_threads(1)) */
+    return g_sgemm ? 0 : -2;
+}
+
+static void *orc_part_worker_blas(void *arg) {
+    orc_part_job *jb = (orc_part_job *)arg;
+    const int k = jb->k, d = jb->d;
+    const int64_t nx = jb->nx;
+    const int64_t YB = 1024, QB = 4096; /* faiss distance_compute_blas_{database,query}_bs */
+    float *keys = (float *)malloc(sizeof(float) * (size_t)k * (size_t)nx);
+    int64_t *ids = (int64_t *)malloc(sizeof(int64_t) * (size_t)k * (size_t)nx);
+    int *cnt = (int *)calloc((size_t)nx, sizeof(int));
+    const int64_t qb_max = nx < QB ? nx : QB;
+    float *blk = (float *)malloc(sizeof(float) * (size_t)qb_max * YB);
+    float *xn = NULL, *yn = (float *)malloc(sizeof(float) * YB);
+    if (jb->metric == ORC_L2) {
+        xn = (float *)malloc(sizeof(float) * (size_t)nx);
+        for (int64_t q = 0; q < nx; q++) xn[q] = orc_ip(jb->x + q * d, jb->x + q * d, d);
+    }
+    for (int64_t q0 = 0; q0 < nx; q0 += QB) {
+        const int64_t nqb = nx - q0 < QB ? nx - q0 : QB;
+        for (int64_t y0 = jb->y0; y0 < jb->y1; y0 += YB) {
+            const int64_t nyb = jb->y1 - y0 < YB ? jb->y1 - y0 : YB;
+            const float *yb = jb->y + y0 * d;
+            /* blk[nqb][nyb] = X[nqb][d] * Y[nyb][d]^T  (row major = 101, NoTrans = 111, Trans = 112) */
+            g_sgemm(101, 111, 112, nqb, nyb, d, 1.0f, jb->x + q0 * d, d, yb, d, 0.0f, blk, nyb);
+            if (jb->metric == ORC_L2)
+                for (int64_t i = 0; i < nyb; i++) yn[i] = orc_ip(yb + (size_t)i * d, yb + (size_t)i * d, d);
+            for (int64_t a = 0; a < nqb; a++) {
+                const int64_t q = q0 + a;
+                orc_topk t = {k, cnt[q], keys + q * k, ids + q * k};
+                const float *row = blk + (size_t)a * nyb;
+                for (int64_t i = 0; i < nyb; i++) {
+                    float key;
+                    if (jb->metric == ORC_L2) {
+                        key = xn[q] + yn[i] - 2 * row[i];
+                        if (key < 0) key = 0;
+                    } else {
+                        key = -row[i];
+                    }
+                    if (t.n == k && !(key <= t.key[k - 1])) continue;
+                    orc_topk_push(&t, key, y0 + i);
+                }
+                cnt[q] = t.n;
+            }
+        }
+    }
+    for (int64_t q = 0; q < nx; q++)
+        for (int j = 0; j < k; j++) {
+            if (j < cnt[q]) {
+                jb->dis[q * k + j] = jb->metric == ORC_L2 ? keys[q * k + j] : -keys[q * k + j];
+                jb->ids[q * k + j] = ids[q * k + j];
+            } else {
+                jb->dis[q * k + j] = jb->metric == ORC_L2 ? FLT_MAX : -FLT_MAX;
+                jb->ids[q * k + j] = -1;
+            }
+        }
+    free(keys);
+    free(ids);
+    free(cnt);
+    free(blk);
+    free(xn);
+    free(yn);
+    return NULL;
+}
+
+/* same contract as orc_knn_flat_parts; returns -1 if orc_blas_load() has not succeeded */
+int orc_knn_flat_parts_blas(int metric, const float *x, int64_t nx, const float *y, int64_t ny, int d, int k, int n_parts,
+                            float *dis, int64_t *ids) {
+    if (!g_sgemm) return -1;
+    if (n_parts < 1) n_parts = 1;
+    if (n_parts > ny && ny > 0) n_parts = (int)ny;
+    orc_part_job *jobs = (orc_part_job *)calloc((size_t)n_parts, sizeof(orc_part_job));
+    pthread_t *th = (pthread_t *)calloc((size_t)n_parts, sizeof(pthread_t));
+    int64_t per = (ny + n_parts - 1) / n_parts;
+    for (int p = 0; p < n_parts; p++) {
+        jobs[p].metric = metric;
+        jobs[p].x = x;
+        jobs[p].nx = nx;
+        jobs[p].y = y;
+        jobs[p].y0 = per * p < ny ? per * p : ny;
+        jobs[p].y1 = per * (p + 1) < ny ? per * (p + 1) : ny;
+        jobs[p].d = d;
+        jobs[p].k = k;
+        jobs[p].dis = (float *)malloc(sizeof(float) * (size_t)k * (size_t)nx);
+        jobs[p].ids = (int64_t *)malloc(sizeof(int64_t) * (size_t)k * (size_t)nx);
+        pthread_create(&th[p], NULL, orc_part_worker_blas, &jobs[p]);
+    }
+    for (int p = 0; p < n_parts; p++) pthread_join(th[p], NULL);
+    float *key = (float *)malloc(sizeof(float) * (size_t)k);
+    int64_t *id = (int64_t *)malloc(sizeof(int64_t) * (size_t)k);
+    for (int64_t q = 0; q < nx; q++) {
+        orc_topk t = {k, 0, key, id};
+        for (int p = 0; p < n_parts; p++)
+            for (int j = 0; j < k; j++) {
+                int64_t rid = jobs[p].ids[q * k + j];
+                if (rid < 0) continue;
+                float s = jobs[p].dis[q * k + j];
+                orc_topk_push(&t, metric == ORC_L2 ? s : -s, rid);
+            }
+        for (int j = 0; j < k; j++) {
+            if (j < t.n) {
+                dis[q * k + j] = metric == ORC_L2 ? key[j] : -key[j];
+                ids[q * k + j] = id[j];
+            } else {
+                dis[q * k + j] = metric == ORC_L2 ? FLT_MAX : -FLT_MAX;
+                ids[q * k + j] = -1;
+            }
+        }
+    }
+    for (int p = 0; p < n_parts; p++) {
+        free(jobs[p].dis);
+        free(jobs[p].ids);
+    }
+    free(key);
+    free(id);
+    free(jobs);
+    free(th);
+    return 0;
+}

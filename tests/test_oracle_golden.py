@@ -240,3 +240,17 @@ def test_cpu_baseline_matches_checker(metric):
     d1, i1 = orc.knn_flat_parts(metric, x, y, 10, n_parts=3)
     assert (i0 == i1).mean() > 0.999
     np.testing.assert_allclose(d0, d1, rtol=2e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("metric", [orc.L2, orc.IP])
+def test_cpu_baseline_blas_matches_checker(metric):
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((45, 96)).astype(F32)
+    y = rng.standard_normal((7003, 96)).astype(F32)
+    d0, i0 = orc.knn_flat(metric, x, y, 10)
+    res = orc.knn_flat_parts_blas(metric, x, y, 10, n_parts=3)
+    if res is None:
+        pytest.skip("no OpenBLAS next to numpy")
+    d1, i1 = res
+    assert (i0 == i1).mean() > 0.999
+    np.testing.assert_allclose(d0, d1, rtol=2e-4, atol=2e-4)
