@@ -51,3 +51,16 @@ def test_compute_fails_loudly_without_gpu():
     assert ei.value.code == 4 and "no CPU fallback" in str(ei.value)
     with pytest.raises(b2.B200Error):
         b2.Corpus(b2.IP, 64)
+
+
+def test_cpp_shim_compiles_and_links_against_the_c_abi():
+    """shim/b200_search_shim.hpp presents Search:: / faiss:: / TANTIVY:: and forwards to the C ABI."""
+    exe = os.path.join(ROOT, "tests", "cpp", "shim_smoke")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           "-I" + os.path.join(ROOT, "shim"), os.path.join(ROOT, "tests", "cpp", "shim_smoke.cpp"), "-o", exe,
+                           "-L" + os.path.join(ROOT, "myscaledb_b200"), "-lb200search",
+                           "-Wl,-rpath,$ORIGIN/../../myscaledb_b200"])
+    assert os.path.exists(exe)
+    if not os.path.exists("/dev/nvidia0"):
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 2 and "no CPU fallback" in r.stdout  # loud failure through SearchIndexException

@@ -60,3 +60,15 @@ def test_random_lists_match_oracle_bitexact(ft, direction):
         exp = orc.hybrid_fusion(ft, vecs[q], txts[q], 20, fusion_weight=0.3, fusion_k=60, vector_scan_direction=direction) \
             if (vecs[q] or txts[q]) else []
         assert [(a, b, c, float(F32(d))) for a, b, c, d in got[q]] == [(a, b, c, float(F32(d))) for a, b, c, d in exp], q
+
+
+def test_cpp_shim_runs_on_gpu():
+    """The reference-side C++ binding (Search::VectorIndex, faiss::knn_L2sqr, TANTIVY::ffi_*) end to end."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "shim_smoke")
+    if not os.path.exists(exe):
+        pytest.skip("shim_smoke not built (run __graft_entry__.build())")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "SHIM OK" in r.stdout, r.stdout + r.stderr
