@@ -23,18 +23,28 @@ constexpr int SMEM_ALIGN_SLACK = 1024;
 constexpr int MAX_STAGES = 6;
 
 // CG = CTAs per MMA (cta_group): 1 or 2
+constexpr int SCRATCH_BYTES = 32 * EPI_THREADS * 4;  // epilogue slow-path scratch [32][128] floats
+
 template <int CG>
 struct Cfg {
     static constexpr int B_ROWS = BN / CG;                 // corpus rows staged by one CTA
     static constexpr int B_BYTES = B_ROWS * BK * 2;        // 32 KB / 16 KB
-    static constexpr int STAGES = CG == 1 ? 4 : 6;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // per CTA
     static constexpr int TX_BYTES = STAGE_BYTES * CG;      // what the (leader's) full barrier expects
-    static constexpr int OFF_A = 0;
-    static constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
-    static constexpr int OFF_SIDE = OFF_B + STAGES * B_BYTES;  // scale[256], bias[256]
-    static constexpr int OFF_BAR = OFF_SIDE + 2 * BN * 4;
-    static constexpr int OFF_LIST = OFF_BAR + 256;
+    // smem layout for a ring of `stages` stages (runtime: 6/5 for pairs, 4/3 single, by top-k list size)
+    __host__ __device__ static constexpr int off_a() { return 0; }
+    __host__ __device__ static constexpr int off_b(int stages) { return stages * A_BYTES; }
+    __host__ __device__ static constexpr int off_side(int stages) { return stages * STAGE_BYTES; }  // scale[256], bias[256]
+    __host__ __device__ static constexpr int off_bar(int stages) { return off_side(stages) + 2 * BN * 4; }
+    __host__ __device__ static constexpr int off_scratch(int stages) { return off_bar(stages) + 256; }
+    __host__ __device__ static constexpr int off_list(int stages) { return off_scratch(stages) + SCRATCH_BYTES; }
+    // deepest ring that leaves room for the per-thread lists (k <= kGemmSmemK) in 227 KB
+    __host__ __device__ static int stages_for(int k_smem) {
+        const int max_stages = CG == 1 ? 4 : 6;
+        int st = max_stages;
+        while (st > 2 && off_list(st) + k_smem * EPI_THREADS * 8 + SMEM_ALIGN_SLACK > 232448) st--;
+        return st;
+    }
 };
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -184,42 +194,81 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float (&v)[32]) 
 // all tcgen05.ld issued by this thread have landed in their registers
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// per-thread sorted list, element j at [j * EPI_THREADS] (bank-conflict free in smem,
-// coalesced in global scratch)
+// Per-thread top-k as an UNSORTED buffer (element j at [j * EPI_THREADS]: bank-conflict free in smem,
+// coalesced in global scratch) plus the position of its current worst element.  An insert overwrites
+// the worst slot and rescans the k slots with independent loads (~60 cycles at k = 10); the first
+// version kept the list sorted and paid a dependent load-compare-store chain per shifted element
+// (~400 cycles per insert, 1.7 ms of start-up "insert storm" per launch, profiles/r01_summary.md).
+// The buffer is sorted once, when the CTA publishes its partial list.
 struct ThreadTopK {
     float *keys;
     uint32_t *ids;
-    int k, n;
-    float thr_key;
+    int k, n, worst;
+    float thr_key;     // key of the current worst kept element (FLT_MAX while n < k)
     uint32_t thr_id;
 };
 
-static __device__ __noinline__ void list_insert(ThreadTopK &t, float key, uint32_t id) {
+__device__ __forceinline__ void list_insert(ThreadTopK &t, float key, uint32_t id) {
     if (!better(key, id, t.thr_key, t.thr_id)) return;
-    int j = t.n < t.k ? t.n : t.k - 1;
-    while (j > 0) {
-        const float pk = t.keys[(j - 1) * EPI_THREADS];
-        const uint32_t pi = t.ids[(j - 1) * EPI_THREADS];
-        if (!better(key, id, pk, pi)) break;
-        t.keys[j * EPI_THREADS] = pk;
-        t.ids[j * EPI_THREADS] = pi;
-        j--;
+    if (t.n < t.k) {
+        t.keys[t.n * EPI_THREADS] = key;
+        t.ids[t.n * EPI_THREADS] = id;
+        t.n++;
+        if (t.n < t.k) return;
+    } else {
+        t.keys[t.worst * EPI_THREADS] = key;
+        t.ids[t.worst * EPI_THREADS] = id;
     }
-    t.keys[j * EPI_THREADS] = key;
-    t.ids[j * EPI_THREADS] = id;
-    if (t.n < t.k) t.n++;
-    if (t.n == t.k) {
-        t.thr_key = t.keys[(t.k - 1) * EPI_THREADS];
-        t.thr_id = t.ids[(t.k - 1) * EPI_THREADS];
+    // rescan for the worst (largest key, ties -> larger id)
+    float wk = t.keys[0];
+    uint32_t wi = t.ids[0];
+    int wp = 0;
+    for (int j = 1; j < t.k; j++) {
+        const float kj = t.keys[j * EPI_THREADS];
+        const uint32_t ij = t.ids[j * EPI_THREADS];
+        if (better(wk, wi, kj, ij)) {
+            wk = kj;
+            wi = ij;
+            wp = j;
+        }
+    }
+    t.worst = wp;
+    t.thr_key = wk;
+    t.thr_id = wi;
+}
+
+// sort the n kept entries best-first (insertion sort, once per kernel) and publish them
+static __device__ __noinline__ void list_publish(ThreadTopK &t, float *out_keys, uint32_t *out_ids) {
+    for (int i = 1; i < t.n; i++) {
+        const float ki = t.keys[i * EPI_THREADS];
+        const uint32_t ii = t.ids[i * EPI_THREADS];
+        int j = i;
+        while (j > 0 && better(ki, ii, t.keys[(j - 1) * EPI_THREADS], t.ids[(j - 1) * EPI_THREADS])) {
+            t.keys[j * EPI_THREADS] = t.keys[(j - 1) * EPI_THREADS];
+            t.ids[j * EPI_THREADS] = t.ids[(j - 1) * EPI_THREADS];
+            j--;
+        }
+        t.keys[j * EPI_THREADS] = ki;
+        t.ids[j * EPI_THREADS] = ii;
+    }
+    for (int j = 0; j < t.k; j++) {
+        out_keys[j] = j < t.n ? t.keys[j * EPI_THREADS] : FLT_MAX;
+        out_ids[j] = j < t.n ? t.ids[j * EPI_THREADS] : kNoId;
     }
 }
 
 // Filter one chunk of 32 accumulator columns of this thread's query row.
-// Plain IP (no side arrays): the score itself is reduced with FMNMX3 max trees and compared
-// against -thr; nothing is negated unless a candidate is actually inserted.
+// Fast path (steady state): reduce the chunk to its best key with FMNMX3 trees, one warp vote,
+// done.  Slow path (some lane of the warp can improve its list; frequent only during the first
+// tiles of a launch): every lane parks its 32 keys in a shared-memory scratch column and the WARP
+// loops while any lane still has a candidate bit, each lane popping its own lowest bit and doing
+// an inlined insert.  Compared with per-element calls under divergence this removed a fixed
+// ~1.3 ms "insert storm" per launch (profiles/r01_summary.md).
+// scratch: this thread's column of a [32][EPI_THREADS] float array.
 __device__ __forceinline__ void epilogue_chunk(ThreadTopK &list, float (&v)[32], bool use_side, const float *scale,
-                                               const float *bias, uint32_t id0, bool tail, int64_t n) {
-    float thr = list.thr_key;
+                                               const float *bias, uint32_t id0, bool tail, int64_t n, float *scratch) {
+    const float thr = list.thr_key;
+    bool mine;
     if (use_side) {
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = fmaf(v[j], scale[j], bias[j]);  // broadcast LDS
@@ -231,17 +280,9 @@ __device__ __forceinline__ void epilogue_chunk(ThreadTopK &list, float (&v)[32],
             m2 = fminf(m2, fminf(v[j + 4], v[j + 5]));
             m3 = fminf(m3, fminf(v[j + 6], v[j + 7]));
         }
-        const float best = fminf(fminf(m0, m1), fminf(m2, m3));
-        if (best <= thr) {
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-                if (v[j] <= thr) {
-                    list_insert(list, v[j], id0 + j);
-                    thr = list.thr_key;
-                }
-            }
-        }
+        mine = fminf(fminf(m0, m1), fminf(m2, m3)) <= thr;
     } else {
+        // plain IP: rank on the raw score with max trees; the key (-score) is formed only when needed
         float m0 = fmaxf(v[0], v[1]), m1 = fmaxf(v[2], v[3]), m2 = fmaxf(v[4], v[5]), m3 = fmaxf(v[6], v[7]);
 #pragma unroll
         for (int j = 8; j < 32; j += 8) {
@@ -250,15 +291,25 @@ __device__ __forceinline__ void epilogue_chunk(ThreadTopK &list, float (&v)[32],
             m2 = fmaxf(m2, fmaxf(v[j + 4], v[j + 5]));
             m3 = fmaxf(m3, fmaxf(v[j + 6], v[j + 7]));
         }
-        const float best = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-        float nthr = -thr;
-        if (best >= nthr) {
+        mine = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) >= -thr;
+    }
+    if (__any_sync(0xffffffffu, mine)) {
+        uint32_t mask = 0;
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                if (v[j] >= nthr && (!tail || (int64_t)(id0 + j) < n)) {
-                    list_insert(list, -v[j], id0 + j);
-                    nthr = -list.thr_key;
-                }
+        for (int j = 0; j < 32; j++) {
+            const float key = use_side ? v[j] : -v[j];
+            scratch[j * EPI_THREADS] = key;
+            if (key <= thr) mask |= 1u << j;
+        }
+        if (tail && !use_side) {  // rows past the end of the corpus (zero-filled by TMA) are not candidates
+            const int64_t left = n - (int64_t)id0;
+            mask = left >= 32 ? mask : left <= 0 ? 0u : (mask & ((1u << left) - 1u));
+        }
+        while (__any_sync(0xffffffffu, mask != 0)) {
+            if (mask) {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1;
+                list_insert(list, scratch[j * EPI_THREADS], id0 + (uint32_t)j);
             }
         }
     }

@@ -39,14 +39,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
                  const GemmTopkParams p) {
     using C = Cfg<CG>;
-    constexpr int STAGES = C::STAGES;
+    const int STAGES = p.stages;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    unsigned char *sA = smem + C::OFF_A;
-    unsigned char *sB = smem + C::OFF_B;
-    float *side_scale = reinterpret_cast<float *>(smem + C::OFF_SIDE);
+    unsigned char *sA = smem + C::off_a();
+    unsigned char *sB = smem + C::off_b(STAGES);
+    float *side_scale = reinterpret_cast<float *>(smem + C::off_side(STAGES));
     float *side_bias = side_scale + BN;
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + C::off_bar(STAGES));
     uint64_t *empty_bar = full_bar + MAX_STAGES;
     uint64_t *tmem_full_bar = empty_bar + MAX_STAGES;
     uint64_t *tmem_empty_bar = tmem_full_bar + ACC_STAGES;
@@ -200,14 +200,16 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const int row = quarter * 32 + lane;          // query row inside the tile
         const int et = threadIdx.x - 64;              // 0..127 among epilogue threads
         const bool use_side = p.row_scale || p.row_bias || p.alive || p.scale_const != -1.f;
+        float *scratch = reinterpret_cast<float *>(smem + C::off_scratch(STAGES)) + et;
         ThreadTopK list;
         list.k = p.k;
         list.n = 0;
+        list.worst = 0;
         list.thr_key = FLT_MAX;
         list.thr_id = 0;
         if (p.k <= kGemmSmemK) {
-            list.keys = reinterpret_cast<float *>(smem + C::OFF_LIST) + row;
-            list.ids = reinterpret_cast<uint32_t *>(smem + C::OFF_LIST + (size_t)p.k * EPI_THREADS * 4) + row;
+            list.keys = reinterpret_cast<float *>(smem + C::off_list(STAGES)) + row;
+            list.ids = reinterpret_cast<uint32_t *>(smem + C::off_list(STAGES) + (size_t)p.k * EPI_THREADS * 4) + row;
         } else {
             list.keys = p.list_keys_gmem + (size_t)blockIdx.x * p.k * EPI_THREADS + row;
             list.ids = p.list_ids_gmem + (size_t)blockIdx.x * p.k * EPI_THREADS + row;
@@ -257,14 +259,14 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 tmem_ld32_issue(taddr + (chunk + 1) * 32, vb);
                 if (!(p.debug & 2))
                     epilogue_chunk(list, va, use_side, side_scale + chunk * 32, side_bias + chunk * 32,
-                                   (uint32_t)(n0 + chunk * 32), tail, p.n);
+                                   (uint32_t)(n0 + chunk * 32), tail, p.n, scratch);
                 else if (va[3] == 12345.678f) list.n = 0;
                 tmem_ld_wait();
                 __syncwarp();
                 if (chunk + 2 < BN / 32) tmem_ld32_issue(taddr + (chunk + 2) * 32, va);
                 if (!(p.debug & 2))
                     epilogue_chunk(list, vb, use_side, side_scale + (chunk + 1) * 32, side_bias + (chunk + 1) * 32,
-                                   (uint32_t)(n0 + (chunk + 1) * 32), tail, p.n);
+                                   (uint32_t)(n0 + (chunk + 1) * 32), tail, p.n, scratch);
                 else if (vb[3] == 12345.678f) list.n = 0;
                 tmem_ld_wait();
             }
@@ -282,10 +284,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         // publish this CTA's per-query partial list
         float *ok = p.part_keys + ((size_t)blockIdx.x * BM + row) * p.k;
         uint32_t *oi = p.part_ids + ((size_t)blockIdx.x * BM + row) * p.k;
-        for (int j = 0; j < p.k; j++) {
-            ok[j] = j < list.n ? list.keys[j * EPI_THREADS] : FLT_MAX;
-            oi[j] = j < list.n ? list.ids[j * EPI_THREADS] : kNoId;
-        }
+        list_publish(list, ok, oi);
     }
 
     tc_fence_before();
@@ -300,10 +299,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 }
 
 template <int CG>
-static cudaError_t launch_cg(const CUtensorMap &map_q, const CUtensorMap &map_c, const GemmTopkParams &p, int grid,
+static cudaError_t launch_cg(const CUtensorMap &map_q, const CUtensorMap &map_c, const GemmTopkParams &p_in, int grid,
                              cudaStream_t s) {
-    size_t smem = Cfg<CG>::OFF_LIST + SMEM_ALIGN_SLACK;
-    if (p.k <= kGemmSmemK) smem += (size_t)p.k * EPI_THREADS * 8;
+    GemmTopkParams p = p_in;
+    const int k_smem = p.k <= kGemmSmemK ? p.k : 0;
+    p.stages = Cfg<CG>::stages_for(k_smem);
+    const size_t smem = (size_t)Cfg<CG>::off_list(p.stages) + (size_t)k_smem * EPI_THREADS * 8 + SMEM_ALIGN_SLACK;
     cudaError_t e = cudaFuncSetAttribute(gemm_topk_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};

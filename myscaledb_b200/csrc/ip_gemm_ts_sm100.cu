@@ -32,7 +32,8 @@ struct TsCfg {
     static constexpr int OFF_B = 0;
     static constexpr int OFF_SIDE = OFF_B + STAGES * STAGE_BYTES;   // scale[TBN], bias[TBN]
     static constexpr int OFF_BAR = OFF_SIDE + 2 * TBN * 4;
-    static constexpr int OFF_LIST = OFF_BAR + 512;
+    static constexpr int OFF_SCRATCH = OFF_BAR + 512;
+    static constexpr int OFF_LIST = OFF_SCRATCH + SCRATCH_BYTES;
 };
 
 __device__ __forceinline__ void umma_ts_cg2(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
@@ -232,9 +233,11 @@ gemm_topk_ts_kernel(const __grid_constant__ CUtensorMap map_c, const GemmTopkPar
         const int row = quarter * 32 + lane;
         const int et = threadIdx.x - 64;
         const bool use_side = p.row_scale || p.row_bias || p.alive || p.scale_const != -1.f;
+        float *scratch = reinterpret_cast<float *>(smem + C::OFF_SCRATCH) + et;
         ThreadTopK list;
         list.k = p.k;
         list.n = 0;
+        list.worst = 0;
         list.thr_key = FLT_MAX;
         list.thr_id = 0;
         if (p.k <= kGemmSmemK) {
@@ -273,12 +276,12 @@ gemm_topk_ts_kernel(const __grid_constant__ CUtensorMap map_c, const GemmTopkPar
                     __syncwarp();
                     tmem_ld32_issue(taddr + (chunk + 1) * 32, vb);
                     epilogue_chunk(list, va, use_side, side_scale + chunk * 32, side_bias + chunk * 32,
-                                   (uint32_t)(n0 + chunk * 32), tail, p.n);
+                                   (uint32_t)(n0 + chunk * 32), tail, p.n, scratch);
                     tmem_ld_wait();
                     __syncwarp();
                     if (chunk + 2 < TBN / 32) tmem_ld32_issue(taddr + (chunk + 2) * 32, va);
                     epilogue_chunk(list, vb, use_side, side_scale + (chunk + 1) * 32, side_bias + (chunk + 1) * 32,
-                                   (uint32_t)(n0 + (chunk + 1) * 32), tail, p.n);
+                                   (uint32_t)(n0 + (chunk + 1) * 32), tail, p.n, scratch);
                     tmem_ld_wait();
                 }
             }
@@ -295,10 +298,7 @@ gemm_topk_ts_kernel(const __grid_constant__ CUtensorMap map_c, const GemmTopkPar
         }
         float *ok = p.part_keys + ((size_t)blockIdx.x * BM + row) * p.k;
         uint32_t *oi = p.part_ids + ((size_t)blockIdx.x * BM + row) * p.k;
-        for (int j = 0; j < p.k; j++) {
-            ok[j] = j < list.n ? list.keys[j * EPI_THREADS] : FLT_MAX;
-            oi[j] = j < list.n ? list.ids[j * EPI_THREADS] : kNoId;
-        }
+        list_publish(list, ok, oi);
     }
 
     tc_fence_before();

@@ -68,6 +68,7 @@ struct GemmTopkParams {
     int q_tiles;               // nq_pad / 128
     int cta_group;             // 1: one CTA per MMA; 2: CTA pairs (cluster of 2), q_tiles must be even
     int *progress;             // [grid / q_tiles][q_tiles] zeroed pacing counters, or null
+    int stages;                // smem ring depth (filled in by the launcher)
     int debug;                 // experiments only (B200_GEMM_DEBUG): 1 no epilogue, 2 TMEM loads only, 4 no TMA
     int sync_slack;            // tiles a CTA may run ahead of the slowest sharer of its corpus tiles
 };
