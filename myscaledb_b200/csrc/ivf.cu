@@ -554,7 +554,7 @@ static int kmeans_device(const float *x, int64_t n, int64_t stride, int d, int n
     gather_rows_kernel<<<gridsz((int64_t)nc * d), 256, 0, s>>>(x, stride, d_pick, nc, d, d_c);
     g_launches++;
     for (int it = 0; it < iters; it++) {
-        rows_sqnorm_kernel<<<gridsz(nc), 256, 0, s>>>(d_c, nc, d, d_cn);
+        rows_sqnorm_kernel<<<(unsigned)ceil_div(nc, 256), 256, 0, s>>>(d_c, nc, d, d_cn);
         kmeans_assign_kernel<<<(unsigned)ceil_div(n, KA_T), 256, 0, s>>>(x, n, stride, d, d_c, nc, d_cn, d_idx, nullptr);
         B200_CUDA_OK(cudaMemsetAsync(d_sums, 0, (size_t)nc * d * 4, s));
         B200_CUDA_OK(cudaMemsetAsync(d_cnt, 0, (size_t)nc * 4, s));
@@ -628,9 +628,9 @@ extern "C" int b200_index_build(b200_index *ix, const float *rows, int64_t n) {
     B200_CUDA_OK(cudaMalloc(&d_list_sorted, (size_t)n * 4));
     B200_CUDA_OK(cudaMalloc(&ix->d_list_ids, (size_t)n * 4));
     B200_CUDA_OK(cudaMalloc(&d_cn, (size_t)nl * 4));
-    rows_sqnorm_kernel<<<gridsz(nl), 256, 0, s>>>(ix->d_centroids, nl, d, d_cn);
+    rows_sqnorm_kernel<<<(unsigned)ceil_div(nl, 256), 256, 0, s>>>(ix->d_centroids, nl, d, d_cn);
     kmeans_assign_kernel<<<(unsigned)ceil_div(n, KA_T), 256, 0, s>>>(x, n, stride, d, ix->d_centroids, nl, d_cn, d_list, nullptr);
-    iota_kernel<<<gridsz(n), 256, 0, s>>>(d_rows_in, n);
+    iota_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(d_rows_in, n);  // one thread per row (not grid-stride)
     g_launches += 3;
     {
         size_t tmp_bytes = 0;
@@ -678,7 +678,7 @@ extern "C" int b200_index_build(b200_index *ix, const float *rows, int64_t n) {
         B200_CUDA_OK(cudaMalloc(&d_code, (size_t)n * 4));
         B200_CUDA_OK(cudaMalloc(&d_res, (size_t)n * dsub * 4));
         B200_CUDA_OK(cudaMalloc(&d_cbn, 256 * 4));
-        invert_perm_kernel<<<gridsz(n), 256, 0, s>>>(ix->d_list_ids, n, d_pos);
+        invert_perm_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(ix->d_list_ids, n, d_pos);
         g_launches++;
         const int64_t ns = std::min<int64_t>(n, 65536);
         for (int j = 0; j < m; j++) {
@@ -690,7 +690,7 @@ extern "C" int b200_index_build(b200_index *ix, const float *rows, int64_t n) {
             B200_TRY(kmeans_device(d_res, ns, step * dsub, dsub, 256, 8, cb, s));
             rows_sqnorm_kernel<<<1, 256, 0, s>>>(cb, 256, dsub, d_cbn);
             kmeans_assign_kernel<<<(unsigned)ceil_div(n, KA_T), 256, 0, s>>>(d_res, n, dsub, dsub, cb, 256, d_cbn, d_code, nullptr);
-            scatter_codes_kernel<<<gridsz(n), 256, 0, s>>>(d_code, d_pos, n, m, j, ix->d_codes);
+            scatter_codes_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(d_code, d_pos, n, m, j, ix->d_codes);
             g_launches += 3;
         }
         B200_CUDA_OK(cudaGetLastError());

@@ -115,3 +115,21 @@ def test_golden_00028_mstg_small_part_falls_back_to_exact(goldens):
     alive = np.ones(1000, bool); alive[0] = False; alive[2] = False
     dis, ids = ic.search(q, 5, alive_bits=orc.pack_bits(alive))
     assert ids[0].tolist() == [e[0] for e in g["expect_cosine_after_delete_id2"]]
+
+
+def test_index_above_one_grid_of_rows_regression():
+    """n larger than one capped launch grid (148*32*256 = 1.2M threads): the per-row build kernels must
+    cover every row (caught by tools/bench_aux.py: recall collapsed at 5M rows)."""
+    rng = np.random.default_rng(12)
+    n, d = 1_500_000, 16
+    centres = rng.standard_normal((2000, d)).astype(F32)
+    y = centres[rng.integers(0, 2000, n)] + 0.2 * rng.standard_normal((n, d)).astype(F32)
+    q = centres[rng.integers(0, 2000, 32)] + 0.2 * rng.standard_normal((32, d)).astype(F32)
+    flat = b2.Corpus(b2.L2, d).append(y)
+    dt, it = flat.search(q, 10)
+    ix = b2.VectorIndex("MSTG", b2.L2, d, "ncentroids=512, M=8").build(y)
+    dg, ig = ix.search(q, 10, "nprobe=64, refine_factor=16")
+    assert _recall(ig, it) >= 0.95
+    iv = b2.VectorIndex("IVFFLAT", b2.L2, d, "ncentroids=256").build(y)
+    d2, i2 = iv.search(q, 10, "nprobe=256")
+    check_topk(b2.L2, q, y, d2, i2, dt, it, rtol=2e-4, atol=2e-5, min_exact=0.99)
