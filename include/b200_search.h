@@ -160,6 +160,22 @@ int b200_index_refine(b200_index *ix, const float *queries, int64_t nq, const in
 int b200_index_free(b200_index *ix);
 
 /* ------------------------------------------------------------------------------------
+ * Filter bitmaps and decoupled-part row-id maps (VIWithMeta::{row_ids_map, inverted_row_ids_map,
+ * inverted_row_sources_map}, VectorIndex/Cache/VICacheObject.h:40-117).
+ * ---------------------------------------------------------------------------------- */
+/* Search::intersectDenseBitmaps (VIWithDataPart.cpp:908): out = a & b */
+int b200_bitmap_and(const uint8_t *a, const uint8_t *b, int64_t nbits, uint8_t *out);
+/* getRealBitmap (VectorIndex/Utils/VIUtils.cpp:479-497): filter over the merged part -> bitmap over this old part */
+int b200_real_bitmap(const uint8_t *filter_bits, int64_t n_new_rows, const uint64_t *inverted_row_ids_map,
+                     const uint8_t *inverted_row_sources_map, uint32_t own_id, int64_t total_vec, uint8_t *out_bits);
+/* VIWithColumnInPart::transferToNewRowIds (VIWithDataPart.cpp:56-68), in place */
+int b200_remap_labels(const uint64_t *row_ids_map, int64_t map_len, int64_t *labels, int64_t n);
+/* VIWithColumnInPart::TransferToOldRowIds (VIWithDataPart.cpp:69-126): order-preserving filter + map */
+int b200_transfer_to_old_row_ids(const int64_t *new_ids, const float *new_dis, int64_t num_candidates,
+                                 const uint64_t *inverted_row_ids_map, const uint8_t *inverted_row_sources_map, int64_t map_len,
+                                 uint32_t own_id, int64_t *out_ids, float *out_dis, int64_t *out_n);
+
+/* ------------------------------------------------------------------------------------
  * BM25 full-text search (Boundary B).  Replaces the TANTIVY::ffi_* calls of TantivyIndexStore
  * (Storages/MergeTree/TantivyIndexStore.cpp): ffi_index_multi_column_docs :742,
  * ffi_index_writer_commit :824, ffi_bm25_search :908/:939, ffi_get_doc_freq :962,

@@ -344,3 +344,37 @@ class VectorIndex:
             self.close()
         except Exception:
             pass
+
+
+def bitmap_and(a, b, nbits):
+    a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
+    out = np.zeros((nbits + 7) // 8, np.uint8)
+    _check(lib().b200_bitmap_and(_p(a, C.c_uint8), _p(b, C.c_uint8), C.c_int64(nbits), _p(out, C.c_uint8)))
+    return out
+
+
+def real_bitmap(filter_bits, n_new_rows, inverted_row_ids_map, inverted_row_sources_map, own_id, total_vec):
+    f = np.ascontiguousarray(filter_bits, np.uint8)
+    ids = np.ascontiguousarray(inverted_row_ids_map, np.uint64)
+    src = np.ascontiguousarray(inverted_row_sources_map, np.uint8)
+    out = np.zeros((total_vec + 7) // 8, np.uint8)
+    _check(lib().b200_real_bitmap(_p(f, C.c_uint8), C.c_int64(n_new_rows), _p(ids, C.c_uint64), _p(src, C.c_uint8),
+                                  C.c_uint32(own_id), C.c_int64(total_vec), _p(out, C.c_uint8)))
+    return out
+
+
+def remap_labels(row_ids_map, labels):
+    m = np.ascontiguousarray(row_ids_map, np.uint64)
+    l = np.ascontiguousarray(labels, np.int64).copy()
+    _check(lib().b200_remap_labels(_p(m, C.c_uint64), C.c_int64(m.size), _p(l, C.c_int64), C.c_int64(l.size)))
+    return l
+
+
+def transfer_to_old_row_ids(new_ids, new_dis, inverted_row_ids_map, inverted_row_sources_map, own_id):
+    ids = np.ascontiguousarray(new_ids, np.int64); dis = np.ascontiguousarray(new_dis, np.float32)
+    m = np.ascontiguousarray(inverted_row_ids_map, np.uint64); src = np.ascontiguousarray(inverted_row_sources_map, np.uint8)
+    o_i = np.empty(ids.size, np.int64); o_d = np.empty(ids.size, np.float32); n = C.c_int64()
+    _check(lib().b200_transfer_to_old_row_ids(_p(ids, C.c_int64), _p(dis, C.c_float), C.c_int64(ids.size), _p(m, C.c_uint64),
+                                              _p(src, C.c_uint8), C.c_int64(m.size), C.c_uint32(own_id), _p(o_i, C.c_int64),
+                                              _p(o_d, C.c_float), C.byref(n)))
+    return o_i[:n.value], o_d[:n.value]
