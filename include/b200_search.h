@@ -157,6 +157,10 @@ int b200_index_search(b200_index *ix, const float *queries, int64_t nq, int k, c
 /* computeTopDistanceSubset: exact distances of candidate ids [nq][ncand] (negative = unused) -> top-k */
 int b200_index_refine(b200_index *ix, const float *queries, int64_t nq, const int64_t *cand_ids, int64_t ncand, int k,
                       float *out_dis, int64_t *out_ids);
+/* VIWithColumnInPart::serialize / load (VIWithDataPart.cpp:451-525, :578-764): one self-describing file
+ * ("B2IX" v1; the closed library's .vidx3 payload cannot be reproduced). */
+int b200_index_save(b200_index *ix, const char *path);
+int b200_index_load(const char *path, b200_index **out);
 int b200_index_free(b200_index *ix);
 
 /* ------------------------------------------------------------------------------------

@@ -894,3 +894,130 @@ extern "C" int b200_index_refine(b200_index *ix, const float *queries, int64_t n
     B200_CUDA_OK(cudaStreamSynchronize(s));
     return B200_OK;
 }
+
+// ------------------------------------------------------------------------------------
+// persistence: VIWithColumnInPart::serialize / load (reference: src/VectorIndex/Common/VIWithDataPart.cpp:451-525,
+// :578-764) write `<idx>-*.vidx3` through Search::IndexDataFileWriter; the on-disk format of the closed library
+// is not reproducible, so this is our own single-file layout ("B2IX" v1): header, raw rows, then the IVF/PQ
+// structures.  Loading re-uploads to HBM and recomputes the row norms on device.
+// ------------------------------------------------------------------------------------
+#include <cstdio>
+
+namespace {
+struct IxHeader {
+    char magic[4];
+    uint32_t version;
+    int32_t type, metric, d, d_pad, nlist, m, dsub, default_nprobe, refine_factor, use_ivf;
+    int64_t n;
+};
+bool wr(FILE *f, const void *p, size_t bytes) { return bytes == 0 || fwrite(p, 1, bytes, f) == bytes; }
+bool rd(FILE *f, void *p, size_t bytes) { return bytes == 0 || fread(p, 1, bytes, f) == bytes; }
+}  // namespace
+
+extern "C" int b200_index_save(b200_index *ix, const char *path) {
+    if (!ix || !path) return fail(B200_ERR_INVALID, "bad arguments");
+    if (!ix->built) return fail(B200_ERR_INVALID, "index not built");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    B200_CUDA_OK(cudaSetDevice(ix->device));
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(B200_ERR_INVALID, std::string("cannot open ") + path);
+    IxHeader h{};
+    memcpy(h.magic, "B2IX", 4);
+    h.version = 1;
+    h.type = ix->type; h.metric = ix->metric; h.d = ix->d; h.d_pad = ix->d_pad; h.nlist = ix->nlist; h.m = ix->m; h.dsub = ix->dsub;
+    h.default_nprobe = ix->default_nprobe; h.refine_factor = ix->refine_factor; h.use_ivf = ix->use_ivf ? 1 : 0; h.n = ix->n;
+    bool ok = wr(f, &h, sizeof(h));
+    // raw rows, unpadded (cosine indexes hold unit vectors; they are written as stored)
+    {
+        const int64_t chunk = std::max<int64_t>(1, (64ll << 20) / ((int64_t)ix->d_pad * 4));
+        std::vector<float> buf((size_t)chunk * ix->d_pad);
+        const float *rows = reinterpret_cast<const float *>(corpus_device_rows(ix->raw));
+        for (int64_t off = 0; ok && off < ix->n; off += chunk) {
+            const int64_t mrows = std::min(chunk, ix->n - off);
+            if (cudaMemcpy(buf.data(), rows + off * ix->d_pad, (size_t)mrows * ix->d_pad * 4, cudaMemcpyDeviceToHost) != cudaSuccess) ok = false;
+            for (int64_t r = 0; ok && r < mrows; r++) ok = wr(f, buf.data() + r * ix->d_pad, (size_t)ix->d * 4);
+        }
+    }
+    if (ok && ix->use_ivf) {
+        std::vector<char> tmp;
+        auto dump = [&](const void *dptr, size_t bytes) {
+            tmp.resize(bytes);
+            if (bytes && cudaMemcpy(tmp.data(), dptr, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+            return wr(f, tmp.data(), bytes);
+        };
+        ok = dump(ix->d_centroids, (size_t)ix->nlist * ix->d * 4) && wr(f, ix->list_off.data(), (size_t)(ix->nlist + 1) * 4) &&
+             dump(ix->d_list_ids, (size_t)ix->n * 4);
+        if (ok && ix->d_pq) ok = dump(ix->d_pq, (size_t)ix->m * 256 * ix->dsub * 4) && dump(ix->d_codes, (size_t)ix->n * ix->m);
+    }
+    ok = (fclose(f) == 0) && ok;
+    return ok ? B200_OK : fail(B200_ERR_INVALID, std::string("write failed: ") + path);
+}
+
+extern "C" int b200_index_load(const char *path, b200_index **out) {
+    if (!path || !out) return fail(B200_ERR_INVALID, "bad arguments");
+    *out = nullptr;
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(B200_ERR_INVALID, std::string("cannot open ") + path);
+    IxHeader h{};
+    if (!rd(f, &h, sizeof(h)) || memcmp(h.magic, "B2IX", 4) != 0 || h.version != 1) {
+        fclose(f);
+        return fail(B200_ERR_INVALID, "not a B2IX v1 index file");
+    }
+    static const char *names[] = {"FLAT", "IVFFLAT", "IVFPQ", "MSTG"};
+    if (h.type < 0 || h.type > 3) {
+        fclose(f);
+        return fail(B200_ERR_INVALID, "corrupt index header");
+    }
+    b200_index *ix = nullptr;
+    int rc = b200_index_create(names[h.type], h.metric, h.d, "", &ix);
+    if (rc != B200_OK) {
+        fclose(f);
+        return rc;
+    }
+    ix->nlist = h.nlist; ix->m = h.m; ix->dsub = h.dsub; ix->default_nprobe = h.default_nprobe; ix->refine_factor = h.refine_factor;
+    ix->use_ivf = h.use_ivf != 0; ix->n = h.n;
+    auto bail = [&](const std::string &msg) {
+        fclose(f);
+        b200_index_free(ix);
+        return fail(B200_ERR_INVALID, msg);
+    };
+    const int raw_metric = h.metric == B200_METRIC_L2 ? B200_METRIC_L2 : B200_METRIC_IP;
+    if (b200_corpus_create(raw_metric, B200_DTYPE_F32, h.d, h.n, &ix->raw) != B200_OK) return bail(b200_last_error());
+    {
+        const int64_t chunk = std::max<int64_t>(1, (64ll << 20) / ((int64_t)h.d * 4));
+        std::vector<float> buf((size_t)chunk * h.d);
+        for (int64_t off = 0; off < h.n; off += chunk) {
+            const int64_t mrows = std::min(chunk, h.n - off);
+            if (!rd(f, buf.data(), (size_t)mrows * h.d * 4)) return bail("truncated index file (rows)");
+            if (b200_corpus_append(ix->raw, buf.data(), mrows) != B200_OK) return bail(b200_last_error());
+        }
+    }
+    if (ix->use_ivf) {
+        std::vector<char> tmp;
+        auto slurp = [&](void **dptr, size_t bytes) {
+            tmp.resize(bytes);
+            if (!rd(f, tmp.data(), bytes)) return false;
+            if (cudaMalloc(dptr, bytes + 256) != cudaSuccess) return false;
+            return cudaMemcpy(*dptr, tmp.data(), bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+        };
+        ix->list_off.resize(h.nlist + 1);
+        if (!slurp((void **)&ix->d_centroids, (size_t)h.nlist * h.d * 4) || !rd(f, ix->list_off.data(), (size_t)(h.nlist + 1) * 4) ||
+            !slurp((void **)&ix->d_list_ids, (size_t)h.n * 4))
+            return bail("truncated index file (lists)");
+        if (cudaMalloc(&ix->d_list_off, (size_t)(h.nlist + 1) * 4) != cudaSuccess ||
+            cudaMemcpy(ix->d_list_off, ix->list_off.data(), (size_t)(h.nlist + 1) * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail("cudaMalloc failed");
+        if (h.type == IDX_IVFPQ || h.type == IDX_MSTG)
+            if (!slurp((void **)&ix->d_pq, (size_t)h.m * 256 * h.dsub * 4) || !slurp((void **)&ix->d_codes, (size_t)h.n * h.m))
+                return bail("truncated index file (codes)");
+        std::vector<float> hc((size_t)h.nlist * h.d);
+        if (cudaMemcpy(hc.data(), ix->d_centroids, hc.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return bail("D2H failed");
+        if (b200_corpus_create(B200_METRIC_L2, B200_DTYPE_F32, h.d, h.nlist, &ix->coarse) != B200_OK ||
+            b200_corpus_append(ix->coarse, hc.data(), h.nlist) != B200_OK)
+            return bail(b200_last_error());
+    }
+    fclose(f);
+    ix->built = true;
+    *out = ix;
+    return B200_OK;
+}
