@@ -324,6 +324,17 @@ class VectorIndex:
         self.last_num_candidates = nc.value
         return dis, ids
 
+    def save(self, path):
+        _check(lib().b200_index_save(self._h, str(path).encode()))
+
+    @classmethod
+    def load(cls, path, d):
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        self.d = d
+        _check(lib().b200_index_load(str(path).encode(), C.byref(self._h)))
+        return self
+
     def refine(self, queries, cand_ids, k):
         q = np.ascontiguousarray(queries, np.float32)
         c = np.ascontiguousarray(cand_ids, np.int64)

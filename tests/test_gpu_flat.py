@@ -225,3 +225,27 @@ def test_topk_merge_device_matches_oracle_merge():
             order = np.lexsort((lab, -sc if desc else sc))[:k]
             assert oi[q].cpu().numpy().tolist() == lab[order].tolist()
             np.testing.assert_array_equal(od[q].cpu().numpy(), sc[order])
+
+
+def test_concurrent_searches_are_reentrant():
+    """ClickHouse calls the library from one ThreadPool worker per part, concurrently."""
+    import threading
+    rng = np.random.default_rng(77)
+    parts = [rng.standard_normal((20000, 64)).astype(F32) for _ in range(4)]
+    x = rng.standard_normal((6, 64)).astype(F32)
+    shared = b2.Corpus(b2.L2, 64).append(parts[0])
+    expect = [orc.knn_flat(orc.L2, x, p, 10) for p in parts]
+    errors = []
+
+    def worker(i):
+        try:
+            for _ in range(5):
+                dg, ig = b2.flat_knn(b2.L2, x, parts[i], 10)          # own temporary corpus
+                check_topk(b2.L2, x, parts[i], dg, ig, *expect[i])
+                dg, ig = shared.search(x, 10)                         # one index shared by all threads
+                check_topk(b2.L2, x, parts[0], dg, ig, *expect[0])
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    assert not errors, errors

@@ -133,3 +133,26 @@ def test_index_above_one_grid_of_rows_regression():
     iv = b2.VectorIndex("IVFFLAT", b2.L2, d, "ncentroids=256").build(y)
     d2, i2 = iv.search(q, 10, "nprobe=256")
     check_topk(b2.L2, q, y, d2, i2, dt, it, rtol=2e-4, atol=2e-5, min_exact=0.99)
+
+
+def test_serialize_load_roundtrip_and_golden_00001_after_reload(goldens, tmp_path):
+    """00001 runs the query again after DETACH/ATTACH (index deserialised from disk): same answer."""
+    g = goldens["00001_flat_l2"]
+    y = np.repeat(np.arange(100, dtype=F32)[:, None], 3, axis=1)
+    ix = b2.VectorIndex("FLAT", b2.L2, 3).build(y)
+    ix.save(tmp_path / "flat.b2ix")
+    re = b2.VectorIndex.load(tmp_path / "flat.b2ix", 3)
+    dis, ids = re.search(np.array([g["query"]], F32), g["k"])
+    assert ids[0].tolist() == [e[0] for e in g["expect_after_reload"]]
+    np.testing.assert_allclose(dis[0], [e[1] for e in g["expect_after_reload"]], rtol=1e-6)
+    # IVFPQ two-stage index: identical results before and after the round trip
+    yy, q = _clustered(40000, 64, 300, 21)
+    a = b2.VectorIndex("MSTG", b2.COSINE, 64, "ncentroids=64, M=16").build(yy)
+    d0, i0 = a.search(q, 10, "nprobe=16")
+    a.save(tmp_path / "mstg.b2ix")
+    b = b2.VectorIndex.load(tmp_path / "mstg.b2ix", 64)
+    assert b.info() == a.info()
+    d1, i1 = b.search(q, 10, "nprobe=16")
+    assert (i0 == i1).all() and np.array_equal(d0, d1)
+    with pytest.raises(b2.B200Error):
+        b2.VectorIndex.load(tmp_path / "missing.b2ix", 64)
