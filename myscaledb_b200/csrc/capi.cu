@@ -105,6 +105,7 @@ struct b200_corpus {
     // workspaces
     DevBuf w_raw, w_q32, w_qbf, w_qnorm, w_pk, w_pi, w_lk, w_li, w_alive, w_odis, w_oids, w_stage, w_prog;
     int sync_slack = 2;
+    int gemm_multicast = 1;  // clusters of two CTA pairs sharing the corpus tile (B200_GEMM_MULTICAST=0 disables)
     int gemm_ts = 0;  // 0 streaming (default: faster at every measured d), 1 TS when d_pad <= 512, 2 TS whenever it fits
     // optional CUDA-event timing of the dominant kernel (scan or GEMM) for the roofline report
     bool timing = false;
@@ -201,6 +202,7 @@ extern "C" int b200_corpus_create(int metric, int dtype, int d, int64_t capacity
     c->sms = num_sms();
     if (const char *ev = getenv("B200_GEMM_SYNC_SLACK")) c->sync_slack = atoi(ev);
     if (const char *ev = getenv("B200_GEMM_TS")) c->gemm_ts = atoi(ev);
+    if (const char *ev = getenv("B200_GEMM_MULTICAST")) c->gemm_multicast = atoi(ev);
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete c;
@@ -311,7 +313,7 @@ extern "C" int b200_corpus_set_path(b200_corpus *c, int path) {
     if (!c || path < 0 || path > 4) return fail(B200_ERR_INVALID, "path must be 0..4");
     c->path = path >= 3 ? 2 : path;
     c->gemm_cta_group = path == 3 ? 1 : 0;
-    if (path == 4) c->gemm_ts = 0;
+    if (path == 4) { c->gemm_ts = 0; c->gemm_multicast = 0; }
     if (path == 2) c->gemm_ts = 2;
     return B200_OK;
 }
@@ -499,7 +501,17 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
                                           c->w_qnorm.as<float>(), s));
             q_add = c->w_qnorm.as<float>();
         }
+        // two pairs per cluster share every corpus tile through TMA multicast when the query tiles allow it
+        int pairs = (cta_group == 2 && q_tiles % 4 == 0 && c->gemm_multicast) ? 2 : 1;
         int grid = gemm_topk_grid(q_tiles, c->n, sms);
+        if (pairs == 2) {
+            // persistent + paced kernel: never launch more clusters than can be co-resident
+            const int maxc = gemm_topk_max_clusters(2, 2, k);
+            const int groups = q_tiles / 4;
+            const int per_group = maxc / groups;
+            if (per_group < 1) pairs = 1;
+            else grid = std::min(grid, per_group * groups * 4);
+        }
         grid = (grid / q_tiles) * q_tiles;
         if (grid < q_tiles) grid = q_tiles;
         B200_TRY(c->w_pk.reserve((size_t)grid * 128 * k * 4));
@@ -525,6 +537,7 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
         gp.k = k;
         gp.q_tiles = q_tiles;
         gp.cta_group = cta_group;
+        gp.pairs_per_cluster = pairs;
         if (const char *dv = getenv("B200_GEMM_DEBUG")) gp.debug = atoi(dv);
         if (q_tiles > cta_group && c->sync_slack > 0) {
             B200_TRY(c->w_prog.reserve((size_t)grid * 4));

@@ -91,15 +91,16 @@ __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanPa
     const unsigned char *base = reinterpret_cast<const unsigned char *>(p.corpus);
 
     for (int64_t it = 0;; it++) {
-        const int64_t row0 = gidx + it * U * total_groups;
+        // a group owns U CONSECUTIVE rows per step (one contiguous U * row_bytes span: DRAM-page friendly)
+        const int64_t row0 = (gidx + it * total_groups) * U;
         // warp-uniform exit: the smallest row of this step over the warp is for sub == 0
-        if (row0 - sub >= p.n) break;
+        if (row0 - (int64_t)sub * U >= p.n) break;
         float acc[U][QT];
         bool valid[U];
         const uint4 *rp[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const int64_t row = row0 + (int64_t)u * total_groups;
+            const int64_t row = row0 + u;
             valid[u] = row < p.n;
             if (valid[u] && p.alive) valid[u] = (p.alive[row >> 3] >> (row & 7)) & 1;
             rp[u] = reinterpret_cast<const uint4 *>(base + (size_t)(valid[u] ? row : 0) * p.row_bytes);
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanPa
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const int64_t row = row0 + (int64_t)u * total_groups;
+            const int64_t row = row0 + u;
             float scale = 1.f;
             if (!L2) scale = (p.row_scale && valid[u]) ? p.row_scale[row] : -1.f;
 #pragma unroll

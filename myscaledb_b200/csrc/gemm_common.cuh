@@ -93,6 +93,16 @@ __device__ __forceinline__ void tma_load_2d_cg2(const CUtensorMap *map, uint64_t
         : "memory");
 }
 
+// 2-CTA + multicast: the box is written at the same CTA-relative offset in every CTA of cta_mask and
+// completes bytes on the mbarrier at `bar`'s offset in the LEADER of each destination's pair.
+__device__ __forceinline__ void tma_load_2d_cg2_mc(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -167,9 +177,8 @@ __device__ __forceinline__ void umma_cg2(uint32_t tmem_d, uint64_t adesc, uint64
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
-// arrive (once all prior MMAs retire) on the barrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_cg2(uint64_t *bar) {
-    const uint16_t mask = 3;
+// arrive (once all prior MMAs retire) on the barrier at this offset in every CTA of `mask` (cluster ranks)
+__device__ __forceinline__ void umma_commit_cg2(uint64_t *bar, uint16_t mask = 3) {
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
             smem_u32(bar)),

@@ -34,7 +34,10 @@
 namespace b200 {
 namespace gemm {
 
-template <int CG>
+// MC = CTA pairs per cluster that consume the SAME corpus tile (different query tiles): the tile is
+// fetched from L2 once per cluster, each CTA loading 1/MC of its half and multicasting it.  The
+// measured limiter of the MC = 1 form is L2->SM bandwidth (~9.8 TB/s, profiles/r01_summary.md).
+template <int CG, int MC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
                  const GemmTopkParams p) {
@@ -53,8 +56,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + ACC_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;
-    const bool is_leader = cta_rank == 0;
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;   // 0 .. CG * MC - 1
+    const uint32_t half = cta_rank & 1;                           // which half of the pair's M = 256 / N = 256
+    const uint32_t pair_in_cluster = cta_rank >> 1;
+    const uint32_t leader_rank = cta_rank & ~1u;
+    const bool is_leader = half == 0;                             // leader of its pair: issues the MMAs
+    const bool paces = cta_rank == 0;                             // one CTA per cluster talks to the pacing counters
 
     // tile schedule: a CTA (CG=1) or CTA pair (CG=2) owns CG query tiles for its whole life and
     // walks the corpus tiles worker, worker + W, ...  (blockIdx = worker * q_tiles + qt)
@@ -69,7 +76,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_c)) : "memory");
         for (int i = 0; i < STAGES; i++) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            mbar_init(&empty_bar[i], MC);  // one commit per pair whose operands live in (or were sent from) this CTA
         }
         for (int i = 0; i < ACC_STAGES; i++) {
             mbar_init(&tmem_full_bar[i], 1);
@@ -109,13 +116,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             // bytes, profiles/r01_*).  Only pacing, no data dependency: plain volatile counters.
             // Bounded wait (~50 us): if the sharers are not co-resident (another kernel holds SMs)
             // pacing is dropped instead of risking a co-residency deadlock.
-            if (pacing && is_leader) {
+            if (pacing && paces) {
                 int ok = 1;
                 if (lane == 0) {
                     volatile int *prog = p.progress + (size_t)worker * p.q_tiles;
                     prog[qt] = ordinal + 1;
                     int spins = 0;
-                    for (int g = 0; g < p.q_tiles; g += CG)
+                    for (int g = 0; g < p.q_tiles; g += CG * MC)
                         while (prog[g] < ordinal + 1 - p.sync_slack && spins < 256) {
                             __nanosleep(200);
                             spins++;
@@ -138,8 +145,19 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     } else {
                         if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], C::TX_BYTES);
                         tma_load_2d_cg2(&map_q, &full_bar[stage], sA + stage * A_BYTES, kb * BK, qt * BM);
-                        tma_load_2d_cg2(&map_c, &full_bar[stage], sB + stage * C::B_BYTES, kb * BK,
-                                        (int)(t * BN + cta_rank * C::B_ROWS));
+                        if (MC == 1) {
+                            tma_load_2d_cg2(&map_c, &full_bar[stage], sB + stage * C::B_BYTES, kb * BK,
+                                            (int)(t * BN + half * C::B_ROWS));
+                        } else {
+                            // this CTA fetches slice `pair_in_cluster` of its half and multicasts it to the CTAs of
+                            // the same half in every pair of the cluster (ranks half, half + 2, ...)
+                            constexpr int SLICE_ROWS = C::B_ROWS / MC;
+                            uint16_t mask = 0;
+                            for (int pp = 0; pp < MC; pp++) mask |= (uint16_t)(1u << (pp * 2 + half));
+                            tma_load_2d_cg2_mc(&map_c, &full_bar[stage],
+                                               sB + stage * C::B_BYTES + pair_in_cluster * (SLICE_ROWS * BK * 2), kb * BK,
+                                               (int)(t * BN + half * C::B_ROWS + pair_in_cluster * SLICE_ROWS), mask);
+                        }
                     }
                 }
                 __syncwarp();
@@ -176,10 +194,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                             else umma_cg2(tmem_d, adesc + k * (UMMA_K * 2 >> 4), bdesc + k * (UMMA_K * 2 >> 4), idesc, acc);
                         }
                         // smem slot free (in both CTAs) once these MMAs retire
-                        if (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_cg2(&empty_bar[stage]);
+                        if (CG == 1) umma_commit(&empty_bar[stage]);
+                        else umma_commit_cg2(&empty_bar[stage], (uint16_t)((1u << (CG * MC)) - 1));  // every CTA of the cluster
                         // accumulator ready for the epilogue (of both CTAs)
                         if (kb == kb_count - 1) {
-                            if (CG == 1) umma_commit(&tmem_full_bar[as]); else umma_commit_cg2(&tmem_full_bar[as]);
+                            if (CG == 1) umma_commit(&tmem_full_bar[as]);
+                            else umma_commit_cg2(&tmem_full_bar[as], (uint16_t)(3u << leader_rank));  // own pair
                         }
                     }
                     __syncwarp();
@@ -241,7 +261,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 __syncwarp();
                 if (lane == 0) {
                     if (CG == 1 || is_leader) mbar_arrive(&tmem_empty_bar[as]);
-                    else mbar_arrive_remote(&tmem_empty_bar[as], 0);
+                    else mbar_arrive_remote(&tmem_empty_bar[as], leader_rank);
                 }
                 if (++as == ACC_STAGES) {
                     as = 0;
@@ -274,7 +294,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             __syncwarp();
             if (lane == 0) {
                 if (CG == 1 || is_leader) mbar_arrive(&tmem_empty_bar[as]);
-                else mbar_arrive_remote(&tmem_empty_bar[as], 0);
+                else mbar_arrive_remote(&tmem_empty_bar[as], leader_rank);
             }
             if (++as == ACC_STAGES) {
                 as = 0;
@@ -298,14 +318,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     }
 }
 
-template <int CG>
+template <int CG, int MC>
 static cudaError_t launch_cg(const CUtensorMap &map_q, const CUtensorMap &map_c, const GemmTopkParams &p_in, int grid,
                              cudaStream_t s) {
     GemmTopkParams p = p_in;
     const int k_smem = p.k <= kGemmSmemK ? p.k : 0;
     p.stages = Cfg<CG>::stages_for(k_smem);
     const size_t smem = (size_t)Cfg<CG>::off_list(p.stages) + (size_t)k_smem * EPI_THREADS * 8 + SMEM_ALIGN_SLACK;
-    cudaError_t e = cudaFuncSetAttribute(gemm_topk_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = gemm_topk_kernel<CG, MC>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
@@ -314,14 +335,41 @@ static cudaError_t launch_cg(const CUtensorMap &map_q, const CUtensorMap &map_c,
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.x = CG * MC;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, gemm_topk_kernel<CG>, map_q, map_c, p);
+    e = cudaLaunchKernelEx(&cfg, kern, map_q, map_c, p);
     g_launches++;
     return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+// how many clusters of CG * MC CTAs of this kernel can be co-resident (persistent grid upper bound)
+template <int CG, int MC>
+static int max_clusters(int k) {
+    const int k_smem = k <= kGemmSmemK ? k : 0;
+    const int stages = Cfg<CG>::stages_for(k_smem);
+    const size_t smem = (size_t)Cfg<CG>::off_list(stages) + (size_t)k_smem * EPI_THREADS * 8 + SMEM_ALIGN_SLACK;
+    auto kern = gemm_topk_kernel<CG, MC>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(CG * MC * 64);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG * MC;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
 }
 
 }  // namespace gemm
@@ -334,20 +382,28 @@ int gemm_topk_grid(int q_tiles, int64_t n, int num_sms) {
     return (int)g;
 }
 
+int gemm_topk_max_clusters(int cta_group, int pairs_per_cluster, int k) {
+    if (cta_group == 2 && pairs_per_cluster == 2) return gemm::max_clusters<2, 2>(k);
+    if (cta_group == 2) return gemm::max_clusters<2, 1>(k);
+    return gemm::max_clusters<1, 1>(k);
+}
+
 cudaError_t launch_gemm_topk(const GemmTopkParams &p, int grid, cudaStream_t s, const char **err_detail) {
     *err_detail = nullptr;
     const int cg = p.cta_group == 2 ? 2 : 1;
-    if (grid % p.q_tiles != 0 || (cg == 2 && (p.q_tiles % 2 != 0))) {
-        *err_detail = "grid must be a multiple of q_tiles (and q_tiles even for cta_group 2)";
+    const int mc = (cg == 2 && p.pairs_per_cluster == 2) ? 2 : 1;
+    if (grid % p.q_tiles != 0 || p.q_tiles % (cg * mc) != 0) {
+        *err_detail = "grid must be a multiple of q_tiles, q_tiles a multiple of the cluster size";
         return cudaErrorInvalidValue;
     }
     CUtensorMap map_q, map_c;
     if (!gemm::encode_rows_map(&map_q, p.queries_bf16, p.nq_pad, p.d_pad, gemm::BM) ||
-        !gemm::encode_rows_map(&map_c, p.corpus_bf16, p.n, p.d_pad, gemm::BN / cg)) {
+        !gemm::encode_rows_map(&map_c, p.corpus_bf16, p.n, p.d_pad, gemm::BN / cg / mc)) {
         *err_detail = "cuTensorMapEncodeTiled failed";
         return cudaErrorInvalidValue;
     }
-    return cg == 2 ? gemm::launch_cg<2>(map_q, map_c, p, grid, s) : gemm::launch_cg<1>(map_q, map_c, p, grid, s);
+    if (mc == 2) return gemm::launch_cg<2, 2>(map_q, map_c, p, grid, s);
+    return cg == 2 ? gemm::launch_cg<2, 1>(map_q, map_c, p, grid, s) : gemm::launch_cg<1, 1>(map_q, map_c, p, grid, s);
 }
 
 }  // namespace b200

@@ -67,6 +67,7 @@ struct GemmTopkParams {
     int nq_pad, d_pad, k;
     int q_tiles;               // nq_pad / 128
     int cta_group;             // 1: one CTA per MMA; 2: CTA pairs (cluster of 2), q_tiles must be even
+    int pairs_per_cluster;     // 1, or 2: two CTA pairs share (TMA-multicast) every corpus tile; q_tiles % 4 == 0
     int *progress;             // [grid / q_tiles][q_tiles] zeroed pacing counters, or null
     int stages;                // smem ring depth (filled in by the launcher)
     int debug;                 // experiments only (B200_GEMM_DEBUG): 1 no epilogue, 2 TMEM loads only, 4 no TMA
@@ -76,6 +77,7 @@ constexpr int kGemmSmemK = 30;
 int gemm_topk_grid(int q_tiles, int64_t n, int num_sms);
 // returns cudaSuccess or an error; tensor maps are encoded inside
 cudaError_t launch_gemm_topk(const GemmTopkParams &p, int grid, cudaStream_t s, const char **err_detail);
+int gemm_topk_max_clusters(int cta_group, int pairs_per_cluster, int k);
 // queries-stationary-in-TMEM form (ip_gemm_ts_sm100.cu): CTA pairs, d_pad <= 768, even q_tiles
 bool gemm_topk_ts_supported(int d_pad, int q_tiles);
 int gemm_topk_ts_tile_rows(int d_pad);
