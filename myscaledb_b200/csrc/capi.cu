@@ -525,7 +525,7 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
         gp.alive = d_alive;
         gp.part_keys = c->w_pk.as<float>();
         gp.part_ids = c->w_pi.as<uint32_t>();
-        if (k > kGemmSmemK) {
+        {  // global scratch for the per-thread lists, used when they do not fit in shared memory (large k)
             B200_TRY(c->w_lk.reserve((size_t)grid * 128 * k * 4));
             B200_TRY(c->w_li.reserve((size_t)grid * 128 * k * 4));
             gp.list_keys_gmem = c->w_lk.as<float>();
@@ -551,7 +551,7 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
         // TS (queries stationary in TMEM): measured slower than streaming at d = 768 (N = 64 MMAs are bound
         // by the 64 B/clk TMEM->tensor-core operand path: 75 vs 32 cycles per MMA); auto-enabled only
         // where a 2 x 128-column accumulator ring fits (d_pad <= 512); gemm_ts = 2 forces it.
-        const bool use_ts = cta_group == 2 && gemm_topk_ts_supported(c->d_pad, q_tiles) &&
+        const bool use_ts = cta_group == 2 && k <= 30 && gemm_topk_ts_supported(c->d_pad, q_tiles) &&
                             (c->gemm_ts == 2 || (c->gemm_ts == 1 && c->d_pad <= 512));
         cudaError_t e = use_ts ? launch_gemm_topk_ts(gp, grid, s, &detail) : launch_gemm_topk(gp, grid, s, &detail);
         timing_end(c, s, ev);

@@ -45,6 +45,9 @@ struct Cfg {
         while (st > 2 && off_list(st) + k_smem * EPI_THREADS * 8 + SMEM_ALIGN_SLACK > 232448) st--;
         return st;
     }
+    __host__ __device__ static bool lists_fit(int k) {
+        return k <= kGemmSmemK && off_list(2) + k * EPI_THREADS * 8 + SMEM_ALIGN_SLACK <= 232448;
+    }
 };
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {

@@ -227,7 +227,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         list.worst = 0;
         list.thr_key = FLT_MAX;
         list.thr_id = 0;
-        if (p.k <= kGemmSmemK) {
+        if (p.lists_in_smem) {
             list.keys = reinterpret_cast<float *>(smem + C::off_list(STAGES)) + row;
             list.ids = reinterpret_cast<uint32_t *>(smem + C::off_list(STAGES) + (size_t)p.k * EPI_THREADS * 4) + row;
         } else {
@@ -322,7 +322,8 @@ template <int CG, int MC>
 static cudaError_t launch_cg(const CUtensorMap &map_q, const CUtensorMap &map_c, const GemmTopkParams &p_in, int grid,
                              cudaStream_t s) {
     GemmTopkParams p = p_in;
-    const int k_smem = p.k <= kGemmSmemK ? p.k : 0;
+    p.lists_in_smem = Cfg<CG>::lists_fit(p.k) ? 1 : 0;
+    const int k_smem = p.lists_in_smem ? p.k : 0;
     p.stages = Cfg<CG>::stages_for(k_smem);
     const size_t smem = (size_t)Cfg<CG>::off_list(p.stages) + (size_t)k_smem * EPI_THREADS * 8 + SMEM_ALIGN_SLACK;
     auto kern = gemm_topk_kernel<CG, MC>;
@@ -348,7 +349,7 @@ static cudaError_t launch_cg(const CUtensorMap &map_q, const CUtensorMap &map_c,
 // how many clusters of CG * MC CTAs of this kernel can be co-resident (persistent grid upper bound)
 template <int CG, int MC>
 static int max_clusters(int k) {
-    const int k_smem = k <= kGemmSmemK ? k : 0;
+    const int k_smem = Cfg<CG>::lists_fit(k) ? k : 0;
     const int stages = Cfg<CG>::stages_for(k_smem);
     const size_t smem = (size_t)Cfg<CG>::off_list(stages) + (size_t)k_smem * EPI_THREADS * 8 + SMEM_ALIGN_SLACK;
     auto kern = gemm_topk_kernel<CG, MC>;

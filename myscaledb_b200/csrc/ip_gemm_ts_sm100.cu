@@ -240,7 +240,7 @@ gemm_topk_ts_kernel(const __grid_constant__ CUtensorMap map_c, const GemmTopkPar
         list.worst = 0;
         list.thr_key = FLT_MAX;
         list.thr_id = 0;
-        if (p.k <= kGemmSmemK) {
+        if (p.lists_in_smem) {
             list.keys = reinterpret_cast<float *>(smem + C::OFF_LIST) + row;
             list.ids = reinterpret_cast<uint32_t *>(smem + C::OFF_LIST + (size_t)p.k * EPI_THREADS * 4) + row;
         } else {
@@ -310,9 +310,11 @@ gemm_topk_ts_kernel(const __grid_constant__ CUtensorMap map_c, const GemmTopkPar
 }
 
 template <int TBN>
-static cudaError_t launch_ts(const CUtensorMap &map_c, const GemmTopkParams &p, int grid, cudaStream_t s) {
+static cudaError_t launch_ts(const CUtensorMap &map_c, const GemmTopkParams &p_in, int grid, cudaStream_t s) {
+    GemmTopkParams p = p_in;
+    p.lists_in_smem = p.k <= 30 ? 1 : 0;
     size_t smem = TsCfg<TBN>::OFF_LIST + SMEM_ALIGN_SLACK;
-    if (p.k <= kGemmSmemK) smem += (size_t)p.k * EPI_THREADS * 8;
+    if (p.lists_in_smem) smem += (size_t)p.k * EPI_THREADS * 8;
     cudaError_t e = cudaFuncSetAttribute(gemm_topk_ts_kernel<TBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};

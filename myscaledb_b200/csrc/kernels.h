@@ -70,10 +70,13 @@ struct GemmTopkParams {
     int pairs_per_cluster;     // 1, or 2: two CTA pairs share (TMA-multicast) every corpus tile; q_tiles % 4 == 0
     int *progress;             // [grid / q_tiles][q_tiles] zeroed pacing counters, or null
     int stages;                // smem ring depth (filled in by the launcher)
+    int lists_in_smem;         // per-thread top-k lists in shared memory (else global scratch); set by the launcher
     int debug;                 // experiments only (B200_GEMM_DEBUG): 1 no epilogue, 2 TMEM loads only, 4 no TMA
     int sync_slack;            // tiles a CTA may run ahead of the slowest sharer of its corpus tiles
 };
-constexpr int kGemmSmemK = 30;
+// per-thread top-k lists live in shared memory up to this k (the smem ring gets shallower: 6 stages up to k = 14,
+// 5 up to 46, 4 up to 78, 3 up to 110, 2 up to 128 for CTA pairs); larger k uses global scratch
+constexpr int kGemmSmemK = 128;
 int gemm_topk_grid(int q_tiles, int64_t n, int num_sms);
 // returns cudaSuccess or an error; tensor maps are encoded inside
 cudaError_t launch_gemm_topk(const GemmTopkParams &p, int grid, cudaStream_t s, const char **err_detail);
