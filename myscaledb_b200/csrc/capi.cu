@@ -93,6 +93,8 @@ struct b200_corpus {
     int64_t cap = 0, n = 0;
     int64_t row_bytes = 0;
     void *data = nullptr;
+    size_t data_cap_bytes = 0;   // allocation size of `data` (owned corpora)
+    int64_t side_cap_rows = 0;   // rows the row_scale / row_bias arrays can hold
     bool owns = true;
     float *row_scale = nullptr;  // cosine: -1/||y||
     float *row_bias = nullptr;   // L2: ||y||^2 (GEMM path)
@@ -213,32 +215,41 @@ extern "C" int b200_corpus_create(int metric, int dtype, int d, int64_t capacity
 }
 
 static int corpus_alloc(b200_corpus *c, int64_t rows) {
-    if (c->data && c->owns && rows <= c->cap) return B200_OK;
     if (c->data && !c->owns) return fail(B200_ERR_INVALID, "corpus adopted device memory; cannot append");
-    int64_t new_cap = std::max<int64_t>(rows, std::max<int64_t>(c->cap, 1));
-    void *nd = nullptr;
     // +1 row of slack so that 16-byte vector loads of the last row never leave the allocation
-    cudaError_t e = cudaMalloc(&nd, (size_t)(new_cap + 1) * c->row_bytes + 256);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        return fail(B200_ERR_NOMEM, std::string("cudaMalloc corpus: ") + cudaGetErrorString(e));
+    const size_t need = (size_t)(rows + 1) * c->row_bytes + 256;
+    const bool want_scale = c->metric == B200_METRIC_COSINE, want_bias = c->metric == B200_METRIC_L2;
+    if (!c->data || c->data_cap_bytes < need) {
+        void *nd = nullptr;
+        cudaError_t e = cudaMalloc(&nd, need);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(B200_ERR_NOMEM, std::string("cudaMalloc corpus: ") + cudaGetErrorString(e));
+        }
+        if (c->data && c->n) {
+            cudaMemcpyAsync(nd, c->data, (size_t)c->n * c->row_bytes, cudaMemcpyDeviceToDevice, c->stream);
+            cudaStreamSynchronize(c->stream);
+        }
+        if (c->data) cudaFree(c->data);
+        c->data = nd;
+        c->data_cap_bytes = need;
     }
-    float *ns = nullptr, *nb = nullptr;
-    if (c->metric == B200_METRIC_COSINE) cudaMalloc(&ns, (size_t)new_cap * 4 + 256);
-    if (c->metric == B200_METRIC_L2) cudaMalloc(&nb, (size_t)new_cap * 4 + 256);
-    if (c->data && c->n) {
-        cudaMemcpyAsync(nd, c->data, (size_t)c->n * c->row_bytes, cudaMemcpyDeviceToDevice, c->stream);
-        if (ns) cudaMemcpyAsync(ns, c->row_scale, (size_t)c->n * 4, cudaMemcpyDeviceToDevice, c->stream);
-        if (nb) cudaMemcpyAsync(nb, c->row_bias, (size_t)c->n * 4, cudaMemcpyDeviceToDevice, c->stream);
-        cudaStreamSynchronize(c->stream);
+    if ((want_scale && (!c->row_scale || c->side_cap_rows < rows)) || (want_bias && (!c->row_bias || c->side_cap_rows < rows))) {
+        float *ns = nullptr, *nb = nullptr;
+        if (want_scale && cudaMalloc(&ns, (size_t)rows * 4 + 256) != cudaSuccess) return fail(B200_ERR_NOMEM, "cudaMalloc row_scale");
+        if (want_bias && cudaMalloc(&nb, (size_t)rows * 4 + 256) != cudaSuccess) return fail(B200_ERR_NOMEM, "cudaMalloc row_bias");
+        if (c->n) {
+            if (ns && c->row_scale) cudaMemcpyAsync(ns, c->row_scale, (size_t)c->n * 4, cudaMemcpyDeviceToDevice, c->stream);
+            if (nb && c->row_bias) cudaMemcpyAsync(nb, c->row_bias, (size_t)c->n * 4, cudaMemcpyDeviceToDevice, c->stream);
+            cudaStreamSynchronize(c->stream);
+        }
+        if (c->row_scale) cudaFree(c->row_scale);
+        if (c->row_bias) cudaFree(c->row_bias);
+        c->row_scale = ns;
+        c->row_bias = nb;
+        c->side_cap_rows = rows;
     }
-    if (c->data) cudaFree(c->data);
-    if (c->row_scale) cudaFree(c->row_scale);
-    if (c->row_bias) cudaFree(c->row_bias);
-    c->data = nd;
-    c->row_scale = ns;
-    c->row_bias = nb;
-    c->cap = new_cap;
+    c->cap = std::max(c->cap, rows);
     c->owns = true;
     return B200_OK;
 }
@@ -257,7 +268,7 @@ extern "C" int b200_corpus_append(b200_corpus *c, const void *rows, int64_t n) {
     if (n == 0) return B200_OK;
     std::lock_guard<std::mutex> lk(c->mu);
     B200_CUDA_OK(cudaSetDevice(c->device));
-    if (c->n + n > c->cap || !c->data) B200_TRY(corpus_alloc(c, std::max(c->n + n, c->cap)));
+    B200_TRY(corpus_alloc(c, std::max(c->n + n, c->cap)));
     char *dst = reinterpret_cast<char *>(c->data) + c->n * c->row_bytes;
     if (c->dtype == B200_DTYPE_BIN) {
         B200_CUDA_OK(cudaMemcpyAsync(dst, rows, (size_t)n * c->row_bytes, cudaMemcpyHostToDevice, c->stream));
@@ -298,6 +309,7 @@ extern "C" int b200_corpus_adopt_device(b200_corpus *c, const void *device_rows,
     c->cap = n;
     if (c->metric == B200_METRIC_COSINE) B200_CUDA_OK(cudaMalloc(&c->row_scale, (size_t)n * 4 + 256));
     if (c->metric == B200_METRIC_L2) B200_CUDA_OK(cudaMalloc(&c->row_bias, (size_t)n * 4 + 256));
+    c->side_cap_rows = n;
     if (c->dtype != B200_DTYPE_BIN) B200_TRY(corpus_norms(c, 0, n));
     B200_CUDA_OK(cudaStreamSynchronize(c->stream));
     return B200_OK;
@@ -622,6 +634,45 @@ extern "C" int b200_corpus_search(b200_corpus *c, const float *queries, int64_t 
     return search_host(c, queries, nq, k, alive_bits, 0, out_dis, out_ids);
 }
 
+// The host-buffer entry points (b200_flat_knn / b200_binary_knn / b200_part_scan) are called once per part or per
+// mark by each ClickHouse worker thread: they reuse one scratch corpus per thread (device buffers, stream and
+// workspaces grow-only) instead of paying cudaMalloc / cudaStreamCreate on every call.
+struct ScratchCorpus {
+    b200_corpus *c = nullptr;
+    ~ScratchCorpus() {
+        if (c) b200_corpus_free(c);
+    }
+};
+static thread_local ScratchCorpus t_scratch;
+
+static int scratch_corpus(int metric, int dtype, int d, int64_t rows, b200_corpus **out) {
+    b200_corpus *c = t_scratch.c;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (c && (c->device != dev || !c->owns)) {
+        b200_corpus_free(c);
+        c = t_scratch.c = nullptr;
+    }
+    if (!c) {
+        B200_TRY(b200_corpus_create(metric, dtype, d, rows, &c));
+        t_scratch.c = c;
+        *out = c;
+        return B200_OK;
+    }
+    // re-dimension in place; corpus_alloc() keeps the device buffers whenever they are large enough
+    c->metric = metric;
+    c->dtype = dtype;
+    c->d = d;
+    c->d_pad = pad_for(dtype, d);
+    c->row_bytes = dtype == B200_DTYPE_BIN ? c->d_pad : (int64_t)c->d_pad * (dtype == B200_DTYPE_BF16 ? 2 : 4);
+    c->n = 0;
+    c->cap = 0;
+    c->path = 0;
+    (void)rows;
+    *out = c;
+    return B200_OK;
+}
+
 static void fill_empty(int metric, int64_t n, float *dis, int64_t *ids, int quirk) {
     for (int64_t i = 0; i < n; i++) {
         ids[i] = -1;
@@ -640,12 +691,9 @@ extern "C" int b200_flat_knn(int metric, const float *x, int64_t nx, const float
         return B200_OK;
     }
     b200_corpus *c = nullptr;
-    B200_TRY(b200_corpus_create(metric, B200_DTYPE_F32, d, ny, &c));
+    B200_TRY(scratch_corpus(metric, B200_DTYPE_F32, d, ny, &c));
     int rc = b200_corpus_append(c, y, ny);
     if (rc == B200_OK) rc = search_host(c, x, nx, k, alive_bits, 0, out_dis, out_ids);
-    std::string keep = g_error;
-    b200_corpus_free(c);
-    g_error = keep;
     return rc;
 }
 
@@ -660,12 +708,9 @@ extern "C" int b200_binary_knn(int metric, const uint8_t *x, int64_t nx, const u
         return B200_OK;
     }
     b200_corpus *c = nullptr;
-    B200_TRY(b200_corpus_create(metric, B200_DTYPE_BIN, nbytes * 8, ny, &c));
+    B200_TRY(scratch_corpus(metric, B200_DTYPE_BIN, nbytes * 8, ny, &c));
     int rc = b200_corpus_append(c, y, ny);
     if (rc == B200_OK) rc = search_host(c, x, nx, k, alive_bits, 0, out_dis, out_ids);
-    std::string keep = g_error;
-    b200_corpus_free(c);
-    g_error = keep;
     return rc;
 }
 
@@ -694,12 +739,9 @@ extern "C" int b200_part_scan(int metric, const void *x, int64_t nx, const void 
     }
     b200_corpus *c = nullptr;
     const bool bin = is_bin_metric(metric);
-    B200_TRY(b200_corpus_create(metric, bin ? B200_DTYPE_BIN : B200_DTYPE_F32, d, ny, &c));
+    B200_TRY(scratch_corpus(metric, bin ? B200_DTYPE_BIN : B200_DTYPE_F32, d, ny, &c));
     int rc = b200_corpus_append(c, y, ny);
     if (rc == B200_OK) rc = search_host(c, x, nx, k, alive_ptr, quirk, out_dis, out_ids);
-    std::string keep = g_error;
-    b200_corpus_free(c);
-    g_error = keep;
     return rc;
 }
 

@@ -114,7 +114,25 @@ def bench_bm25():
                       "cpu_oracle_qps_1_thread_scaled": 1.0 / t_cpu}))
 
 
+def bench_flat10k():
+    """BASELINE.json configs[0]: FLAT L2 distance(), 10k rows x 128-d fp32, single query, top-10."""
+    rng = np.random.default_rng(1)
+    y = rng.standard_normal((10_000, 128)).astype(np.float32)
+    q = np.random.default_rng(2).standard_normal((1, 128)).astype(np.float32)
+    t_cold, _ = timed(lambda: b2.part_scan(b2.L2, q, y, 10), reps=50)          # host part column in, results out
+    c = b2.Corpus(b2.L2, 128).append(y)
+    c.enable_timing(True)
+    t_res, _ = timed(lambda: c.search(q, 10), reps=200)                       # resident part / FLAT index
+    kms, kn = c.kernel_time(reset=True)
+    t_cpu, _ = timed(lambda: orc.part_scan(orc.L2, q, y, 10), reps=50)
+    print(json.dumps({"workload": "FLAT L2 distance(), 10k x 128 fp32, nq=1, top-10 (config 1; 5.12 MB per query)",
+                      "gpu_part_scan_host_buffers_us": t_cold * 1e6, "gpu_resident_search_us": t_res * 1e6,
+                      "scan_kernel_us": kms / max(kn, 1) * 1e3, "scan_kernel_GB_per_s": 5.12e6 / (kms / max(kn, 1) * 1e-3) / 1e9,
+                      "cpu_oracle_1_thread_us": t_cpu * 1e6,
+                      "note": "launch/latency-bound: one 5 MB part is smaller than one wave of loads"}))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["ivfpq", "mstg", "bm25"]
     for w in which:
-        {"ivfpq": bench_ivfpq, "mstg": bench_mstg, "bm25": bench_bm25}[w]()
+        {"ivfpq": bench_ivfpq, "mstg": bench_mstg, "bm25": bench_bm25, "flat10k": bench_flat10k}[w]()
