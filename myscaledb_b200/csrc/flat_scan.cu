@@ -68,10 +68,18 @@ __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanPa
     const int64_t q0 = (int64_t)blockIdx.y * QT;
     const int nq_here = (int)min((int64_t)QT, p.nq - q0);
 
-    // stage queries (zero-padded) in shared memory
+    // stage queries (zero-padded) in shared memory.  bf16 rows consume 8 query floats per 16-byte chunk: they are
+    // stored as two float4 planes ([chunk][0..3] and [chunk][4..7]) so that consecutive lanes read consecutive
+    // 16-byte words (a single 32-byte-strided array costs a 2-way bank conflict on every LDS.128).
     for (int i = threadIdx.x; i < QT * p.d_pad; i += kScanThreads) {
         const int q = i / p.d_pad, j = i - q * p.d_pad;
-        qs[i] = (q < nq_here) ? p.queries[(q0 + q) * p.d_pad + j] : 0.f;
+        const float v = (q < nq_here) ? p.queries[(q0 + q) * p.d_pad + j] : 0.f;
+        if (E == 8) {
+            const int c = j >> 3, e = j & 7;
+            qs[q * p.d_pad + (e >> 2) * (p.d_pad >> 1) + c * 4 + (e & 3)] = v;
+        } else {
+            qs[i] = v;
+        }
     }
     WarpTopK lists[QT];
 #pragma unroll
@@ -124,10 +132,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanPa
 #pragma unroll
                     for (int q = 0; q < QT; q++) {
                         float x[E];
-                        const float4 *qp = reinterpret_cast<const float4 *>(qs + (size_t)q * p.d_pad + (size_t)c * E);
 #pragma unroll
                         for (int e4 = 0; e4 < E / 4; e4++) {
-                            const float4 t = qp[e4];
+                            const float4 t = *reinterpret_cast<const float4 *>(
+                                qs + (size_t)q * p.d_pad + (E == 8 ? (size_t)e4 * (p.d_pad >> 1) + (size_t)c * 4 : (size_t)c * 4));
                             x[e4 * 4 + 0] = t.x;
                             x[e4 * 4 + 1] = t.y;
                             x[e4 * 4 + 2] = t.z;
