@@ -54,47 +54,67 @@ def config_of(a, n):
             "cache": "inputs (15.4 GB corpus) larger than L2; no flush needed"}
 
 
+_NVML_LOOP = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+print("ready", mx, flush=True)
+while True:
+    print(time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), int(get(h)), flush=True)
+    time.sleep(0.004)
+"""
+
+
 class ClockSampler:
-    """SM clock + throttle reasons DURING the timed region, sampled through NVML every ~5 ms
-    (nvidia-smi -lms is too coarse for millisecond steps); falls back to nvidia-smi."""
+    """SM clock + throttle reasons DURING the timed region: a helper process polls NVML every ~5 ms
+    (a thread in this process starves behind the launch loop's GIL; nvidia-smi -lms is too coarse)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.samples, self.mask, self.max_mhz = index, [], 0, None
-        self._stop = threading.Event()
-        self._thr = None
-        self.err = None
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        self.phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+        self.proc, self.max_mhz, self.t0, self.t1 = None, None, None, None
 
-    def _loop(self):
+    def launch(self):
         try:
-            import pynvml as nv
-            nv.nvmlInit()
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
-            h = nv.nvmlDeviceGetHandleByIndex(phys)
-            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
-            while not self._stop.is_set():
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                self.mask |= int(get_reasons(h))
-                time.sleep(0.005)
-        except Exception as e:  # pragma: no cover
-            self.err = str(e)
+            self.proc = subprocess.Popen([sys.executable, "-c", _NVML_LOOP, str(self.phys)], stdout=subprocess.PIPE, text=True)
+            first = self.proc.stdout.readline().split()
+            self.max_mhz = float(first[1]) if first and first[0] == "ready" else None
+        except Exception:
+            self.proc = None
 
     def start(self):
-        self._thr = threading.Thread(target=self._loop, daemon=True)
-        self._thr.start()
+        if self.proc is None:
+            self.launch()
+        self.t0 = time.time()
 
     def stop(self):
-        self._stop.set()
-        if self._thr:
-            self._thr.join(2)
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [f"no samples ({self.err})"], "samples": 0}
-        sm = sorted(self.samples)
+        self.t1 = time.time()
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML helper unavailable"], "samples": 0}
+        time.sleep(0.02)
+        self.proc.terminate()
+        out = self.proc.stdout.read()
+        sm, mask = [], 0
+        for ln in out.splitlines():
+            f = ln.split()
+            if len(f) == 3:
+                try:
+                    t, c, r = float(f[0]), float(f[1]), int(f[2])
+                except ValueError:
+                    continue
+                if self.t0 <= t <= self.t1:
+                    sm.append(c)
+                    mask |= r
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples in the timed region"], "samples": 0}
+        sm.sort()
         return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(n for bit, n in self.REASONS.items() if self.mask & bit), "samples": len(sm),
-                "how": "NVML, 5 ms period, during the timed region"}
+                "reasons": sorted(n for bit, n in self.REASONS.items() if mask & bit), "samples": len(sm),
+                "how": "NVML helper process, ~5 ms period, samples inside the timed region only"}
 
 
 def make_queries(a):
@@ -277,12 +297,13 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing (value) ----
+    sampler = ClockSampler(local)
+    sampler.launch()
     for _ in range(max(a.warmup, 3)):
         step_device()
     barrier()
     index.kernel_time(reset=True)
     S.launch_count(reset=True)
-    sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
