@@ -27,7 +27,12 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "QPS, FLAT brute-force IP top-10, 10M x 768-d bf16, batch 1024"
+METRIC = "QPS, FLAT brute-force IP top-10, 10M x 768-d bf16, batch 1024"  # BASELINE.json's metric at the default sizes
+
+
+def metric_name(a):
+    rows = f"{a.rows // 1_000_000}M" if a.rows % 1_000_000 == 0 else str(a.rows)
+    return f"QPS, FLAT brute-force IP top-{a.k}, {rows} x {a.dim}-d bf16, batch {a.nq}"
 CHUNK = 250_000
 
 
@@ -210,7 +215,7 @@ def reference_arm(a):
     cb = {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
           "sample": f"each step = {a.nq} queries x {rows} of {a.rows} rows, scaled linearly; oracle/cpu_baseline.c, {how} "
                     "(reference threading model: ThreadPool over parts, kernel single-threaded inside a part)"}
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": a.gpus,
+    print(json.dumps({"impl": "reference", "metric": metric_name(a), "value": qps, "unit": "queries/s", "n_gpus": a.gpus,
                       "steps": a.steps, "warmup": a.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
                       "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": config_of(a, a.gpus), "cpu_baseline": cb,
@@ -372,7 +377,7 @@ def main():
         flops_per_launch = 2.0 * nq * shard_rows * a.dim
         achieved = flops_per_launch / (kern_ms / max(kern_n, 1) * 1e-3) / 1e12 if kern_n else None
         out = {
-            "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": N, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "metric": metric_name(a), "value": qps, "unit": "queries/s", "n_gpus": N, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": config_of(a, N), "clocks": clocks,
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * a.dim * 4,

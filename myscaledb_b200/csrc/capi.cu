@@ -24,12 +24,6 @@ int fail(int code, const std::string &msg) {
     return code;
 }
 
-struct DeviceInfo {
-    int checked = 0;  // 0 unknown, 1 ok, -1 none
-    int num_sms = 148;
-    std::string why;
-};
-
 static int ensure_device() {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -513,16 +507,25 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
                                           c->w_qnorm.as<float>(), s));
             q_add = c->w_qnorm.as<float>();
         }
-        // two pairs per cluster share every corpus tile through TMA multicast when the query tiles allow it
-        int pairs = (cta_group == 2 && q_tiles % 4 == 0 && c->gemm_multicast) ? 2 : 1;
+        // 2 or 4 CTA pairs per cluster share every corpus tile through TMA multicast when the query tiles allow it
+        // (gemm_multicast: 0 off, 2 / 4 pairs per cluster, 1 = auto: 4 when q_tiles % 8 == 0 else 2)
+        int pairs = 1;
+        if (cta_group == 2 && c->gemm_multicast) {
+            const int want = c->gemm_multicast == 1 ? 4 : c->gemm_multicast;
+            if (want >= 4 && q_tiles % 8 == 0) pairs = 4;
+            else if (want >= 2 && q_tiles % 4 == 0) pairs = 2;
+        }
         int grid = gemm_topk_grid(q_tiles, c->n, sms);
-        if (pairs == 2) {
+        while (pairs > 1) {
             // persistent + paced kernel: never launch more clusters than can be co-resident
-            const int maxc = gemm_topk_max_clusters(2, 2, k);
-            const int groups = q_tiles / 4;
+            const int maxc = gemm_topk_max_clusters(2, pairs, k);
+            const int groups = q_tiles / (2 * pairs);
             const int per_group = maxc / groups;
-            if (per_group < 1) pairs = 1;
-            else grid = std::min(grid, per_group * groups * 4);
+            if (per_group >= 1) {
+                grid = std::min(grid, per_group * groups * 2 * pairs);
+                break;
+            }
+            pairs /= 2;
         }
         grid = (grid / q_tiles) * q_tiles;
         if (grid < q_tiles) grid = q_tiles;

@@ -19,11 +19,6 @@ constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
 
 // ------------------------------------------------------------------------------------
-template <int N>
-struct QChunk {
-    float v[N];
-};
-
 template <bool BF16>
 struct ChunkTraits;
 template <>

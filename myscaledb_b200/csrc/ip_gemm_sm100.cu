@@ -384,6 +384,7 @@ int gemm_topk_grid(int q_tiles, int64_t n, int num_sms) {
 }
 
 int gemm_topk_max_clusters(int cta_group, int pairs_per_cluster, int k) {
+    if (cta_group == 2 && pairs_per_cluster == 4) return gemm::max_clusters<2, 4>(k);
     if (cta_group == 2 && pairs_per_cluster == 2) return gemm::max_clusters<2, 2>(k);
     if (cta_group == 2) return gemm::max_clusters<2, 1>(k);
     return gemm::max_clusters<1, 1>(k);
@@ -392,7 +393,7 @@ int gemm_topk_max_clusters(int cta_group, int pairs_per_cluster, int k) {
 cudaError_t launch_gemm_topk(const GemmTopkParams &p, int grid, cudaStream_t s, const char **err_detail) {
     *err_detail = nullptr;
     const int cg = p.cta_group == 2 ? 2 : 1;
-    const int mc = (cg == 2 && p.pairs_per_cluster == 2) ? 2 : 1;
+    const int mc = (cg == 2 && (p.pairs_per_cluster == 2 || p.pairs_per_cluster == 4)) ? p.pairs_per_cluster : 1;
     if (grid % p.q_tiles != 0 || p.q_tiles % (cg * mc) != 0) {
         *err_detail = "grid must be a multiple of q_tiles, q_tiles a multiple of the cluster size";
         return cudaErrorInvalidValue;
@@ -403,6 +404,7 @@ cudaError_t launch_gemm_topk(const GemmTopkParams &p, int grid, cudaStream_t s, 
         *err_detail = "cuTensorMapEncodeTiled failed";
         return cudaErrorInvalidValue;
     }
+    if (mc == 4) return gemm::launch_cg<2, 4>(map_q, map_c, p, grid, s);
     if (mc == 2) return gemm::launch_cg<2, 2>(map_q, map_c, p, grid, s);
     return cg == 2 ? gemm::launch_cg<2, 1>(map_q, map_c, p, grid, s) : gemm::launch_cg<1, 1>(map_q, map_c, p, grid, s);
 }

@@ -151,7 +151,7 @@ def test_scan_bf16_corpus():
 @pytest.mark.parametrize("metric", [b2.IP, b2.L2, b2.COSINE])
 @pytest.mark.parametrize("n,d,nq,k,path", [(20000, 768, 128, 10, 2), (5000, 64, 37, 30, 2), (70001, 128, 300, 10, 2),
                                            (70001, 128, 300, 10, 3), (70001, 128, 300, 10, 4), (1000, 96, 20, 50, 2),
-                                           (33333, 768, 1024, 10, 2), (33333, 768, 1024, 10, 4), (257, 64, 129, 5, 2),
+                                           (33333, 768, 1024, 10, 2), (33333, 768, 1024, 10, 4), (33333, 768, 512, 10, 2), (257, 64, 129, 5, 2),
                                            (9000, 512, 256, 10, 2), (9000, 832, 256, 10, 2)])
 def test_gemm_path_matches_oracle(metric, n, d, nq, k, path):
     """path 2 = auto (CTA pairs, queries stationary in TMEM when d <= 768), 3 = single-CTA MMAs only,
