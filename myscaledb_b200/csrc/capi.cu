@@ -99,7 +99,7 @@ struct b200_corpus {
     cudaStream_t stream = nullptr;
     std::mutex mu;
     // workspaces
-    DevBuf w_raw, w_q32, w_qbf, w_qnorm, w_pk, w_pi, w_lk, w_li, w_alive, w_odis, w_oids, w_stage, w_prog;
+    DevBuf w_raw, w_q32, w_qbf, w_qlo, w_qnorm, w_pk, w_pi, w_lk, w_li, w_alive, w_odis, w_oids, w_stage, w_prog;
     int sync_slack = 2;
     int gemm_multicast = 1;  // clusters of two CTA pairs sharing the corpus tile (B200_GEMM_MULTICAST=0 disables)
     int gemm_ts = 0;  // 0 streaming (default: faster at every measured d), 1 TS when d_pad <= 512, 2 TS whenever it fits
@@ -360,7 +360,7 @@ extern "C" int b200_corpus_free(b200_corpus *c) {
     if (c->data && c->owns) cudaFree(c->data);
     if (c->row_scale) cudaFree(c->row_scale);
     if (c->row_bias) cudaFree(c->row_bias);
-    for (DevBuf *b : {&c->w_raw, &c->w_q32, &c->w_qbf, &c->w_qnorm, &c->w_pk, &c->w_pi, &c->w_lk, &c->w_li, &c->w_alive,
+    for (DevBuf *b : {&c->w_raw, &c->w_q32, &c->w_qbf, &c->w_qlo, &c->w_qnorm, &c->w_pk, &c->w_pi, &c->w_lk, &c->w_li, &c->w_alive,
                       &c->w_odis, &c->w_oids, &c->w_stage, &c->w_prog})
         b->release();
     for (auto *v : {&c->ev_used, &c->ev_free})
@@ -423,13 +423,14 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
     float *q32 = c->w_q32.as<float>();
     B200_CUDA_OK(launch_pad_rows_f32(reinterpret_cast<const float *>(d_queries), c->d, q32, c->d_pad, nq, s));
     int path = c->path;
-    if (path == 0) path = (c->dtype == B200_DTYPE_BF16 && nq >= 16) ? 2 : 1;
+    // auto: tensor cores from 16 queries up (bf16 rows: kind::f16 GEMM; fp32 rows: 3xTF32 split GEMM, same accuracy
+    // class as the fp32 FMA scan); very large k stays on the scan path, whose lists are warp-cooperative
+    if (path == 0) path = (nq >= 16 && k <= (c->dtype == B200_DTYPE_BF16 ? 1024 : 256)) ? 2 : 1;
+    if (path == 3 || path == 4) { if (c->dtype != B200_DTYPE_BF16) path = 2; }
     // scan path: queries normalised in fp32 like the reference.  GEMM path: the bf16 operand
     // keeps the caller's values (normalising first would add a bf16 rounding of the unit
     // vector); the positive per-query factor 1/||q|| is applied when the result is emitted.
     if (c->metric == B200_METRIC_COSINE && path == 1) B200_CUDA_OK(launch_normalize_rows_f32(q32, c->d_pad, nq, s));
-    if (path == 2 && c->dtype != B200_DTYPE_BF16)
-        return fail(B200_ERR_UNSUPPORTED, "the tcgen05 GEMM path needs a bf16 corpus");
 
     const int out_mode_scan = c->metric == B200_METRIC_L2 ? kOutKey : c->metric == B200_METRIC_IP ? kOutNeg : kOutOnePlus;
 
@@ -492,25 +493,38 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
     const int64_t QCHUNK = 1024;
     for (int64_t qb = 0; qb < nq; qb += QCHUNK) {
         const int64_t nq_c = std::min(QCHUNK, nq - qb);
-        // >= 2 query tiles: CTA pairs (tcgen05 cta_group::2), query tiles padded to an even count
-        const int cta_group = (nq_c > 128 && c->gemm_cta_group != 1) ? 2 : 1;
+        const bool f32 = c->dtype == B200_DTYPE_F32;
+        // >= 2 query tiles: CTA pairs (tcgen05 cta_group::2), query tiles padded to an even count;
+        // the fp32 (3xTF32) kernel exists as CTA pairs only
+        const int cta_group = (f32 || (nq_c > 128 && c->gemm_cta_group != 1)) ? 2 : 1;
         const int nq_pad = (int)round_up(nq_c, 128 * cta_group);
         const int q_tiles = nq_pad / 128;
-        B200_TRY(c->w_qbf.reserve((size_t)nq_pad * c->d_pad * 2));
-        B200_CUDA_OK(cudaMemsetAsync(c->w_qbf.p, 0, (size_t)nq_pad * c->d_pad * 2, s));
-        B200_CUDA_OK(launch_f32_to_bf16_rows(q32 + qb * c->d_pad, c->d_pad, c->w_qbf.p, c->d_pad, nq_c, s));
+        if (f32) {
+            // fp32 rows: queries split once per batch into TF32 hi / lo planes (ip_gemm_tf32x3_sm100.cu)
+            B200_TRY(c->w_qbf.reserve((size_t)nq_pad * c->d_pad * 4));
+            B200_TRY(c->w_qlo.reserve((size_t)nq_pad * c->d_pad * 4));
+            B200_CUDA_OK(launch_split_tf32(q32 + qb * c->d_pad, nq_c, c->d_pad, c->w_qbf.as<float>(), c->w_qlo.as<float>(), nq_pad, s));
+        } else {
+            B200_TRY(c->w_qbf.reserve((size_t)nq_pad * c->d_pad * 2));
+            B200_CUDA_OK(cudaMemsetAsync(c->w_qbf.p, 0, (size_t)nq_pad * c->d_pad * 2, s));
+            B200_CUDA_OK(launch_f32_to_bf16_rows(q32 + qb * c->d_pad, c->d_pad, c->w_qbf.p, c->d_pad, nq_c, s));
+        }
         const float *q_add = nullptr;
         if (c->metric == B200_METRIC_L2 || c->metric == B200_METRIC_COSINE) {
-            // L2: ||q||^2 of the bf16-rounded query; cosine: -(1/||q||) (mode 1 stores the negative)
+            // L2: ||q||^2 of the operand the MMA sees (bf16-rounded / fp32); cosine: -(1/||q||) (mode 1 stores the negative)
             B200_TRY(c->w_qnorm.reserve((size_t)nq_pad * 4));
-            B200_CUDA_OK(launch_row_norms(c->w_qbf.p, 1, c->d_pad, nq_c, c->metric == B200_METRIC_L2 ? 0 : 1,
-                                          c->w_qnorm.as<float>(), s));
+            if (f32)
+                B200_CUDA_OK(launch_row_norms(q32 + qb * c->d_pad, 0, c->d_pad, nq_c, c->metric == B200_METRIC_L2 ? 0 : 1,
+                                              c->w_qnorm.as<float>(), s));
+            else
+                B200_CUDA_OK(launch_row_norms(c->w_qbf.p, 1, c->d_pad, nq_c, c->metric == B200_METRIC_L2 ? 0 : 1,
+                                              c->w_qnorm.as<float>(), s));
             q_add = c->w_qnorm.as<float>();
         }
         // 2 or 4 CTA pairs per cluster share every corpus tile through TMA multicast when the query tiles allow it
         // (gemm_multicast: 0 off, 2 / 4 pairs per cluster, 1 = auto: 4 when q_tiles % 8 == 0 else 2)
         int pairs = 1;
-        if (cta_group == 2 && c->gemm_multicast) {
+        if (cta_group == 2 && c->gemm_multicast && !f32) {
             const int want = c->gemm_multicast == 1 ? 4 : c->gemm_multicast;
             if (want >= 4 && q_tiles % 8 == 0) pairs = 4;
             else if (want >= 2 && q_tiles % 4 == 0) pairs = 2;
@@ -534,6 +548,7 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
         GemmTopkParams gp{};
         gp.corpus_bf16 = c->data;
         gp.queries_bf16 = c->w_qbf.p;
+        gp.queries_lo = f32 ? c->w_qlo.p : nullptr;
         gp.row_scale = c->metric == B200_METRIC_COSINE ? c->row_scale : nullptr;
         gp.scale_const = c->metric == B200_METRIC_L2 ? -2.f : -1.f;
         gp.row_bias = c->metric == B200_METRIC_L2 ? c->row_bias : nullptr;
@@ -566,9 +581,10 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
         // TS (queries stationary in TMEM): measured slower than streaming at d = 768 (N = 64 MMAs are bound
         // by the 64 B/clk TMEM->tensor-core operand path: 75 vs 32 cycles per MMA); auto-enabled only
         // where a 2 x 128-column accumulator ring fits (d_pad <= 512); gemm_ts = 2 forces it.
-        const bool use_ts = cta_group == 2 && k <= 30 && gemm_topk_ts_supported(c->d_pad, q_tiles) &&
+        const bool use_ts = !f32 && cta_group == 2 && k <= 30 && gemm_topk_ts_supported(c->d_pad, q_tiles) &&
                             (c->gemm_ts == 2 || (c->gemm_ts == 1 && c->d_pad <= 512));
-        cudaError_t e = use_ts ? launch_gemm_topk_ts(gp, grid, s, &detail) : launch_gemm_topk(gp, grid, s, &detail);
+        cudaError_t e = f32 ? launch_gemm3_topk(gp, grid, s, &detail)
+                            : use_ts ? launch_gemm_topk_ts(gp, grid, s, &detail) : launch_gemm_topk(gp, grid, s, &detail);
         timing_end(c, s, ev);
         if (e != cudaSuccess)
             return fail(B200_ERR_CUDA, std::string("gemm_topk launch: ") + (detail ? detail : cudaGetErrorString(e)));

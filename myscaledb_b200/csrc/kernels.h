@@ -54,7 +54,8 @@ cudaError_t launch_topk_merge(const MergeParams &p, bool external, cudaStream_t 
 // ---- tcgen05 bf16 GEMM + fused top-k (ip_gemm_sm100.cu) ---------------------------
 struct GemmTopkParams {
     const void *corpus_bf16;   // [n][d_pad] bf16, d_pad % 64 == 0
-    const void *queries_bf16;  // [nq_pad][d_pad] bf16, nq_pad % 128 == 0
+    const void *queries_bf16;  // [nq_pad][d_pad] bf16, nq_pad % 128 == 0 (3xTF32 kernel: fp32 hi plane; corpus_bf16 = fp32 rows)
+    const void *queries_lo;    // 3xTF32 kernel only: fp32 lo plane [nq_pad][d_pad]
     const float *row_scale;    // per corpus row multiplier a[j] or null (= scale_const)
     float scale_const;         // -1 for IP, -2 for L2
     const float *row_bias;     // per corpus row addend b[j] or null (=0)
@@ -85,6 +86,10 @@ int gemm_topk_max_clusters(int cta_group, int pairs_per_cluster, int k);
 bool gemm_topk_ts_supported(int d_pad, int q_tiles);
 int gemm_topk_ts_tile_rows(int d_pad);
 cudaError_t launch_gemm_topk_ts(const GemmTopkParams &p, int grid, cudaStream_t s, const char **err_detail);
+
+// ---- fp32 rows on the tensor cores with fp32-level accuracy (ip_gemm_tf32x3_sm100.cu): CTA pairs, even q_tiles
+cudaError_t launch_split_tf32(const float *src, int64_t n_src, int d_pad, float *hi, float *lo, int64_t n_pad, cudaStream_t s);
+cudaError_t launch_gemm3_topk(const GemmTopkParams &p, int grid, cudaStream_t s, const char **err_detail);
 
 // ---- elementwise prep kernels (prep.cu) --------------------------------------------
 cudaError_t launch_f32_to_bf16_rows(const float *src, int d, void *dst, int d_pad, int64_t n, cudaStream_t s);

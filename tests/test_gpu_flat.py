@@ -6,7 +6,7 @@ import pytest
 import myscaledb_b200 as b2
 import oracle as orc
 from myscaledb_b200 import search as S
-from tests.util import check_topk, to_bf16_values
+from tests.util import check_topk, exact_distance, to_bf16_values
 
 pytestmark = pytest.mark.gpu
 F32 = np.float32
@@ -175,6 +175,50 @@ def _prep_cos(x, y):
     orc.lib().orc_normalize(x.ctypes.data_as(orc.C.POINTER(orc.C.c_float)), orc.C.c_int64(x.shape[0]), orc.C.c_int(x.shape[1]))
     orc.lib().orc_normalize(y.ctypes.data_as(orc.C.POINTER(orc.C.c_float)), orc.C.c_int64(y.shape[0]), orc.C.c_int(y.shape[1]))
     return x, y
+
+
+@pytest.mark.parametrize("metric", [b2.IP, b2.L2, b2.COSINE])
+@pytest.mark.parametrize("n,d,nq,k", [(20000, 768, 128, 10), (5000, 64, 37, 30), (70001, 128, 300, 10), (1000, 96, 20, 50),
+                                      (33333, 768, 1024, 10), (257, 50, 129, 5), (9000, 100, 256, 100), (4000, 1536, 16, 10)])
+def test_tf32x3_path_matches_oracle(metric, n, d, nq, k):
+    """fp32 corpus, batch of queries: three TF32 tensor-core products per k-step (ip_gemm_tf32x3_sm100.cu) must give
+    fp32-class results on arbitrary fp32 inputs (NOT pre-rounded), i.e. the same tolerance as the fp32 FMA scan."""
+    rng = np.random.default_rng(7 * n + d + nq + metric)
+    y = rng.standard_normal((n, d)).astype(F32)
+    x = rng.standard_normal((nq, d)).astype(F32)
+    c = b2.Corpus(metric, d).append(y)
+    c.set_path(2)
+    dg, ig = c.search(x, k)
+    c.close()
+    do, io = orc.knn_flat_parts(orc.IP if metric != orc.L2 else orc.L2, *(_prep_cos(x, y) if metric == b2.COSINE else (x, y)), k, 4)
+    if metric == b2.COSINE:
+        do = 1 - do
+    check_topk(metric, x, y, dg, ig, do, io, rtol=4e-5, atol=2e-5 if metric == b2.L2 else 2e-6, min_exact=0.995)
+    # against fp64 ground truth: ~1e-5 relative (measured; the tensor core's fp32 accumulator truncates), an order
+    # inside the 1e-4 contract and ~100x tighter than one TF32 pass or bf16 operands
+    for q in range(0, nq, max(1, nq // 8)):
+        t = np.array([exact_distance(metric, x[q], y[j]) for j in ig[q]])
+        assert np.abs(t - dg[q]).max() <= 4e-5 * max(1.0, np.abs(t).max())
+
+
+def test_tf32x3_auto_path_filter_and_scan_agreement():
+    """Auto path for an fp32 corpus and >= 16 queries is the tensor-core kernel; it must agree with the fp32 FMA
+    scan (two independent GPU paths) under a DenseBitmap filter, through the one-shot b200_flat_knn as well."""
+    rng = np.random.default_rng(77)
+    y = rng.standard_normal((120000, 200)).astype(F32)
+    x = rng.standard_normal((64, 200)).astype(F32)
+    alive = rng.random(120000) < 0.3
+    bits = orc.pack_bits(alive)
+    c = b2.Corpus(b2.L2, 200).append(y)
+    n0 = S.launch_count()
+    d2, i2 = c.search(x, 10, alive_bits=bits)
+    c.set_path(1); d1, i1 = c.search(x, 10, alive_bits=bits)
+    c.close()
+    assert alive[i2].all()
+    check_topk(b2.L2, x, y, d2, i2, d1, i1, rtol=4e-5, atol=2e-5, min_exact=0.995)
+    d3, i3 = b2.flat_knn(b2.L2, x, y, 10, alive_bits=bits)
+    assert (i3 == i2).all() and np.allclose(d3, d2, rtol=0, atol=0)
+    assert S.launch_count() > n0
 
 
 def test_gemm_path_alive_bitmap():
