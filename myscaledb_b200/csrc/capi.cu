@@ -264,18 +264,17 @@ extern "C" int b200_corpus_append(b200_corpus *c, const void *rows, int64_t n) {
     B200_CUDA_OK(cudaSetDevice(c->device));
     B200_TRY(corpus_alloc(c, std::max(c->n + n, c->cap)));
     char *dst = reinterpret_cast<char *>(c->data) + c->n * c->row_bytes;
-    if (c->dtype == B200_DTYPE_BIN) {
-        B200_CUDA_OK(cudaMemcpyAsync(dst, rows, (size_t)n * c->row_bytes, cudaMemcpyHostToDevice, c->stream));
-    } else if (c->dtype == B200_DTYPE_F32 && c->d == c->d_pad) {
-        B200_CUDA_OK(cudaMemcpyAsync(dst, rows, (size_t)n * c->row_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (c->dtype == B200_DTYPE_BIN || (c->dtype == B200_DTYPE_F32 && c->d == c->d_pad)) {
+        // rows already have the HBM layout: pageable host memory -> device through the pinned ring (ingest.cu)
+        B200_TRY(staged_h2d(dst, rows, (size_t)n * c->row_bytes, c->device, c->stream));
     } else {
         // stage raw fp32 rows in chunks, then pad / convert on device
         const int64_t chunk = std::max<int64_t>(1, (int64_t)(256ll << 20) / ((int64_t)c->d * 4));
         for (int64_t off = 0; off < n; off += chunk) {
             const int64_t m = std::min(chunk, n - off);
             B200_TRY(c->w_raw.reserve((size_t)m * c->d * 4));
-            B200_CUDA_OK(cudaMemcpyAsync(c->w_raw.p, reinterpret_cast<const float *>(rows) + off * c->d, (size_t)m * c->d * 4,
-                                         cudaMemcpyHostToDevice, c->stream));
+            B200_TRY(staged_h2d(c->w_raw.p, reinterpret_cast<const float *>(rows) + off * c->d, (size_t)m * c->d * 4, c->device,
+                                c->stream));
             char *dd = dst + off * c->row_bytes;
             if (c->dtype == B200_DTYPE_BF16)
                 B200_CUDA_OK(launch_f32_to_bf16_rows(c->w_raw.as<float>(), c->d, dd, c->d_pad, m, c->stream));

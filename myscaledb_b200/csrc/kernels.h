@@ -91,6 +91,9 @@ cudaError_t launch_gemm_topk_ts(const GemmTopkParams &p, int grid, cudaStream_t 
 cudaError_t launch_split_tf32(const float *src, int64_t n_src, int d_pad, float *hi, float *lo, int64_t n_pad, cudaStream_t s);
 cudaError_t launch_gemm3_topk(const GemmTopkParams &p, int grid, cudaStream_t s, const char **err_detail);
 
+// ---- host ingest (ingest.cu): pageable host memory -> device through a multi-threaded pinned ring; returns a B200_* code
+int staged_h2d(void *dst, const void *src, size_t bytes, int device, cudaStream_t s);
+
 // ---- elementwise prep kernels (prep.cu) --------------------------------------------
 cudaError_t launch_f32_to_bf16_rows(const float *src, int d, void *dst, int d_pad, int64_t n, cudaStream_t s);
 cudaError_t launch_pad_rows_f32(const float *src, int d, float *dst, int d_pad, int64_t n, cudaStream_t s);

@@ -132,7 +132,26 @@ def bench_flat10k():
                       "note": "launch/latency-bound: one 5 MB part is smaller than one wave of loads"}))
 
 
+def bench_ingest():
+    """Cold brute force: the part column starts in pageable host memory (the reference's vectorScanWithoutIndex case)."""
+    n, d = 1_000_000, 768
+    rng = np.random.default_rng(3)
+    y = rng.standard_normal((n, d), dtype=np.float32)
+    q = rng.standard_normal((1, d), dtype=np.float32)
+    out = {"workload": f"cold FLAT L2 part scan, {n} x {d} fp32 part in pageable host memory ({n * d * 4 / 1e9:.2f} GB), nq=1, top-10",
+           "points": []}
+    for threads in ("0", "2", "4", "6", "8"):
+        os.environ["B200_INGEST_THREADS"] = threads
+        t, _ = timed(lambda: b2.part_scan(b2.L2, q, y, 10), reps=3)
+        out["points"].append({"ingest_threads": int(threads), "s_per_scan": t, "host_to_hbm_GB_per_s": n * d * 4 / t / 1e9})
+    del os.environ["B200_INGEST_THREADS"]
+    t0 = time.perf_counter()
+    orc.part_scan(orc.L2, q, y[:200_000], 10)
+    out["cpu_oracle_1_thread_s_scaled"] = (time.perf_counter() - t0) * n / 200_000
+    print(json.dumps(out))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["ivfpq", "mstg", "bm25"]
     for w in which:
-        {"ivfpq": bench_ivfpq, "mstg": bench_mstg, "bm25": bench_bm25, "flat10k": bench_flat10k}[w]()
+        {"ivfpq": bench_ivfpq, "mstg": bench_mstg, "bm25": bench_bm25, "flat10k": bench_flat10k, "ingest": bench_ingest}[w]()
