@@ -184,20 +184,8 @@ __global__ void __launch_bounds__(256) bm25_score_kernel(const Bm25ScoreParams p
         }
     }
     __syncthreads();
-    if (warp == 0) {
-        for (int w = 1; w < 8; w++)
-            for (int j = 0; j < p.k; j++) {
-                const float ck = lk[(size_t)w * p.k + j];
-                if (!(ck < FLT_MAX)) break;
-                list.insert(ck, li[(size_t)w * p.k + j]);
-            }
-        float *ok = p.part_keys + ((size_t)q * gridDim.x + blockIdx.x) * p.k;
-        uint32_t *oi = p.part_ids + ((size_t)q * gridDim.x + blockIdx.x) * p.k;
-        for (int j = lane; j < p.k; j += 32) {
-            ok[j] = j < list.n ? list.keys[j] : FLT_MAX;
-            oi[j] = j < list.n ? list.ids[j] : kNoId;
-        }
-    }
+    block_rank_merge(lk, li, 8, p.k, p.k, p.part_keys + ((size_t)q * gridDim.x + blockIdx.x) * p.k,
+                     p.part_ids + ((size_t)q * gridDim.x + blockIdx.x) * p.k);
 }
 
 // doc ordinal -> row id on the merged result

@@ -180,29 +180,11 @@ __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanPa
         }
     }
     __syncthreads();
-    // block merge: warp 0 absorbs the lists of warps 1..7, then writes the partial
-    if (warp == 0) {
-#pragma unroll
-        for (int q = 0; q < QT; q++) {
-            if (q >= nq_here) break;
-            for (int w = 1; w < kScanWarps; w++) {
-                const float *wk = lk + ((size_t)w * QT + q) * p.k;
-                const uint32_t *wi = li + ((size_t)w * QT + q) * p.k;
-                // slots beyond a warp's n hold the FLT_MAX sentinel
-                for (int j = 0; j < p.k; j++) {
-                    const float ck = wk[j];
-                    if (!(ck < FLT_MAX)) break;
-                    lists[q].insert(ck, wi[j]);
-                }
-            }
-            float *ok = p.part_keys + ((q0 + q) * (int64_t)gridDim.x + blockIdx.x) * p.k;
-            uint32_t *oi = p.part_ids + ((q0 + q) * (int64_t)gridDim.x + blockIdx.x) * p.k;
-            for (int j = lane; j < p.k; j += 32) {
-                ok[j] = j < lists[q].n ? lists[q].keys[j] : FLT_MAX;
-                oi[j] = j < lists[q].n ? lists[q].ids[j] : kNoId;
-            }
-        }
-    }
+    // block merge: the 8 warp lists of every query -> this block's partial list (slots beyond a warp's n hold FLT_MAX)
+    for (int q = 0; q < nq_here; q++)
+        block_rank_merge(lk + (size_t)q * p.k, li + (size_t)q * p.k, kScanWarps, QT * p.k, p.k,
+                         p.part_keys + ((q0 + q) * (int64_t)gridDim.x + blockIdx.x) * p.k,
+                         p.part_ids + ((q0 + q) * (int64_t)gridDim.x + blockIdx.x) * p.k);
 }
 
 // ------------------------------------------------------------------------------------
@@ -257,20 +239,8 @@ __global__ void __launch_bounds__(kScanThreads) binary_scan_kernel(const BinaryS
         }
     }
     __syncthreads();
-    if (warp == 0) {
-        for (int w = 1; w < kScanWarps; w++)
-            for (int j = 0; j < p.k; j++) {
-                const float ck = lk[(size_t)w * p.k + j];
-                if (!(ck < FLT_MAX)) break;
-                list.insert(ck, li[(size_t)w * p.k + j]);
-            }
-        float *ok = p.part_keys + (q * (int64_t)gridDim.x + blockIdx.x) * p.k;
-        uint32_t *oi = p.part_ids + (q * (int64_t)gridDim.x + blockIdx.x) * p.k;
-        for (int j = lane; j < p.k; j += 32) {
-            ok[j] = j < list.n ? list.keys[j] : FLT_MAX;
-            oi[j] = j < list.n ? list.ids[j] : kNoId;
-        }
-    }
+    block_rank_merge(lk, li, kScanWarps, p.k, p.k, p.part_keys + (q * (int64_t)gridDim.x + blockIdx.x) * p.k,
+                     p.part_ids + (q * (int64_t)gridDim.x + blockIdx.x) * p.k);
 }
 
 // ------------------------------------------------------------------------------------
@@ -291,6 +261,33 @@ __global__ void __launch_bounds__(kScanThreads) topk_merge_kernel(const MergePar
     const float *keys = reinterpret_cast<const float *>(p.in_keys);
     const IdT *ids = reinterpret_cast<const IdT *>(p.in_ids);
     const int64_t ncand = (int64_t)p.n_lists * p.k_in;
+    // Pre-filter.  Every input list is sorted best-first and holds its partition's full top-k_in, so with k_in >= k
+    // the k-th entry of ANY list bounds the global k-th key from above: candidates beyond the smallest such bound
+    // cannot be in the result.  Typically ~2k of the n_lists * k candidates survive, which keeps the warp-list
+    // inserts (O(k / 32) each) off the critical path for k in the hundreds (IVF: 32 lists x 160).
+    if (p.k_in >= p.k) {
+        __shared__ float bound_s[kScanWarps];
+        float b = FLT_MAX;
+        for (int l = threadIdx.x; l < p.n_lists; l += kScanThreads) {
+            const int64_t off = (int64_t)l * p.list_stride + q * p.q_stride + (p.k - 1);
+            const int64_t ioff = (int64_t)l * (p.id_list_stride ? p.id_list_stride : p.list_stride) + q * p.q_stride + (p.k - 1);
+            float v = keys[off];
+            if (EXTERNAL) v = (int64_t)ids[ioff] < 0 ? FLT_MAX : (p.descending ? -v : v);
+            else if ((uint32_t)ids[ioff] == kNoId) v = FLT_MAX;
+            b = fminf(b, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) b = fminf(b, __shfl_xor_sync(0xffffffffu, b, o));
+        if (lane == 0) bound_s[warp] = b;
+        __syncthreads();
+        b = bound_s[0];
+#pragma unroll
+        for (int w = 1; w < kScanWarps; w++) b = fminf(b, bound_s[w]);
+        if (b < FLT_MAX) {
+            list.thr_key = b;       // keys equal to the bound still pass (largest id as the tie-break)
+            list.thr_id = kNoId;
+        }
+    }
     for (int64_t c0 = (int64_t)warp * 32; c0 < ncand; c0 += kScanThreads) {
         const int64_t c = c0 + lane;
         float key = FLT_MAX;
@@ -325,19 +322,17 @@ __global__ void __launch_bounds__(kScanThreads) topk_merge_kernel(const MergePar
         }
     }
     __syncthreads();
-    if (warp == 0) {
-        for (int w = 1; w < kScanWarps; w++)
-            for (int j = 0; j < p.k; j++) {
-                const float ck = lk[(size_t)w * p.k + j];
-                if (!(ck < FLT_MAX)) break;
-                list.insert(ck, li[(size_t)w * p.k + j]);
-            }
-        for (int j = lane; j < p.k; j += 32) {
+    float *fk = lk + (size_t)kScanWarps * p.k * 2;  // merged list, behind the warp lists (keys + ids)
+    uint32_t *fi = reinterpret_cast<uint32_t *>(fk + p.k);
+    block_rank_merge(lk, li, kScanWarps, p.k, p.k, fk, fi);
+    __syncthreads();
+    {
+        for (int j = threadIdx.x; j < p.k; j += kScanThreads) {
             float dis;
             int64_t id;
-            if (j < list.n) {
-                const float key = list.keys[j];
-                id = (int64_t)list.ids[j] + p.id_offset;
+            if (fi[j] != kNoId) {
+                const float key = fk[j];
+                id = (int64_t)fi[j] + p.id_offset;
                 switch (p.out_mode) {
                     case kOutKey: dis = key; break;
                     case kOutNeg: dis = -key; break;
@@ -412,7 +407,7 @@ cudaError_t launch_binary_scan(const BinaryScanParams &p, int blocks_x, cudaStre
 }
 
 cudaError_t launch_topk_merge(const MergeParams &p, bool external, cudaStream_t s) {
-    const size_t smem = (size_t)kScanWarps * p.k * 8;
+    const size_t smem = (size_t)(kScanWarps + 1) * p.k * 8;
     auto go = [&](auto kern) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

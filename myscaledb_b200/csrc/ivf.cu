@@ -241,20 +241,9 @@ __global__ void __launch_bounds__(256) ivf_flat_scan_kernel(const IvfScanParams 
         }
     }
     __syncthreads();
-    if (warp == 0) {
-        for (int w = 1; w < 8; w++)
-            for (int j = 0; j < p.k; j++) {
-                const float ck = lk[(size_t)w * p.k + j];
-                if (!(ck < FLT_MAX)) break;
-                list.insert(ck, li[(size_t)w * p.k + j]);
-            }
-        float *ok = p.part_keys + ((size_t)q * p.nprobe + pr) * p.k;
-        uint32_t *oi = p.part_ids + ((size_t)q * p.nprobe + pr) * p.k;
-        for (int j = lane; j < p.k; j += 32) {
-            ok[j] = j < list.n ? list.keys[j] : FLT_MAX;
-            oi[j] = j < list.n ? list.ids[j] : kNoId;
-        }
-    }
+    // the 8 warp lists -> this (query, list)'s partial top-k
+    block_rank_merge(lk, li, 8, p.k, p.k, p.part_keys + ((size_t)q * p.nprobe + pr) * p.k,
+                     p.part_ids + ((size_t)q * p.nprobe + pr) * p.k);
 }
 
 __global__ void __launch_bounds__(256) ivfpq_scan_kernel(const IvfScanParams p) {
@@ -262,29 +251,60 @@ __global__ void __launch_bounds__(256) ivfpq_scan_kernel(const IvfScanParams p) 
     float *lut = reinterpret_cast<float *>(smem_raw);          // [m][256]
     float *lk = lut + (size_t)p.m * 256;                       // [8][k]
     uint32_t *li = reinterpret_cast<uint32_t *>(lk + 8 * p.k);
-    __shared__ float bias_s;
+    __shared__ float bias_s, bias_w[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t q = blockIdx.y;
     const int pr = blockIdx.x;
     WarpTopK list;
     list.init(lk + (size_t)warp * p.k, li + (size_t)warp * p.k, p.k);
     for (int j = lane; j < p.k; j += 32) list.keys[j] = FLT_MAX;
+    float *rs = reinterpret_cast<float *>(li + 8 * p.k);  // [d]: residual q - centroid (L2) or the query (IP)
     const int64_t l = p.probe[q * p.nprobe + pr];
     if (l >= 0) {
         const float *qv = p.queries + q * p.d_pad;
         const float *cv = p.centroids + l * p.d;
-        // look-up table on the residual (L2) / on the query (IP, plus the q.centroid bias)
+        float b = 0.f;
+        for (int i = threadIdx.x; i < p.d; i += 256) {
+            const float x = qv[i], c = cv[i];
+            rs[i] = p.l2 ? x - c : x;
+            b = fmaf(x, c, b);
+        }
+        if (!p.l2) {  // IP: the q . centroid term is the same for every row of the list
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+            if (lane == 0) bias_w[warp] = b;
+        }
+    }
+    __syncthreads();
+    if (l >= 0) {
+        // look-up table on the residual (L2) / on the query (IP): one thread per (sub-quantiser, centroid) entry, its
+        // dsub codebook floats read as whole 16-byte words (a warp reads one contiguous span of the codebook)
         for (int e = threadIdx.x; e < p.m * 256; e += 256) {
-            const int j = e >> 8, c = e & 255;
-            const float *cw = p.pq + ((size_t)j * 256 + c) * p.dsub;
+            const int j = e >> 8;
+            const float *cw = p.pq + (size_t)e * p.dsub;
+            const float *r = rs + j * p.dsub;
             float s = 0.f;
-            for (int t = 0; t < p.dsub; t++) {
-                const int dd = j * p.dsub + t;
-                if (p.l2) {
-                    const float r = qv[dd] - cv[dd] - cw[t];
-                    s = fmaf(r, r, s);
-                } else {
-                    s = fmaf(qv[dd], cw[t], s);
+            if ((p.dsub & 3) == 0) {
+                for (int t = 0; t < p.dsub; t += 4) {
+                    const float4 w = *reinterpret_cast<const float4 *>(cw + t);
+                    if (p.l2) {
+                        float u = r[t] - w.x; s = fmaf(u, u, s);
+                        u = r[t + 1] - w.y; s = fmaf(u, u, s);
+                        u = r[t + 2] - w.z; s = fmaf(u, u, s);
+                        u = r[t + 3] - w.w; s = fmaf(u, u, s);
+                    } else {
+                        s = fmaf(r[t], w.x, s); s = fmaf(r[t + 1], w.y, s);
+                        s = fmaf(r[t + 2], w.z, s); s = fmaf(r[t + 3], w.w, s);
+                    }
+                }
+            } else {
+                for (int t = 0; t < p.dsub; t++) {
+                    if (p.l2) {
+                        const float u = r[t] - cw[t];
+                        s = fmaf(u, u, s);
+                    } else {
+                        s = fmaf(r[t], cw[t], s);
+                    }
                 }
             }
             lut[e] = s;
@@ -292,7 +312,7 @@ __global__ void __launch_bounds__(256) ivfpq_scan_kernel(const IvfScanParams p) 
         if (threadIdx.x == 0) {
             float b = 0.f;
             if (!p.l2)
-                for (int dd = 0; dd < p.d; dd++) b = fmaf(qv[dd], cv[dd], b);
+                for (int w = 0; w < 8; w++) b += bias_w[w];
             bias_s = b;
         }
     }
@@ -312,7 +332,21 @@ __global__ void __launch_bounds__(256) ivfpq_scan_kernel(const IvfScanParams p) 
             if (ok) {
                 const uint8_t *code = p.codes + (size_t)r * p.m;
                 float s = 0.f;
-                if ((p.m & 3) == 0) {
+                if ((p.m & 15) == 0) {
+                    const uint4 *cq = reinterpret_cast<const uint4 *>(code);
+                    for (int j16 = 0; j16 < p.m / 16; j16++) {
+                        const uint4 w4 = cq[j16];
+                        const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                        for (int h = 0; h < 4; h++) {
+                            const float *lt = lut + (size_t)(j16 * 16 + h * 4) * 256;
+                            s += lt[ww[h] & 255];
+                            s += lt[256 + ((ww[h] >> 8) & 255)];
+                            s += lt[512 + ((ww[h] >> 16) & 255)];
+                            s += lt[768 + (ww[h] >> 24)];
+                        }
+                    }
+                } else if ((p.m & 3) == 0) {
                     const uint32_t *cw = reinterpret_cast<const uint32_t *>(code);
                     for (int j4 = 0; j4 < p.m / 4; j4++) {
                         const uint32_t w = cw[j4];
@@ -336,20 +370,9 @@ __global__ void __launch_bounds__(256) ivfpq_scan_kernel(const IvfScanParams p) 
         }
     }
     __syncthreads();
-    if (warp == 0) {
-        for (int w = 1; w < 8; w++)
-            for (int j = 0; j < p.k; j++) {
-                const float ck = lk[(size_t)w * p.k + j];
-                if (!(ck < FLT_MAX)) break;
-                list.insert(ck, li[(size_t)w * p.k + j]);
-            }
-        float *ok = p.part_keys + ((size_t)q * p.nprobe + pr) * p.k;
-        uint32_t *oi = p.part_ids + ((size_t)q * p.nprobe + pr) * p.k;
-        for (int j = lane; j < p.k; j += 32) {
-            ok[j] = j < list.n ? list.keys[j] : FLT_MAX;
-            oi[j] = j < list.n ? list.ids[j] : kNoId;
-        }
-    }
+    // the 8 warp lists -> this (query, list)'s partial top-k
+    block_rank_merge(lk, li, 8, p.k, p.k, p.part_keys + ((size_t)q * p.nprobe + pr) * p.k,
+                     p.part_ids + ((size_t)q * p.nprobe + pr) * p.k);
 }
 
 // ------------------------------------------------------------------------------------
@@ -403,19 +426,15 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineParams p) {
         list.insert(p.l2 ? acc : -acc, (uint32_t)id);
     }
     __syncthreads();
-    if (warp == 0) {
-        for (int w = 1; w < 8; w++)
-            for (int j = 0; j < p.k; j++) {
-                const float ck = lk[(size_t)w * p.k + j];
-                if (!(ck < FLT_MAX)) break;
-                list.insert(ck, li[(size_t)w * p.k + j]);
-            }
-        for (int j = lane; j < p.k; j += 32) {
-            const bool have = j < list.n;
-            const float key = have ? list.keys[j] : 0.f;
-            p.out_ids[q * p.k + j] = have ? (int64_t)list.ids[j] : -1;
-            p.out_dis[q * p.k + j] = !have ? (p.l2 || p.cosine ? FLT_MAX : -FLT_MAX) : p.l2 ? key : p.cosine ? 1.f + key : -key;
-        }
+    float *fk = lk + (size_t)8 * p.k * 2;  // merged list, behind the 8 warp lists (keys + ids)
+    uint32_t *fi = reinterpret_cast<uint32_t *>(fk + p.k);
+    block_rank_merge(lk, li, 8, p.k, p.k, fk, fi);
+    __syncthreads();
+    for (int j = threadIdx.x; j < p.k; j += blockDim.x) {
+        const bool have = fi[j] != kNoId;
+        const float key = have ? fk[j] : 0.f;
+        p.out_ids[q * p.k + j] = have ? (int64_t)fi[j] : -1;
+        p.out_dis[q * p.k + j] = !have ? (p.l2 || p.cosine ? FLT_MAX : -FLT_MAX) : p.l2 ? key : p.cosine ? 1.f + key : -key;
     }
 }
 
@@ -448,6 +467,7 @@ struct b200_index {
     uint32_t *d_list_off = nullptr, *d_list_ids = nullptr;
     uint8_t *d_codes = nullptr;
     std::vector<uint32_t> list_off;
+    double biased_list_rows = 0;    // sum(size^2) / n over the inverted lists (planner input)
     int device = 0;
     cudaStream_t stream = nullptr;
     std::mutex mu;
@@ -535,6 +555,15 @@ extern "C" int b200_index_free(b200_index *ix) {
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
     return B200_OK;
+}
+
+static void set_biased_list_rows(b200_index *ix) {
+    double ss = 0;
+    for (int l = 0; l < ix->nlist; l++) {
+        const double sz = (double)ix->list_off[l + 1] - (double)ix->list_off[l];
+        ss += sz * sz;
+    }
+    ix->biased_list_rows = ix->n > 0 ? ss / (double)ix->n : 0;
 }
 
 // k-means on device rows x [n][stride]; centroids written to d_c [nc][d]
@@ -650,6 +679,7 @@ extern "C" int b200_index_build(b200_index *ix, const float *rows, int64_t n) {
         ix->list_off.assign(nl + 1, 0);
         for (int64_t i = 0; i < n; i++) ix->list_off[ls[i] + 1]++;
         for (int l = 0; l < nl; l++) ix->list_off[l + 1] += ix->list_off[l];
+        set_biased_list_rows(ix);
         B200_CUDA_OK(cudaMalloc(&ix->d_list_off, (size_t)(nl + 1) * 4));
         B200_CUDA_OK(cudaMemcpy(ix->d_list_off, ix->list_off.data(), (size_t)(nl + 1) * 4, cudaMemcpyHostToDevice));
     }
@@ -733,7 +763,7 @@ static int refine_device(b200_index *ix, const float *d_q /*[nq][d_pad] prepared
     rp.k = k;
     rp.l2 = ix->metric == B200_METRIC_L2;
     rp.cosine = ix->metric == B200_METRIC_COSINE;
-    const size_t smem = (size_t)ix->d_pad * 4 + (size_t)8 * k * 8;
+    const size_t smem = (size_t)ix->d_pad * 4 + (size_t)9 * k * 8;
     B200_CUDA_OK(cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     refine_kernel<<<(unsigned)nq, 256, smem, s>>>(rp);
     g_launches++;
@@ -750,6 +780,33 @@ static int prepare_queries(b200_index *ix, const float *queries, int64_t nq, cud
     return B200_OK;
 }
 
+// Batch planner.  An IVF probe costs per query; the exact pass costs per 8-query scan pass or per 256-query tensor-core
+// tile.  Rates are measured ones (profiles/r01_ivf_latency.log):
+//  * IVF: one CTA per (query, list) walks its list at ~8 rows/us (PQ, 96-byte codes) or ~25 rows/us (IVFFLAT rows of
+//    3 KB); 296 CTAs run at once; ~0.2 ms of fixed work (coarse probe, merges, refine).  The list a query lands in is
+//    size-biased: expected rows = sum(size^2) / n, which is what `biased_list_rows` holds (clustered data makes it
+//    10x the mean).
+//  * exact: one query 5 TB/s, up to 8 queries 2.5 TB/s per pass, 16+ queries 850 TFLOP/s of tf32 MMA work at three
+//    products per term (ip_gemm_tf32x3_sm100.cu), never below the one-pass HBM time.
+// `exact_batch=0|1` in the search parameters overrides the choice.
+static bool exact_batch_is_cheaper(const b200_index *ix, int64_t nq, const char *params) {
+    const int force = parse_int_param(params, "exact_batch", -1);
+    if (force >= 0) return force != 0;
+    int nprobe = parse_int_param(params, "nprobe", ix->default_nprobe);
+    nprobe = std::max(1, std::min(nprobe, ix->nlist));
+    const double list_rows = ix->biased_list_rows > 0 ? ix->biased_list_rows : (double)ix->n / ix->nlist;
+    const double t_list = list_rows / (ix->type == IDX_IVFFLAT ? 25e6 : 8e6);
+    const double waves = std::max(1.0, (double)nq * nprobe / 296.0);
+    const double t_ivf = 0.2e-3 + t_list * waves;
+    const double row_bytes = (double)ix->n * ix->d_pad * 4;
+    double t_exact;
+    if (nq >= 16) t_exact = std::max(row_bytes / 5e12, (double)round_up(nq, 256) * ix->n * ix->d_pad * 6.0 / 850e12);
+    else if (nq == 1) t_exact = row_bytes / 5e12;
+    else t_exact = (double)ceil_div(nq, 8) * row_bytes / 2.5e12;
+    t_exact += 0.1e-3;
+    return t_exact < t_ivf;
+}
+
 // Search::VectorIndex::search(queries, k, params, first_stage_only, filter) (VIWithDataPart.cpp:926)
 extern "C" int b200_index_search(b200_index *ix, const float *queries, int64_t nq, int k, const char *params, int first_stage_only,
                                  const uint8_t *alive_bits, float *out_dis, int64_t *out_ids, int64_t *out_num_candidates) {
@@ -757,8 +814,9 @@ extern "C" int b200_index_search(b200_index *ix, const float *queries, int64_t n
     if (!ix->built) return fail(B200_ERR_INVALID, "index not built");
     if (out_num_candidates) *out_num_candidates = k;
     if (nq == 0) return B200_OK;
-    if (!ix->use_ivf) {
-        // FLAT / fallback-to-flat: exact scan of the raw rows
+    if (!ix->use_ivf || exact_batch_is_cheaper(ix, nq, params)) {
+        // FLAT / fallback-to-flat, or a batch large enough that one exact pass over the raw rows on the tensor cores
+        // (3xTF32, ip_gemm_tf32x3_sm100.cu) costs less than nq list probes: exact scan of the raw rows, recall 1
         int rc = b200_corpus_search(ix->raw, queries, nq, k, alive_bits, out_dis, out_ids);
         if (rc == B200_OK && ix->metric == B200_METRIC_COSINE) {
             // raw rows are unit vectors searched under IP with unnormalised queries: finish the cosine
@@ -833,7 +891,7 @@ extern "C" int b200_index_search(b200_index *ix, const float *queries, int64_t n
         B200_CUDA_OK(cudaFuncSetAttribute(ivf_flat_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ivf_flat_scan_kernel<<<grid, 256, smem, s>>>(sp);
     } else {
-        const size_t smem = (size_t)ix->m * 256 * 4 + (size_t)8 * k1 * 8;
+        const size_t smem = (size_t)ix->m * 256 * 4 + (size_t)8 * k1 * 8 + (size_t)ix->d * 4;
         if (smem > 220 * 1024) return fail(B200_ERR_UNSUPPORTED, "PQ look-up table (m * 1 KB) + top-k lists exceed shared memory");
         B200_CUDA_OK(cudaFuncSetAttribute(ivfpq_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ivfpq_scan_kernel<<<grid, 256, smem, s>>>(sp);
@@ -1007,6 +1065,9 @@ extern "C" int b200_index_load(const char *path, b200_index **out) {
         if (cudaMalloc(&ix->d_list_off, (size_t)(h.nlist + 1) * 4) != cudaSuccess ||
             cudaMemcpy(ix->d_list_off, ix->list_off.data(), (size_t)(h.nlist + 1) * 4, cudaMemcpyHostToDevice) != cudaSuccess)
             return bail("cudaMalloc failed");
+        ix->nlist = h.nlist;
+        ix->n = h.n;
+        set_biased_list_rows(ix);
         if (h.type == IDX_IVFPQ || h.type == IDX_MSTG)
             if (!slurp((void **)&ix->d_pq, (size_t)h.m * 256 * h.dsub * 4) || !slurp((void **)&ix->d_codes, (size_t)h.n * h.m))
                 return bail("truncated index file (codes)");

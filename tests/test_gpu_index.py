@@ -30,11 +30,11 @@ def test_ivfflat_all_lists_equals_exact(metric):
     y, q = _clustered(30000, 64, 200, 1)
     ix = b2.VectorIndex("IVFFLAT", metric, 64, "ncentroids=64").build(y)
     assert ix.info()["uses_ivf"]
-    dg, ig = ix.search(q, 10, "nprobe=64")
+    dg, ig = ix.search(q, 10, "nprobe=64, exact_batch=0")
     do, io = orc.search_without_index(metric, q, y, 10)
     check_topk(metric, q, y, dg, ig, do, io, rtol=2e-4, atol=2e-5, min_exact=0.995)
     # a few lists only: recall drops but stays high on clustered data
-    d2, i2 = ix.search(q, 10, "nprobe=8")
+    d2, i2 = ix.search(q, 10, "nprobe=8, exact_batch=0")
     assert _recall(i2, io) > 0.8
 
 
@@ -42,7 +42,7 @@ def test_ivfflat_alive_bitmap():
     y, q = _clustered(20000, 32, 100, 2)
     alive = np.random.default_rng(3).random(20000) < 0.5
     ix = b2.VectorIndex("IVFFLAT", b2.L2, 32, "ncentroids=32").build(y)
-    dg, ig = ix.search(q, 10, "nprobe=32", alive_bits=orc.pack_bits(alive))
+    dg, ig = ix.search(q, 10, "nprobe=32, exact_batch=0", alive_bits=orc.pack_bits(alive))
     do, io = orc.search_without_index(orc.L2, q, y, 10, alive=orc.pack_bits(alive))
     check_topk(b2.L2, q, y, dg, ig, do, io, rtol=2e-4, atol=2e-5, min_exact=0.995)
 
@@ -54,7 +54,7 @@ def test_two_stage_mstg_recall_and_exact_distances(metric):
     info = ix.info()
     assert info["uses_ivf"] and info["m"] == 24
     do, io = orc.search_without_index(metric, q, y, 10)
-    dg, ig = ix.search(q, 10, "nprobe=32, refine_factor=16")
+    dg, ig = ix.search(q, 10, "nprobe=32, refine_factor=16, exact_batch=0")
     assert ix.last_num_candidates == 160
     rec = _recall(ig, io)
     assert rec >= 0.95, rec
@@ -65,17 +65,37 @@ def test_two_stage_mstg_recall_and_exact_distances(metric):
             assert abs(dg[qi, j] - t) <= 1e-4 * max(1.0, abs(t))
     assert (np.diff(dg, axis=1) >= -1e-6).all()
     # first stage only: approximate (ADC) distances, wider candidate list semantics of the reference
-    d1, i1 = ix.search(q, 160, "nprobe=32", first_stage_only=True)
+    d1, i1 = ix.search(q, 160, "nprobe=32, exact_batch=0", first_stage_only=True)
     assert (i1 >= 0).all() and (np.diff(d1, axis=1) >= -1e-6).all()
     # the 160 first-stage candidates must already contain (almost) all true top-10 -- that is what stage 2 re-ranks
     assert np.mean([len(set(a.tolist()) & set(b.tolist())) / 10 for a, b in zip(i1, io)]) >= 0.95
+
+
+def test_batch_planner_routes_large_batches_to_the_exact_tensor_core_pass():
+    """With no `exact_batch` override the index compares the cost of nq list probes with one exact 3xTF32 pass over
+    the raw rows: a 64-query batch on a 400k-row part goes exact (recall 1, k candidates), one query probes the lists."""
+    y, q = _clustered(400000, 96, 2000, 5)
+    ix = b2.VectorIndex("MSTG", b2.L2, 96, "ncentroids=512, M=24").build(y)
+    do, io = orc.search_without_index(orc.L2, q, y, 10)
+    dg, ig = ix.search(q, 10, "nprobe=32, refine_factor=16")
+    assert ix.last_num_candidates == 10          # exact route: no over-fetch
+    check_topk(b2.L2, q, y, dg, ig, do, io, rtol=4e-5, atol=2e-5, min_exact=0.995)
+    d1, i1 = ix.search(q[:1], 10, "nprobe=32, refine_factor=16, exact_batch=0")
+    assert ix.last_num_candidates == 160         # forced probe: IVFPQ candidates + exact refine
+    assert _recall(i1, io[:1]) >= 0.9
+    d2, i2 = ix.search(q[:1], 10, "nprobe=32, refine_factor=16, exact_batch=1")
+    assert ix.last_num_candidates == 10 and i2[0].tolist() == io[0].tolist()
+    # one query, no override: whichever route the cost model picks (it depends on how skewed the lists came out),
+    # the answer must be a valid two-stage / exact result
+    d3, i3 = ix.search(q[:1], 10, "nprobe=32, refine_factor=16")
+    assert ix.last_num_candidates in (10, 160) and _recall(i3, io[:1]) >= 0.9
 
 
 def test_ivfpq_ip_adc_recall():
     y, q = _clustered(40000, 64, 300, 8)
     ix = b2.VectorIndex("IVFPQ", b2.IP, 64, "ncentroids=64, M=32").build(y)
     do, io = orc.search_without_index(orc.IP, q, y, 10)
-    dg, ig = ix.search(q, 10, "nprobe=64")
+    dg, ig = ix.search(q, 10, "nprobe=64, exact_batch=0")
     assert _recall(ig, io) >= 0.6
     # ADC scores approximate the true inner products
     true = np.array([[float(q[a] @ y[ig[a, j]]) for j in range(10)] for a in range(len(q))])
@@ -128,10 +148,10 @@ def test_index_above_one_grid_of_rows_regression():
     flat = b2.Corpus(b2.L2, d).append(y)
     dt, it = flat.search(q, 10)
     ix = b2.VectorIndex("MSTG", b2.L2, d, "ncentroids=512, M=8").build(y)
-    dg, ig = ix.search(q, 10, "nprobe=64, refine_factor=16")
+    dg, ig = ix.search(q, 10, "nprobe=64, refine_factor=16, exact_batch=0")
     assert _recall(ig, it) >= 0.95
     iv = b2.VectorIndex("IVFFLAT", b2.L2, d, "ncentroids=256").build(y)
-    d2, i2 = iv.search(q, 10, "nprobe=256")
+    d2, i2 = iv.search(q, 10, "nprobe=256, exact_batch=0")
     check_topk(b2.L2, q, y, d2, i2, dt, it, rtol=2e-4, atol=2e-5, min_exact=0.99)
 
 
@@ -148,11 +168,11 @@ def test_serialize_load_roundtrip_and_golden_00001_after_reload(goldens, tmp_pat
     # IVFPQ two-stage index: identical results before and after the round trip
     yy, q = _clustered(40000, 64, 300, 21)
     a = b2.VectorIndex("MSTG", b2.COSINE, 64, "ncentroids=64, M=16").build(yy)
-    d0, i0 = a.search(q, 10, "nprobe=16")
+    d0, i0 = a.search(q, 10, "nprobe=16, exact_batch=0")
     a.save(tmp_path / "mstg.b2ix")
     b = b2.VectorIndex.load(tmp_path / "mstg.b2ix", 64)
     assert b.info() == a.info()
-    d1, i1 = b.search(q, 10, "nprobe=16")
+    d1, i1 = b.search(q, 10, "nprobe=16, exact_batch=0")
     assert (i0 == i1).all() and np.array_equal(d0, d1)
     with pytest.raises(b2.B200Error):
         b2.VectorIndex.load(tmp_path / "missing.b2ix", 64)

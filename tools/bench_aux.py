@@ -52,10 +52,13 @@ def bench_ivfpq():
     out = {"workload": f"IVFPQ nlist={nlist} m={m}, {n} x {d}-d fp32 unit vectors, batch {nq}, top-{k} (config 4 shape, 1 GPU)",
            "build_s": t_build, "points": []}
     for nprobe in (8, 32, 64):
-        t, (dis, ids) = timed(lambda: ix.search(q, k, f"nprobe={nprobe}"))
+        t, (dis, ids) = timed(lambda: ix.search(q, k, f"nprobe={nprobe}, exact_batch=0"))
         out["points"].append({"nprobe": nprobe, "qps": nq / t, "recall@10_first_stage": recall(ids[:1000], truth),
                               "code_bytes_per_query": nprobe / nlist * n * m,
                               "code_GB_per_s": nprobe / nlist * n * m * nq / t / 1e9})
+    # the index's own batch planner (no override): one exact 3xTF32 pass over the raw fp32 rows when that is cheaper
+    t, (dis, ids) = timed(lambda: ix.search(q, k, "nprobe=32"))
+    out["planner_auto"] = {"qps": nq / t, "recall@10": recall(ids[:1000], truth), "candidates": ix.last_num_candidates}
     print(json.dumps(out))
 
 
@@ -70,8 +73,12 @@ def bench_mstg():
     out = {"workload": f"two-stage (MSTG-type: IVFPQ + exact refine) {n} x {d}-d fp32, batch {nq}, top-{k} (config 3 shape, 1 GPU shard)",
            "build_s": t_build, "exact_flat_scan_qps": nq / t_flat, "points": []}
     for nprobe, rf in ((16, 8), (32, 16), (64, 16)):
-        t, (dis, ids) = timed(lambda: ix.search(q, k, f"nprobe={nprobe}, refine_factor={rf}"))
+        t, (dis, ids) = timed(lambda: ix.search(q, k, f"nprobe={nprobe}, refine_factor={rf}, exact_batch=0"))
         out["points"].append({"nprobe": nprobe, "refine_factor": rf, "qps": nq / t, "recall@10": recall(ids, truth)})
+    for nq_b in (256, 16, 1):
+        t, (dis, ids) = timed(lambda: ix.search(q[:nq_b], k, "nprobe=32, refine_factor=16"))
+        out.setdefault("planner_auto", []).append({"batch": nq_b, "qps": nq_b / t, "recall@10": recall(ids, truth[:nq_b]),
+                                                   "candidates": ix.last_num_candidates})
     # CPU arm: the oracle's exact threaded brute force on a row sample (the reference would run its closed CPU MSTG)
     rows = 100_000
     t0 = time.perf_counter()
