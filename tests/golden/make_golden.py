@@ -178,6 +178,45 @@ def main():
         "rsf_1part": [[int(x[0]), float(x[1])] for x in s["Hybrid search RSF result with 1 part after optimize final"]],
     }
 
+    # 00003: PREWHERE filter on the 100-row FLAT table (filter bitmap path), top-20 ordered by (d, id)
+    r = rows(read("00003_mqvs_distance_with_prewhere.reference"))
+    g["00003_prewhere"] = {
+        "source": "tests/queries/2_vector_search/00003_mqvs_distance_with_prewhere.{sh,reference}",
+        "corpus": "row n = [n,n,n] for n in range(100)", "query": [1.0, 1.0, 1.0], "metric": "L2", "k": 20,
+        "filter": "id < 10 or id > 60",
+        "expect": [[int(x[0]), float(x[2])] for x in r],
+    }
+
+    # 00008: empty vectors (ids 10..29 are []), 430 rows, query [20]*3: first through the IVFFLAT index, then FLAT
+    r = rows(read("00008_mqvs_empty_vector.reference"))
+    g["00008_empty_vectors"] = {
+        "source": "tests/queries/2_vector_search/00008_mqvs_empty_vector.{sh,reference} + helpers/00000_prepare_data_with_empty_vectors.sh",
+        "corpus": "ids 0..9 = [n]*3, ids 10..29 = [] (empty), ids 30..429 = [n]*3", "query": [20.0] * 3, "metric": "L2", "k": 10,
+        "expect_ivfflat": [[int(x[0]), float(x[2])] for x in r[:10]],
+        "expect_flat": [[int(x[0]), float(x[2])] for x in r[10:20]],
+    }
+
+    # 00009 / 00011: brute force + PREWHERE on the 10030-row table with empty vectors (helper 2), top-100
+    for name, key, flt, q in (("00009_mqvs_brute_force_search_prewhere_0", "00009_bruteforce_prewhere",
+                               "id > 5000 or id in (9, 31, 999, 1)", [10020.1] * 3),
+                              ("00011_mqvs_brute_force_search_where", "00011_bruteforce_prewhere_sparse",
+                               "id < 50 or id in (51, 55, 99, 100, 9999)", [10020.0] * 3)):
+        r = rows(read(name + ".reference"))
+        g[key] = {
+            "source": f"tests/queries/2_vector_search/{name}.{{sh,reference}} + helpers/00000_prepare_index_2.sh",
+            "corpus": "ids 0..9 = [n]*3, ids 10..29 = [] (empty), ids 30..10029 = [n]*3; index_granularity=128",
+            "query": q, "metric": "L2", "k": 100, "filter": flt,
+            "expect": [[int(x[0]), float(x[2])] for x in r],
+        }
+
+    # 00016: lightweight delete of id = 2 on 2100 rows, top-10
+    r = [x for x in rows(read("00016_mqvs_lightweight_delete_with_vector.reference")) if len(x) == 3]
+    g["00016_lightweight_delete"] = {
+        "source": "tests/queries/2_vector_search/00016_mqvs_lightweight_delete_with_vector.{sql,reference}",
+        "corpus": "row n = [n,n,n] for n in range(2100); DELETE WHERE id = 2", "query": [0.1] * 3, "metric": "L2", "k": 10,
+        "expect": [[int(x[0]), float(x[2])] for x in r],
+    }
+
     with open(os.path.join(OUT, "reference_goldens.json"), "w") as f:
         json.dump(g, f, indent=1)
     print("wrote", os.path.join(OUT, "reference_goldens.json"), "cases:", list(g))

@@ -34,6 +34,58 @@ def test_golden_00012_part_scan_with_empty_rows(goldens):
     np.testing.assert_allclose(dis[0], [e[1] for e in g["expect"]], rtol=1e-5)
 
 
+def _expect(dis, ids, exp, k, rtol=1e-6):
+    n = len(exp)
+    assert ids[0, :n].tolist() == [e[0] for e in exp]
+    np.testing.assert_allclose(dis[0, :n], [e[1] for e in exp], rtol=rtol)
+    assert (ids[0, n:k] == -1).all()
+
+
+def test_golden_00003_prewhere_filter(goldens):
+    g = goldens["00003_prewhere"]
+    idv = np.arange(100)
+    bits = orc.pack_bits((idv < 10) | (idv > 60))
+    q = np.array([g["query"]], F32)
+    dis, ids = b2.part_scan(b2.L2, q, _nnn(0, 100), g["k"], block_rows=1024, filter_bits=bits)
+    _expect(dis, ids, g["expect"], g["k"])
+    c = b2.Corpus(b2.L2, 3).append(_nnn(0, 100))  # FLAT index + DenseBitmap filter
+    dis, ids = c.search(q, g["k"], alive_bits=bits)
+    _expect(dis, ids, g["expect"], g["k"])
+
+
+def test_golden_00008_empty_vectors(goldens):
+    g = goldens["00008_empty_vectors"]
+    y = _nnn(0, 430)
+    y[10:30] = np.finfo(np.float32).max
+    q = np.array([g["query"]], F32)
+    dis, ids = b2.part_scan(b2.L2, q, y, g["k"], block_rows=1024)
+    _expect(dis, ids, g["expect_flat"], g["k"])
+    keep = np.r_[0:10, 30:430]  # an index is built from the rows that exist; labels map back through the row ids
+    ix = b2.VectorIndex("IVFFLAT", b2.L2, 3, "ncentroids = 10").build(y[keep])
+    dis, pos = ix.search(q, g["k"], "nprobe=10")
+    assert keep[pos[0]].tolist() == [e[0] for e in g["expect_ivfflat"]]
+    np.testing.assert_allclose(dis[0], [e[1] for e in g["expect_ivfflat"]], rtol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["00009_bruteforce_prewhere", "00011_bruteforce_prewhere_sparse"])
+def test_golden_00009_00011_bruteforce_with_prewhere(goldens, name):
+    g = goldens[name]
+    idv = np.arange(10030)
+    m = ((idv > 5000) | np.isin(idv, [9, 31, 999, 1])) if name.startswith("00009") else ((idv < 50) | np.isin(idv, [51, 55, 99, 100, 9999]))
+    y = _nnn(0, 10030)
+    y[10:30] = np.finfo(np.float32).max
+    dis, ids = b2.part_scan(b2.L2, np.array([g["query"]], F32), y, g["k"], block_rows=128, filter_bits=orc.pack_bits(m))
+    _expect(dis, ids, g["expect"], g["k"], rtol=1e-5)
+
+
+def test_golden_00016_lightweight_delete(goldens):
+    g = goldens["00016_lightweight_delete"]
+    row_exists = np.ones(2100, np.uint8)
+    row_exists[2] = 0
+    dis, ids = b2.part_scan(b2.L2, np.array([g["query"]], F32), _nnn(0, 2100), g["k"], block_rows=1024, row_exists=row_exists)
+    _expect(dis, ids, g["expect"], g["k"])
+
+
 @pytest.mark.parametrize("name,metric", [("00002_batch_l2", b2.L2), ("00002_batch_ip", b2.IP)])
 def test_golden_00002_batch(goldens, name, metric):
     g = goldens[name]

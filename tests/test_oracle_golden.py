@@ -254,3 +254,64 @@ def test_cpu_baseline_blas_matches_checker(metric):
     d1, i1 = res
     assert (i0 == i1).mean() > 0.999
     np.testing.assert_allclose(d0, d1, rtol=2e-4, atol=2e-4)
+
+
+# ---------------------------------------------------------------- filters, empty rows, lightweight delete (more goldens)
+def _helper2_corpus():
+    """helpers/00000_prepare_index_2.sh: ids 0..9 = [n]*3, ids 10..29 empty vectors, ids 30..10029 = [n]*3."""
+    y = _corpus_nnn(0, 10030)
+    y[10:30] = np.finfo(np.float32).max  # empty rows padded FLT_MAX (MergeTreeVSManager.cpp:1380)
+    return y
+
+
+def _check_exact(dis, ids, exp, k):
+    n = len(exp)
+    assert ids[0, :n].tolist() == [e[0] for e in exp]
+    assert dis[0, :n].tolist() == [float(F32(e[1])) for e in exp]
+    assert (ids[0, n:k] == -1).all()
+
+
+def test_00003_prewhere_filter_bitmap_bitexact(goldens):
+    g = goldens["00003_prewhere"]
+    idv = np.arange(100)
+    bits = orc.pack_bits((idv < 10) | (idv > 60))
+    dis, ids = orc.part_scan(orc.L2, np.array([g["query"]], F32), _corpus_nnn(0, 100), g["k"], block_rows=1024, filter_bits=bits)
+    _check_exact(dis, ids, g["expect"], g["k"])
+    dis, ids = orc.knn_flat(orc.L2, np.array([g["query"]], F32), _corpus_nnn(0, 100), g["k"], alive=bits)  # FLAT index + filter
+    _check_exact(dis, ids, g["expect"], g["k"])
+
+
+def test_00008_empty_vectors_bitexact(goldens):
+    g = goldens["00008_empty_vectors"]
+    y = _corpus_nnn(0, 430)
+    y[10:30] = np.finfo(np.float32).max
+    with np.errstate(over="ignore"):
+        dis, ids = orc.part_scan(orc.L2, np.array([g["query"]], F32), y, g["k"], block_rows=1024)
+    _check_exact(dis, ids, g["expect_flat"], g["k"])
+    # an index never receives the empty rows (VIPartReader skips them): same answer from the rows that exist
+    keep = np.r_[0:10, 30:430]
+    dis, pos = orc.knn_flat(orc.L2, np.array([g["query"]], F32), y[keep], g["k"])
+    assert keep[pos[0]].tolist() == [e[0] for e in g["expect_ivfflat"]]
+    assert dis[0].tolist() == [float(F32(e[1])) for e in g["expect_ivfflat"]]
+
+
+@pytest.mark.parametrize("name", ["00009_bruteforce_prewhere", "00011_bruteforce_prewhere_sparse"])
+def test_00009_00011_bruteforce_with_prewhere_bitexact(goldens, name):
+    g = goldens[name]
+    idv = np.arange(10030)
+    if name.startswith("00009"):
+        m = (idv > 5000) | np.isin(idv, [9, 31, 999, 1])
+    else:
+        m = (idv < 50) | np.isin(idv, [51, 55, 99, 100, 9999])
+    with np.errstate(over="ignore"):
+        dis, ids = orc.part_scan(orc.L2, np.array([g["query"]], F32), _helper2_corpus(), g["k"], block_rows=128,
+                                 filter_bits=orc.pack_bits(m))
+    _check_exact(dis, ids, g["expect"], g["k"])
+
+
+def test_00016_lightweight_delete_bitexact(goldens):
+    g = goldens["00016_lightweight_delete"]
+    row_exists = np.ones(2100, np.uint8)
+    row_exists[2] = 0
+    dis, ids = orc.part_scan(orc.L2, np.array([g["query"]], F32), _corpus_nnn(0, 2100), g["k"], block_rows=1024, row_exists=row_exists)
+    _check_exact(dis, ids, g["expect"], g["k"])
