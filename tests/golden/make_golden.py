@@ -217,6 +217,22 @@ def main():
         "expect": [[int(x[0]), float(x[2])] for x in r],
     }
 
+    # 00040 with lightweight delete: same 20 docs; DELETE id = 13 keeps the index statistics (the doc stays in the
+    # segment, only the alive bitmap changes); hybrid RSF with an EMPTY text list (part without an FTS index)
+    s = sections(read("00040_mqvs_hybrid_search_with_lwd.reference"), lambda ln: not re.match(r"^\d+(\t|$)", ln))
+    pr = lambda h: [[int(x[0]), float(x[1])] for x in s[h]]
+    g["00040_hybrid_with_lwd"] = {
+        "source": "tests/queries/2_vector_search/00040_mqvs_hybrid_search_with_lwd.{sql,reference}",
+        "docs": "the 20 docs of 00040_hybrid; vectors [n,n,n]", "query_text": "Ancient", "query_vector": [1.0, 1.0, 1.0],
+        "deleted_id": 13,
+        "text_before_lwd_top1": pr("text search before LWD"),
+        "text_after_lwd_top1": pr("text search after LWD"),
+        "text_no_index": pr("text search on part w/o tantivy index"),
+        "rsf_no_text_index": pr("hybrid search rsf on part w/o tantivy index"),
+        "text_after_lwd_top2": pr("text search on part with index after LWD"),
+        "rsf_after_lwd": pr("hybrid search rsf on part with index after LWD"),
+    }
+
     with open(os.path.join(OUT, "reference_goldens.json"), "w") as f:
         json.dump(g, f, indent=1)
     print("wrote", os.path.join(OUT, "reference_goldens.json"), "cases:", list(g))

@@ -39,6 +39,33 @@ def test_goldens_rsf_rrf_end_to_end_on_gpu(goldens):
     assert [[i, s] for i, s in _order(rsf)] == [[e[0], float(F32(e[1]))] for e in goldens["00041_multi_parts"]["rsf_1part"]]
 
 
+def test_golden_00040_hybrid_with_lightweight_delete_on_gpu(goldens):
+    """DELETE id = 13: statistics unchanged, alive bitmap drops the doc; a part without an FTS index gives the fusion
+    an EMPTY text list (00040_mqvs_hybrid_search_with_lwd)."""
+    g = goldens["00040_hybrid_with_lwd"]
+    ix = b2.BM25Index(1)
+    for rid, _, doc in goldens["00040_hybrid"]["docs"]:
+        ix.add_doc(rid, [doc])
+    ix.commit()
+    rows, sc = ix.search(g["query_text"], 1)
+    assert [[int(rows[0]), float(sc[0])]] == [[e[0], float(F32(e[1]))] for e in g["text_before_lwd_top1"]]
+    alive = np.ones(20, bool); alive[g["deleted_id"]] = False
+    rows, sc = ix.search(g["query_text"], 2, alive_bits=orc.pack_bits(alive))
+    assert [[int(r), float(x)] for r, x in zip(rows, sc)] == [[e[0], float(F32(e[1]))] for e in g["text_after_lwd_top2"]]
+    y = np.repeat(np.arange(20, dtype=np.float32)[:, None], 3, axis=1)
+    q = np.array([g["query_vector"]], F32)
+    dis, ids = b2.part_scan(b2.L2, q, y, 5)
+    vec = [(0, 0, int(i), float(d)) for i, d in zip(ids[0], dis[0])]
+    rsf = b2.hybrid_fusion_batch("rsf", [vec], [[]], 5)[0]
+    assert [[i, x] for i, x in _order(rsf)] == [[e[0], float(F32(e[1]))] for e in g["rsf_no_text_index"]]
+    dis, ids = b2.part_scan(b2.L2, q, y, 5, row_exists=alive.astype(np.uint8))
+    vec = [(0, 0, int(i), float(d)) for i, d in zip(ids[0], dis[0])]
+    rows, sc = ix.search(g["query_text"], 5, alive_bits=orc.pack_bits(alive))
+    txt = [(0, 0, int(r), float(x)) for r, x in zip(rows, sc)]
+    rsf = b2.hybrid_fusion_batch("rsf", [vec], [txt], 5)[0]
+    assert [[i, x] for i, x in _order(rsf)] == [[e[0], float(F32(e[1]))] for e in g["rsf_after_lwd"]]
+
+
 @pytest.mark.parametrize("ft", ["rsf", "rrf"])
 @pytest.mark.parametrize("direction", [1, -1])
 def test_random_lists_match_oracle_bitexact(ft, direction):

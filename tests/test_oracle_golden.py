@@ -315,3 +315,29 @@ def test_00016_lightweight_delete_bitexact(goldens):
     row_exists[2] = 0
     dis, ids = orc.part_scan(orc.L2, np.array([g["query"]], F32), _corpus_nnn(0, 2100), g["k"], block_rows=1024, row_exists=row_exists)
     _check_exact(dis, ids, g["expect"], g["k"])
+
+
+def test_00040_hybrid_with_lightweight_delete_bitexact(goldens):
+    """DELETE id = 13: the document stays in the segment (statistics unchanged), only the alive bitmap drops it;
+    a part without an FTS index contributes an EMPTY text list to the fusion."""
+    g = goldens["00040_hybrid_with_lwd"]
+    ix = _index20(goldens)
+    rows, sc = ix.search(g["query_text"], 1)
+    assert [[int(rows[0]), float(sc[0])]] == [[e[0], float(F32(e[1]))] for e in g["text_before_lwd_top1"]]
+    alive = np.ones(20, bool); alive[g["deleted_id"]] = False
+    rows, sc = ix.search(g["query_text"], 2, alive=orc.pack_bits(alive))
+    assert [[int(r), float(x)] for r, x in zip(rows, sc)] == [[e[0], float(F32(e[1]))] for e in g["text_after_lwd_top2"]]
+    # vector side: brute force over [n,n,n], num_candidates = 5 (as in the other 00040 goldens)
+    y = _corpus_nnn(0, 20)
+    q = np.array([g["query_vector"]], F32)
+    dis, ids = orc.part_scan(orc.L2, q, y, 5)
+    vec = [(0, 0, int(i), float(d)) for i, d in zip(ids[0], dis[0])]
+    rsf = orc.hybrid_fusion("rsf", vec, [], 5)
+    assert [[i, float(F32(x))] for i, x in _order_by_score_desc_id(rsf)] == [[e[0], float(F32(e[1]))] for e in g["rsf_no_text_index"]]
+    row_exists = alive.astype(np.uint8)
+    dis, ids = orc.part_scan(orc.L2, q, y, 5, row_exists=row_exists)
+    vec = [(0, 0, int(i), float(d)) for i, d in zip(ids[0], dis[0])]
+    rows, sc = ix.search(g["query_text"], 5, alive=orc.pack_bits(alive))
+    txt = [(0, 0, int(r), float(x)) for r, x in zip(rows, sc)]
+    rsf = orc.hybrid_fusion("rsf", vec, txt, 5)
+    assert [[i, float(F32(x))] for i, x in _order_by_score_desc_id(rsf)] == [[e[0], float(F32(e[1]))] for e in g["rsf_after_lwd"]]
