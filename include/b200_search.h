@@ -38,6 +38,7 @@ extern "C" {
 #define B200_ERR_UNSUPPORTED 3 /* valid request this build does not implement */
 #define B200_ERR_NO_DEVICE 4   /* no sm_100 device visible */
 #define B200_ERR_NOMEM 5
+#define B200_ERR_NOT_FOUND 6   /* cache miss */
 
 /* Search::Metric (MergeTreeVSManager.cpp:1560-1578) */
 #define B200_METRIC_L2 0
@@ -162,6 +163,39 @@ int b200_index_refine(b200_index *ix, const float *queries, int64_t nq, const in
 int b200_index_save(b200_index *ix, const char *path);
 int b200_index_load(const char *path, b200_index **out);
 int b200_index_free(b200_index *ix);
+
+/* ------------------------------------------------------------------------------------
+ * HBM residency cache: the device-side VICacheManager (VectorIndex/Cache/VICacheManager.cpp:65-157, an
+ * LRUResourceCache keyed by CacheKey = table path / part / index / column, VICacheObject.h:119-137, weighted by
+ * getResourceUsage().memory_usage_bytes).  One process-wide cache; keys are the caller's CacheKey::toString().
+ * Entries are pinned while a caller holds them (get / put return pinned); only unpinned entries are evicted,
+ * least recently used first; an expired entry that is still pinned is freed at its last release.
+ * ---------------------------------------------------------------------------------- */
+#define B200_CACHE_CORPUS 0   /* b200_corpus *, freed with b200_corpus_free */
+#define B200_CACHE_INDEX 1    /* b200_index *,  freed with b200_index_free */
+#define B200_CACHE_BM25 2     /* b200_bm25 *,   freed with b200_bm25_free */
+#define B200_CACHE_OPAQUE 3   /* caller-defined object, freed with the deleter passed to b200_cache_put_opaque */
+/* VICacheManager::setCacheSize -> updateMaxWeight: shrinking evicts unpinned entries at once */
+int b200_cache_set_capacity(uint64_t bytes);
+/* VICacheManager::get: B200_OK (pinned handle in *handle, its kind in *kind) or B200_ERR_NOT_FOUND */
+int b200_cache_get(const char *key, void **handle, int *kind);
+/* VICacheManager::put / load (getOrSet): inserts `handle` weighing `bytes` and pins it; if the key is already
+ * resident, *resident is the EXISTING pinned handle and `handle` stays the caller's (free it).  B200_ERR_NOMEM when
+ * it does not fit even after evicting every unpinned entry (ownership stays with the caller). */
+int b200_cache_put(const char *key, int kind, void *handle, uint64_t bytes, void **resident);
+int b200_cache_put_opaque(const char *key, void *handle, uint64_t bytes, void (*deleter)(void *), void **resident);
+/* drop one pin taken by get / put */
+int b200_cache_release(const char *key);
+/* VICacheManager::forceExpire -> tryRemove: freed now, or at the last release if pinned */
+int b200_cache_expire(const char *key);
+/* removes every entry whose key starts with `prefix` (a dropped table or part: removeOldParts); returns how many */
+int b200_cache_expire_prefix(const char *prefix, int64_t *out_removed);
+/* VICacheManager::countItem and the CurrentMetrics counters */
+int b200_cache_stats(uint64_t *capacity, uint64_t *used, uint64_t *items, uint64_t *hits, uint64_t *misses,
+                     uint64_t *evictions);
+/* getResourceUsage().memory_usage_bytes of a resident object (rows + side arrays / lists + codes), for `bytes` above */
+int b200_corpus_memory_bytes(const b200_corpus *c, uint64_t *out_bytes);
+int b200_index_memory_bytes(const b200_index *ix, uint64_t *out_bytes);
 
 /* ------------------------------------------------------------------------------------
  * Filter bitmaps and decoupled-part row-id maps (VIWithMeta::{row_ids_map, inverted_row_ids_map,

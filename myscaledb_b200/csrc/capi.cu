@@ -289,6 +289,16 @@ extern "C" int b200_corpus_append(b200_corpus *c, const void *rows, int64_t n) {
     return B200_OK;
 }
 
+extern "C" int b200_corpus_memory_bytes(const b200_corpus *c, uint64_t *out_bytes) {
+    if (!c || !out_bytes) return fail(B200_ERR_INVALID, "bad arguments");
+    // rows (as allocated; adopted rows belong to the caller but still occupy HBM) + per-row side arrays
+    uint64_t b = c->owns ? (uint64_t)c->data_cap_bytes : (uint64_t)c->n * (uint64_t)c->row_bytes;
+    if (c->row_scale) b += (uint64_t)std::max(c->side_cap_rows, c->n) * 4;
+    if (c->row_bias) b += (uint64_t)std::max(c->side_cap_rows, c->n) * 4;
+    *out_bytes = b;
+    return B200_OK;
+}
+
 extern "C" int b200_corpus_adopt_device(b200_corpus *c, const void *device_rows, int64_t n) {
     if (!c || !device_rows || n < 0) return fail(B200_ERR_INVALID, "bad arguments");
     std::lock_guard<std::mutex> lk(c->mu);

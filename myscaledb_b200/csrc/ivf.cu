@@ -739,6 +739,19 @@ extern "C" int b200_index_build(b200_index *ix, const float *rows, int64_t n) {
     return B200_OK;
 }
 
+extern "C" int b200_index_memory_bytes(const b200_index *ix, uint64_t *out_bytes) {
+    if (!ix || !out_bytes) return fail(B200_ERR_INVALID, "bad arguments");
+    uint64_t b = 0, t = 0;
+    if (ix->raw && b200_corpus_memory_bytes(ix->raw, &t) == B200_OK) b += t;
+    if (ix->coarse && b200_corpus_memory_bytes(ix->coarse, &t) == B200_OK) b += t;
+    if (ix->use_ivf) {
+        b += (uint64_t)ix->nlist * ix->d * 4 + (uint64_t)(ix->nlist + 1) * 4 + (uint64_t)ix->n * 4;  // centroids, offsets, ids
+        if (ix->d_pq) b += (uint64_t)ix->m * 256 * ix->dsub * 4 + (uint64_t)ix->n * ix->m;          // codebook, codes
+    }
+    *out_bytes = b;
+    return B200_OK;
+}
+
 extern "C" int b200_index_info(const b200_index *ix, int64_t *n, int *nlist, int *m, int *uses_ivf) {
     if (!ix) return fail(B200_ERR_INVALID, "null index");
     if (n) *n = ix->n;

@@ -99,6 +99,15 @@ class Corpus:
         self.metric, self.d, self.dtype = metric, d, dtype
         _check(lib().b200_corpus_create(C.c_int(metric), C.c_int(dtype), C.c_int(d), C.c_int64(capacity), C.byref(self._h)))
 
+    @classmethod
+    def borrowed(cls, handle: int, metric, d, dtype=F32):
+        """Non-owning view of a corpus held by the residency cache (cache_get): never freed by this wrapper."""
+        self = cls.__new__(cls)
+        self._h = C.c_void_p(handle)
+        self.metric, self.d, self.dtype = metric, d, dtype
+        self.close = lambda: None
+        return self
+
     def append(self, rows):
         rows = np.ascontiguousarray(rows, np.uint8 if self.dtype == BIN else np.float32)
         _check(lib().b200_corpus_append(self._h, rows.ctypes.data_as(C.c_void_p), C.c_int64(rows.shape[0])))
@@ -389,3 +398,76 @@ def transfer_to_old_row_ids(new_ids, new_dis, inverted_row_ids_map, inverted_row
                                               _p(src, C.c_uint8), C.c_int64(m.size), C.c_uint32(own_id), _p(o_i, C.c_int64),
                                               _p(o_d, C.c_float), C.byref(n)))
     return o_i[:n.value], o_d[:n.value]
+
+
+# --------------------------------------------------------------------------------------------------
+# HBM residency cache (the device-side VICacheManager): keys are CacheKey strings; see include/b200_search.h
+# --------------------------------------------------------------------------------------------------
+CACHE_CORPUS, CACHE_INDEX, CACHE_BM25, CACHE_OPAQUE = 0, 1, 2, 3
+_DELETER = C.CFUNCTYPE(None, C.c_void_p)
+
+
+class CacheMiss(KeyError):
+    pass
+
+
+def cache_set_capacity(nbytes: int):
+    _check(lib().b200_cache_set_capacity(C.c_uint64(nbytes)))
+
+
+def cache_get(key: str):
+    """-> (handle address, kind); raises CacheMiss.  The entry stays pinned until cache_release(key)."""
+    h, kind = C.c_void_p(), C.c_int()
+    rc = lib().b200_cache_get(key.encode(), C.byref(h), C.byref(kind))
+    if rc == 6:
+        raise CacheMiss(key)
+    _check(rc)
+    return h.value, kind.value
+
+
+def cache_put(key: str, obj, nbytes: int = None):
+    """Hands a Corpus / VectorIndex / BM25Index to the cache (which then owns the device object) and pins it.
+    Returns the resident handle address (the existing one when the key was already cached; obj then stays the caller's)."""
+    kind = CACHE_CORPUS if isinstance(obj, Corpus) else CACHE_INDEX if isinstance(obj, VectorIndex) else CACHE_BM25
+    if nbytes is None:
+        b = C.c_uint64()
+        if kind == CACHE_CORPUS:
+            _check(lib().b200_corpus_memory_bytes(obj._h, C.byref(b)))
+        elif kind == CACHE_INDEX:
+            _check(lib().b200_index_memory_bytes(obj._h, C.byref(b)))
+        nbytes = b.value
+    res = C.c_void_p()
+    _check(lib().b200_cache_put(key.encode(), C.c_int(kind), obj._h, C.c_uint64(nbytes), C.byref(res)))
+    if res.value == (obj._h.value if isinstance(obj._h, C.c_void_p) else obj._h):
+        obj._h = C.c_void_p()  # ownership moved to the cache: the wrapper must not free it
+    return res.value
+
+
+def cache_put_opaque(key: str, handle: int, nbytes: int, deleter):
+    """deleter: a _DELETER(ctypes callback) kept alive by the caller."""
+    res = C.c_void_p()
+    _check(lib().b200_cache_put_opaque(key.encode(), C.c_void_p(handle), C.c_uint64(nbytes), deleter, C.byref(res)))
+    return res.value
+
+
+def cache_release(key: str):
+    _check(lib().b200_cache_release(key.encode()))
+
+
+def cache_expire(key: str):
+    rc = lib().b200_cache_expire(key.encode())
+    if rc == 6:
+        raise CacheMiss(key)
+    _check(rc)
+
+
+def cache_expire_prefix(prefix: str) -> int:
+    n = C.c_int64()
+    _check(lib().b200_cache_expire_prefix(prefix.encode(), C.byref(n)))
+    return n.value
+
+
+def cache_stats() -> dict:
+    v = [C.c_uint64() for _ in range(6)]
+    _check(lib().b200_cache_stats(*[C.byref(x) for x in v]))
+    return dict(zip(("capacity", "used", "items", "hits", "misses", "evictions"), (x.value for x in v)))

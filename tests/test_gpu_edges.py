@@ -104,3 +104,32 @@ def test_binary_odd_sizes(nbytes):
         dg, ig = b2.binary_knn(metric, x, y, 12)
         do, io = orc.knn_binary(metric, x, y, 12)
         assert (ig == io).all() and np.array_equal(dg, do)
+
+
+def test_residency_cache_holds_real_corpora_and_evicts_by_hbm_bytes():
+    """VICacheManager on the device: parts' FLAT corpora cached by CacheKey string, LRU by their HBM bytes."""
+    rng = np.random.default_rng(3)
+    ya = rng.standard_normal((20000, 64)).astype(F32)
+    yb = rng.standard_normal((30000, 64)).astype(F32)
+    q = rng.standard_normal((3, 64)).astype(F32)
+    S.cache_expire_prefix("gpu/")
+    a = b2.Corpus(b2.L2, 64).append(ya)
+    b = b2.Corpus(b2.L2, 64).append(yb)
+    da, ia = a.search(q, 5)
+    S.cache_set_capacity(int(30000 * 64 * 4 * 1.5))      # room for b alone (or a alone), not both
+    ha = S.cache_put("gpu/t/part_a/v1", a)
+    assert a._h.value is None                            # the cache owns the device object now
+    S.cache_release("gpu/t/part_a/v1")
+    h, kind = S.cache_get("gpu/t/part_a/v1")
+    assert h == ha and kind == S.CACHE_CORPUS
+    d2, i2 = b2.Corpus.borrowed(h, b2.L2, 64).search(q, 5)   # search through the cached handle
+    assert (i2 == ia).all() and np.array_equal(d2, da)
+    S.cache_release("gpu/t/part_a/v1")
+    S.cache_put("gpu/t/part_b/v1", b)                    # evicts part_a (LRU, unpinned): its HBM is freed
+    with pytest.raises(S.CacheMiss):
+        S.cache_get("gpu/t/part_a/v1")
+    st = S.cache_stats()
+    assert st["used"] >= 30000 * 64 * 4 and st["evictions"] >= 1
+    S.cache_release("gpu/t/part_b/v1")
+    assert S.cache_expire_prefix("gpu/") == 1
+    S.cache_set_capacity(2 ** 63)
