@@ -415,7 +415,12 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "b200::gemm::gemm_topk_kernel (tcgen05 bf16 GEMM + fused top-k)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this workload,
+                         # from the committed ncu --set full capture (profiles/r01_gemm_topk_cg2_mc2.ncu-rep:
+                         # 15.363287 GB + 8.07 MB); other shapes have no capture -> null
+                         "traffic": 15.371355e9 if (N == 1 and a.rows == 10_000_000 and a.dim == 768 and nq == 1024 and k == 10) else None,
+                         "traffic_unit": "bytes per launch",
                          "flops_per_launch": flops_per_launch, "launch_ms": kern_ms / max(kern_n, 1),
                          "launches_timed": int(kern_n), "peak_source": peak_src,
                          "hbm_algorithmic_bytes_per_launch": shard_rows * a.dim * 2},
