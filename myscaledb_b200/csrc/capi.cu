@@ -432,9 +432,17 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
     float *q32 = c->w_q32.as<float>();
     B200_CUDA_OK(launch_pad_rows_f32(reinterpret_cast<const float *>(d_queries), c->d, q32, c->d_pad, nq, s));
     int path = c->path;
-    // auto: tensor cores from 16 queries up (bf16 rows: kind::f16 GEMM; fp32 rows: 3xTF32 split GEMM, same accuracy
-    // class as the fp32 FMA scan); very large k stays on the scan path, whose lists are warp-cooperative
-    if (path == 0) path = (nq >= 16 && k <= (c->dtype == B200_DTYPE_BF16 ? 1024 : 256)) ? 2 : 1;
+    // auto: when the batch goes to the tensor cores (bf16 rows: kind::f16 GEMM; fp32 rows: 3xTF32 split GEMM, same
+    // accuracy class as the fp32 FMA scan).  Measured crossovers (profiles/r01_small_batch.log, 4M x 768): bf16 rows
+    // 0.92 ms per <= 128-query batch (the HBM floor) vs 1.3 ms for ONE query on the scan; fp32 rows 3.6 ms vs 5.1 ms
+    // for 8 queries on the scan.  L2 keeps faiss' own switch: below distance_compute_blas_threshold = 20 queries the
+    // reference sums exact differences, from 20 up it uses ||x||^2 + ||y||^2 - 2xy like the GEMM kernels do (which
+    // cancels badly for far-from-origin data), so L2 batches move to the tensor cores at 20.  Very large k stays on
+    // the scan path, whose lists are warp-cooperative.
+    if (path == 0) {
+        const int64_t min_nq = c->metric == B200_METRIC_L2 ? 20 : (c->dtype == B200_DTYPE_BF16 ? 2 : 5);
+        path = (nq >= min_nq && k <= (c->dtype == B200_DTYPE_BF16 ? 1024 : 256)) ? 2 : 1;
+    }
     if (path == 3 || path == 4) { if (c->dtype != B200_DTYPE_BF16) path = 2; }
     // scan path: queries normalised in fp32 like the reference.  GEMM path: the bf16 operand
     // keeps the caller's values (normalising first would add a bf16 rounding of the unit
@@ -504,8 +512,8 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
         const int64_t nq_c = std::min(QCHUNK, nq - qb);
         const bool f32 = c->dtype == B200_DTYPE_F32;
         // >= 2 query tiles: CTA pairs (tcgen05 cta_group::2), query tiles padded to an even count;
-        // the fp32 (3xTF32) kernel exists as CTA pairs only
-        const int cta_group = (f32 || (nq_c > 128 && c->gemm_cta_group != 1)) ? 2 : 1;
+        // up to 128 queries: one CTA per MMA (a pair would spend half of its rows on padding)
+        const int cta_group = (nq_c > 128 && c->gemm_cta_group != 1) ? 2 : 1;
         const int nq_pad = (int)round_up(nq_c, 128 * cta_group);
         const int q_tiles = nq_pad / 128;
         if (f32) {
@@ -572,6 +580,7 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
         }
         gp.n = c->n;
         gp.nq_pad = nq_pad;
+        gp.nq_valid = (int)nq_c;
         gp.d_pad = c->d_pad;
         gp.k = k;
         gp.q_tiles = q_tiles;

@@ -25,6 +25,8 @@
 // Barriers per stage: full (leader; both CTAs' query planes landed), bfull (local; this CTA's
 // corpus half landed), conv (leader; 2 x 4 converter warps done), empty (both; MMAs retired).
 // Ranked key, filters, partial lists and the merge are those of ip_gemm_sm100.cu.
+// Batches of up to 128 queries use the single-CTA form (CG = 1: M = 128, the whole 256-row corpus tile per CTA,
+// 2 stages of 96 KB) so that no MMA row is spent on padding.
 #include "gemm_common.cuh"
 
 namespace b200 {
@@ -34,30 +36,47 @@ using namespace gemm;
 
 constexpr int BK3 = 32;                       // fp32 per k-block = one 128-byte swizzle row
 constexpr int UMMA_K3 = 8;                    // tf32 MMA K
-constexpr int STAGES3 = 3;
 constexpr int A3_BYTES = BM * BK3 * 4;        // 16 KB per plane
-constexpr int B3_ROWS = BN / 2;               // corpus rows staged by one CTA of the pair
-constexpr int B3_BYTES = B3_ROWS * BK3 * 4;   // 16 KB
-constexpr int STAGE3_BYTES = 2 * A3_BYTES + 2 * B3_BYTES;
 constexpr int CONV_WARPS = 4;
 constexpr int NUM_THREADS3 = 64 + EPI_THREADS + CONV_WARPS * 32;  // 320
-constexpr int OFF_AHI = 0;
-constexpr int OFF_ALO = STAGES3 * A3_BYTES;
-constexpr int OFF_B = 2 * STAGES3 * A3_BYTES;
-constexpr int OFF_BLO = OFF_B + STAGES3 * B3_BYTES;
-constexpr int OFF_SIDE = STAGES3 * STAGE3_BYTES;
-constexpr int OFF_BAR = OFF_SIDE + 2 * BN * 4;
-constexpr int OFF_SCRATCH = OFF_BAR + 256;
-constexpr int OFF_LIST = OFF_SCRATCH + SCRATCH_BYTES;
 constexpr int SMEM_LIMIT = 232448;
 
-static bool lists_fit(int k) { return OFF_LIST + k * EPI_THREADS * 8 + SMEM_ALIGN_SLACK <= SMEM_LIMIT; }
+// CG = 2: CTA pair, M = 256 (two query tiles), each CTA stages half of the 256-row corpus tile, 3 stages of 64 KB.
+// CG = 1: one CTA, M = 128 (batches of up to 128 queries: a pair would waste half of its MMA rows), the whole
+//         corpus tile per CTA, 2 stages of 96 KB.
+template <int CG>
+struct Cfg3 {
+    static constexpr int STAGES = CG == 2 ? 3 : 2;
+    static constexpr int B_ROWS = BN / CG;                  // corpus rows staged by one CTA
+    static constexpr int B_BYTES = B_ROWS * BK3 * 4;        // 16 KB / 32 KB
+    static constexpr int STAGE_BYTES = 2 * A3_BYTES + 2 * B_BYTES;
+    static constexpr int OFF_AHI = 0;
+    static constexpr int OFF_ALO = STAGES * A3_BYTES;
+    static constexpr int OFF_B = 2 * STAGES * A3_BYTES;
+    static constexpr int OFF_BLO = OFF_B + STAGES * B_BYTES;
+    static constexpr int OFF_SIDE = STAGES * STAGE_BYTES;
+    static constexpr int OFF_BAR = OFF_SIDE + 2 * BN * 4;
+    static constexpr int OFF_SCRATCH = OFF_BAR + 256;
+    static constexpr int OFF_LIST = OFF_SCRATCH + SCRATCH_BYTES;
+    static constexpr int CONV_ITERS = B_BYTES / 16 / (CONV_WARPS * 32);  // 16-byte words per converter thread and stage
+    static bool lists_fit(int k) { return OFF_LIST + k * EPI_THREADS * 8 + SMEM_ALIGN_SLACK <= SMEM_LIMIT; }
+};
 
-// kind::tf32, A = B = tf32 (K-major), D = f32, M = 256 (pair), N = 256
-__device__ __forceinline__ constexpr uint32_t make_idesc_tf32() {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * 2) >> 4) << 24);
+// kind::tf32, A = B = tf32 (K-major), D = f32, M = 128 * CG, N = 256
+__device__ __forceinline__ constexpr uint32_t make_idesc_tf32(int cg) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * cg) >> 4) << 24);
 }
 
+__device__ __forceinline__ void umma_tf32_cg1(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
 __device__ __forceinline__ void umma_tf32_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile(
         "{\n\t"
@@ -90,27 +109,30 @@ __global__ void split_tf32_kernel(const float *__restrict__ src, int64_t n_src, 
     }
 }
 
+template <int CG>
 __global__ void __launch_bounds__(NUM_THREADS3, 1)
 gemm3_topk_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant__ CUtensorMap map_qlo,
                   const __grid_constant__ CUtensorMap map_c, const GemmTopkParams p) {
+    using C = Cfg3<CG>;
+    constexpr int STAGES = C::STAGES;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    unsigned char *sAhi = smem + OFF_AHI;
-    unsigned char *sAlo = smem + OFF_ALO;
-    unsigned char *sB = smem + OFF_B;
-    unsigned char *sBlo = smem + OFF_BLO;
-    float *side_scale = reinterpret_cast<float *>(smem + OFF_SIDE);
+    unsigned char *sAhi = smem + C::OFF_AHI;
+    unsigned char *sAlo = smem + C::OFF_ALO;
+    unsigned char *sB = smem + C::OFF_B;
+    unsigned char *sBlo = smem + C::OFF_BLO;
+    float *side_scale = reinterpret_cast<float *>(smem + C::OFF_SIDE);
     float *side_bias = side_scale + BN;
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
-    uint64_t *bfull_bar = full_bar + STAGES3;
-    uint64_t *conv_bar = bfull_bar + STAGES3;
-    uint64_t *empty_bar = conv_bar + STAGES3;
-    uint64_t *tmem_full_bar = empty_bar + STAGES3;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
+    uint64_t *bfull_bar = full_bar + STAGES;
+    uint64_t *conv_bar = bfull_bar + STAGES;
+    uint64_t *empty_bar = conv_bar + STAGES;
+    uint64_t *tmem_full_bar = empty_bar + STAGES;
     uint64_t *tmem_empty_bar = tmem_full_bar + ACC_STAGES;
     uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + ACC_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t cta_rank = cluster_ctarank();  // 0 / 1
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;  // 0 / 1
     const uint32_t half = cta_rank & 1;
     const bool is_leader = half == 0;
 
@@ -124,44 +146,51 @@ gemm3_topk_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_qhi)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_qlo)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_c)) : "memory");
-        for (int i = 0; i < STAGES3; i++) {
+        for (int i = 0; i < STAGES; i++) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&bfull_bar[i], 1);
-            mbar_init(&conv_bar[i], 2 * CONV_WARPS);
+            mbar_init(&conv_bar[i], CG * CONV_WARPS);
             mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < ACC_STAGES; i++) {
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], 4 * 2);
+            mbar_init(&tmem_empty_bar[i], 4 * CG);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
-                     "n"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        if (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                         "n"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                         "n"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    cluster_sync_all();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer (both CTAs) =====================
+        // ===================== TMA producer (every CTA) =====================
         int stage = 0;
         uint32_t phase = 0;
         int ordinal = 0;
         bool pacing = p.progress != nullptr;
         for (int64_t t = worker; t < n_tiles; t += W, ordinal++) {
-            // pacing across the pairs that stream the same corpus tiles for other query tiles (see ip_gemm_sm100.cu)
+            // pacing across the CTAs (pairs) that stream the same corpus tiles for other query tiles (see ip_gemm_sm100.cu)
             if (pacing && is_leader) {
                 int ok = 1;
                 if (lane == 0) {
                     volatile int *prog = p.progress + (size_t)worker * p.q_tiles;
                     prog[qt] = ordinal + 1;
                     int spins = 0;
-                    for (int g = 0; g < p.q_tiles; g += 2)
+                    for (int g = 0; g < p.q_tiles; g += CG)
                         while (prog[g] < ordinal + 1 - p.sync_slack && spins < 256) {
                             __nanosleep(200);
                             spins++;
@@ -175,14 +204,20 @@ gemm3_topk_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_cons
             for (int kb = 0; kb < kb_count; kb++) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (elect_one()) {
-                    if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * 2 * A3_BYTES);
-                    tma_load_2d_cg2(&map_qhi, &full_bar[stage], sAhi + stage * A3_BYTES, kb * BK3, qt * BM);
-                    tma_load_2d_cg2(&map_qlo, &full_bar[stage], sAlo + stage * A3_BYTES, kb * BK3, qt * BM);
-                    mbar_arrive_expect_tx(&bfull_bar[stage], B3_BYTES);
-                    tma_load_2d(&map_c, &bfull_bar[stage], sB + stage * B3_BYTES, kb * BK3, (int)(t * BN + half * B3_ROWS));
+                    if (CG == 1) {
+                        mbar_arrive_expect_tx(&full_bar[stage], 2 * A3_BYTES);
+                        tma_load_2d(&map_qhi, &full_bar[stage], sAhi + stage * A3_BYTES, kb * BK3, qt * BM);
+                        tma_load_2d(&map_qlo, &full_bar[stage], sAlo + stage * A3_BYTES, kb * BK3, qt * BM);
+                    } else {
+                        if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * 2 * A3_BYTES);
+                        tma_load_2d_cg2(&map_qhi, &full_bar[stage], sAhi + stage * A3_BYTES, kb * BK3, qt * BM);
+                        tma_load_2d_cg2(&map_qlo, &full_bar[stage], sAlo + stage * A3_BYTES, kb * BK3, qt * BM);
+                    }
+                    mbar_arrive_expect_tx(&bfull_bar[stage], C::B_BYTES);
+                    tma_load_2d(&map_c, &bfull_bar[stage], sB + stage * C::B_BYTES, kb * BK3, (int)(t * BN + half * C::B_ROWS));
                 }
                 __syncwarp();
-                if (++stage == STAGES3) {
+                if (++stage == STAGES) {
                     stage = 0;
                     phase ^= 1;
                 }
@@ -191,7 +226,7 @@ gemm3_topk_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_cons
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (is_leader) {
-            constexpr uint32_t idesc = make_idesc_tf32();
+            constexpr uint32_t idesc = make_idesc_tf32(CG);
             const uint64_t ahi0 = make_smem_desc(smem_u32(sAhi));
             const uint64_t alo0 = make_smem_desc(smem_u32(sAlo));
             const uint64_t b0 = make_smem_desc(smem_u32(sB));
@@ -203,26 +238,38 @@ gemm3_topk_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_cons
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
                 for (int kb = 0; kb < kb_count; kb++) {
-                    mbar_wait(&full_bar[stage], phase);   // query planes of both CTAs
-                    mbar_wait(&conv_bar[stage], phase);   // corpus halves landed and split in both CTAs
+                    mbar_wait(&full_bar[stage], phase);   // query planes (of both CTAs)
+                    mbar_wait(&conv_bar[stage], phase);   // corpus (halves) landed and split
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t ahi = ahi0 + (uint64_t)(stage * (A3_BYTES >> 4));
                         const uint64_t alo = alo0 + (uint64_t)(stage * (A3_BYTES >> 4));
-                        const uint64_t b = b0 + (uint64_t)(stage * (B3_BYTES >> 4));
-                        const uint64_t blo = blo0 + (uint64_t)(stage * (B3_BYTES >> 4));
+                        const uint64_t b = b0 + (uint64_t)(stage * (C::B_BYTES >> 4));
+                        const uint64_t blo = blo0 + (uint64_t)(stage * (C::B_BYTES >> 4));
 #pragma unroll
                         for (int k = 0; k < BK3 / UMMA_K3; k++) {
                             const uint64_t off = (uint64_t)(k * (UMMA_K3 * 4 >> 4));
-                            umma_tf32_cg2(tmem_d, alo + off, b + off, idesc, (kb | k) != 0 ? 1u : 0u);  // small terms first
-                            umma_tf32_cg2(tmem_d, ahi + off, blo + off, idesc, 1u);
-                            umma_tf32_cg2(tmem_d, ahi + off, b + off, idesc, 1u);
+                            const uint32_t acc0 = (kb | k) != 0 ? 1u : 0u;  // small terms first
+                            if (CG == 1) {
+                                umma_tf32_cg1(tmem_d, alo + off, b + off, idesc, acc0);
+                                umma_tf32_cg1(tmem_d, ahi + off, blo + off, idesc, 1u);
+                                umma_tf32_cg1(tmem_d, ahi + off, b + off, idesc, 1u);
+                            } else {
+                                umma_tf32_cg2(tmem_d, alo + off, b + off, idesc, acc0);
+                                umma_tf32_cg2(tmem_d, ahi + off, blo + off, idesc, 1u);
+                                umma_tf32_cg2(tmem_d, ahi + off, b + off, idesc, 1u);
+                            }
                         }
-                        umma_commit_cg2(&empty_bar[stage], 3);
-                        if (kb == kb_count - 1) umma_commit_cg2(&tmem_full_bar[as], 3);
+                        if (CG == 1) {
+                            umma_commit(&empty_bar[stage]);
+                            if (kb == kb_count - 1) umma_commit(&tmem_full_bar[as]);
+                        } else {
+                            umma_commit_cg2(&empty_bar[stage], 3);
+                            if (kb == kb_count - 1) umma_commit_cg2(&tmem_full_bar[as], 3);
+                        }
                     }
                     __syncwarp();
-                    if (++stage == STAGES3) {
+                    if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -241,20 +288,23 @@ gemm3_topk_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_cons
         for (int64_t t = worker; t < n_tiles; t += W) {
             for (int kb = 0; kb < kb_count; kb++) {
                 mbar_wait(&bfull_bar[stage], phase);
-                uint4 *b = reinterpret_cast<uint4 *>(sB + stage * B3_BYTES);
-                uint4 *bl = reinterpret_cast<uint4 *>(sBlo + stage * B3_BYTES);
-                uint4 raw[B3_BYTES / 16 / (CONV_WARPS * 32)];
+                uint4 *b = reinterpret_cast<uint4 *>(sB + stage * C::B_BYTES);
+                uint4 *bl = reinterpret_cast<uint4 *>(sBlo + stage * C::B_BYTES);
 #pragma unroll
-                for (int i = 0; i < B3_BYTES / 16 / (CONV_WARPS * 32); i++) raw[i] = b[ct + i * (CONV_WARPS * 32)];
+                for (int i0 = 0; i0 < C::CONV_ITERS; i0 += 8) {
+                    uint4 raw[8];
 #pragma unroll
-                for (int i = 0; i < B3_BYTES / 16 / (CONV_WARPS * 32); i++) {
-                    uint4 h, l;
-                    split_tf32(raw[i].x, h.x, l.x);
-                    split_tf32(raw[i].y, h.y, l.y);
-                    split_tf32(raw[i].z, h.z, l.z);
-                    split_tf32(raw[i].w, h.w, l.w);
-                    b[ct + i * (CONV_WARPS * 32)] = h;
-                    bl[ct + i * (CONV_WARPS * 32)] = l;
+                    for (int i = 0; i < 8; i++) raw[i] = b[ct + (i0 + i) * (CONV_WARPS * 32)];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        uint4 h, l;
+                        split_tf32(raw[i].x, h.x, l.x);
+                        split_tf32(raw[i].y, h.y, l.y);
+                        split_tf32(raw[i].z, h.z, l.z);
+                        split_tf32(raw[i].w, h.w, l.w);
+                        b[ct + (i0 + i) * (CONV_WARPS * 32)] = h;
+                        bl[ct + (i0 + i) * (CONV_WARPS * 32)] = l;
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA's reads
                 __syncwarp();
@@ -262,7 +312,7 @@ gemm3_topk_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_cons
                     if (is_leader) mbar_arrive(&conv_bar[stage]);
                     else mbar_arrive_remote(&conv_bar[stage], 0);
                 }
-                if (++stage == STAGES3) {
+                if (++stage == STAGES) {
                     stage = 0;
                     phase ^= 1;
                 }
@@ -274,16 +324,17 @@ gemm3_topk_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_cons
         const int row = quarter * 32 + lane;
         const int et = threadIdx.x - 64;
         const bool use_side = p.row_scale || p.row_bias || p.alive || p.scale_const != -1.f;
-        float *scratch = reinterpret_cast<float *>(smem + OFF_SCRATCH) + et;
+        float *scratch = reinterpret_cast<float *>(smem + C::OFF_SCRATCH) + et;
         ThreadTopK list;
         list.k = p.k;
         list.n = 0;
         list.worst = 0;
-        list.thr_key = FLT_MAX;
+        // rows past the batch (zero padding up to the tile size) must never pay for the slow path: nothing beats -FLT_MAX
+        list.thr_key = (qt * BM + row < p.nq_valid) ? FLT_MAX : -FLT_MAX;
         list.thr_id = 0;
         if (p.lists_in_smem) {
-            list.keys = reinterpret_cast<float *>(smem + OFF_LIST) + row;
-            list.ids = reinterpret_cast<uint32_t *>(smem + OFF_LIST + (size_t)p.k * EPI_THREADS * 4) + row;
+            list.keys = reinterpret_cast<float *>(smem + C::OFF_LIST) + row;
+            list.ids = reinterpret_cast<uint32_t *>(smem + C::OFF_LIST + (size_t)p.k * EPI_THREADS * 4) + row;
         } else {
             list.keys = p.list_keys_gmem + (size_t)blockIdx.x * p.k * EPI_THREADS + row;
             list.ids = p.list_ids_gmem + (size_t)blockIdx.x * p.k * EPI_THREADS + row;
@@ -341,10 +392,13 @@ gemm3_topk_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_cons
     }
 
     tc_fence_before();
-    cluster_sync_all();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        if (CG == 1)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
 }
 
@@ -373,25 +427,17 @@ cudaError_t launch_split_tf32(const float *src, int64_t n_src, int d_pad, float 
     return cudaGetLastError();
 }
 
-cudaError_t launch_gemm3_topk(const GemmTopkParams &p_in, int grid, cudaStream_t s, const char **err_detail) {
+template <int CG>
+static cudaError_t launch3_cg(const CUtensorMap &map_qhi, const CUtensorMap &map_qlo, const CUtensorMap &map_c,
+                              const GemmTopkParams &p_in, int grid, cudaStream_t s) {
     using namespace gemm3;
-    *err_detail = nullptr;
+    using C = Cfg3<CG>;
     GemmTopkParams p = p_in;
-    if (p.q_tiles % 2 != 0 || grid % p.q_tiles != 0 || !p.queries_lo) {
-        *err_detail = "gemm3: q_tiles must be even, grid a multiple of q_tiles, queries_lo set";
-        return cudaErrorInvalidValue;
-    }
-    CUtensorMap map_qhi, map_qlo, map_c;
-    if (!encode_rows_map_f32(&map_qhi, p.queries_bf16, p.nq_pad, p.d_pad, BM) ||
-        !encode_rows_map_f32(&map_qlo, p.queries_lo, p.nq_pad, p.d_pad, BM) ||
-        !encode_rows_map_f32(&map_c, p.corpus_bf16, p.n, p.d_pad, B3_ROWS)) {
-        *err_detail = "cuTensorMapEncodeTiled failed";
-        return cudaErrorInvalidValue;
-    }
-    p.lists_in_smem = lists_fit(p.k) ? 1 : 0;
-    p.stages = STAGES3;
-    const size_t smem = (size_t)OFF_LIST + (p.lists_in_smem ? (size_t)p.k * EPI_THREADS * 8 : 0) + SMEM_ALIGN_SLACK;
-    cudaError_t e = cudaFuncSetAttribute(gemm3_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    p.lists_in_smem = C::lists_fit(p.k) ? 1 : 0;
+    p.stages = C::STAGES;
+    const size_t smem = (size_t)C::OFF_LIST + (p.lists_in_smem ? (size_t)p.k * EPI_THREADS * 8 : 0) + SMEM_ALIGN_SLACK;
+    auto kern = gemm3_topk_kernel<CG>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
@@ -400,14 +446,32 @@ cudaError_t launch_gemm3_topk(const GemmTopkParams &p_in, int grid, cudaStream_t
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.x = CG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, gemm3_topk_kernel, map_qhi, map_qlo, map_c, p);
+    e = cudaLaunchKernelEx(&cfg, kern, map_qhi, map_qlo, map_c, p);
     g_launches++;
     return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+cudaError_t launch_gemm3_topk(const GemmTopkParams &p, int grid, cudaStream_t s, const char **err_detail) {
+    using namespace gemm3;
+    *err_detail = nullptr;
+    const int cg = p.cta_group == 2 ? 2 : 1;
+    if (p.q_tiles % cg != 0 || grid % p.q_tiles != 0 || !p.queries_lo) {
+        *err_detail = "gemm3: q_tiles must be a multiple of cta_group, grid a multiple of q_tiles, queries_lo set";
+        return cudaErrorInvalidValue;
+    }
+    CUtensorMap map_qhi, map_qlo, map_c;
+    if (!encode_rows_map_f32(&map_qhi, p.queries_bf16, p.nq_pad, p.d_pad, BM) ||
+        !encode_rows_map_f32(&map_qlo, p.queries_lo, p.nq_pad, p.d_pad, BM) ||
+        !encode_rows_map_f32(&map_c, p.corpus_bf16, p.n, p.d_pad, BN / cg)) {
+        *err_detail = "cuTensorMapEncodeTiled failed";
+        return cudaErrorInvalidValue;
+    }
+    return cg == 2 ? launch3_cg<2>(map_qhi, map_qlo, map_c, p, grid, s) : launch3_cg<1>(map_qhi, map_qlo, map_c, p, grid, s);
 }
 
 }  // namespace b200

@@ -238,7 +238,8 @@ gemm_topk_ts_kernel(const __grid_constant__ CUtensorMap map_c, const GemmTopkPar
         list.k = p.k;
         list.n = 0;
         list.worst = 0;
-        list.thr_key = FLT_MAX;
+        // rows past the batch (zero padding up to the tile size) must never pay for the slow path: nothing beats -FLT_MAX
+        list.thr_key = (qt * BM + row < p.nq_valid) ? FLT_MAX : -FLT_MAX;
         list.thr_id = 0;
         if (p.lists_in_smem) {
             list.keys = reinterpret_cast<float *>(smem + C::OFF_LIST) + row;

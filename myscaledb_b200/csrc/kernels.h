@@ -66,6 +66,7 @@ struct GemmTopkParams {
     uint32_t *list_ids_gmem;
     int64_t n;
     int nq_pad, d_pad, k;
+    int nq_valid;              // queries actually in the batch (rows past it are padding)
     int q_tiles;               // nq_pad / 128
     int cta_group;             // 1: one CTA per MMA; 2: CTA pairs (cluster of 2), q_tiles must be even
     int pairs_per_cluster;     // 1, or 2: two CTA pairs share (TMA-multicast) every corpus tile; q_tiles % 4 == 0
