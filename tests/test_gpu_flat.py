@@ -161,9 +161,17 @@ def test_scan_matches_oracle(metric, n, d, nq, k):
     rng = np.random.default_rng(n + d + nq)
     y = rng.standard_normal((n, d)).astype(F32)
     x = rng.standard_normal((nq, d)).astype(F32)
-    dg, ig = b2.flat_knn(metric, x, y, k)
     do, io = orc.search_without_index(metric, x, y, k)
+    # the fp32 FMA scan kernel itself (path 1), whatever the batch size
+    c = b2.Corpus(metric, d).append(y)
+    c.set_path(1)
+    dg, ig = c.search(x, k)
+    c.close()
     check_topk(metric, x, y, dg, ig, do, io)
+    # the one-shot entry point with automatic path selection: IP / cosine batches of >= 5 queries run on the 3xTF32
+    # tensor-core kernel, whose ~1e-5 relative error may swap a near tie (still inside the 1e-4 contract)
+    dg, ig = b2.flat_knn(metric, x, y, k)
+    check_topk(metric, x, y, dg, ig, do, io, min_exact=0.999 if (nq < 5 or metric == b2.L2) else 0.99)
 
 
 def test_scan_alive_bitmap_and_ip_min_quirk():
