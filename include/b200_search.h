@@ -152,7 +152,10 @@ int b200_index_create(const char *type, int metric, int d, const char *params, b
 int b200_index_build(b200_index *ix, const float *rows, int64_t n);
 int b200_index_info(const b200_index *ix, int64_t *n, int *nlist, int *m, int *uses_ivf);
 /* first_stage_only (MSTG): return the first-stage candidates with approximate distances;
- * out_num_candidates receives the width the first stage ran with (SearchResult::getNumCandidates). */
+ * out_num_candidates receives the width the first stage ran with (SearchResult::getNumCandidates).
+ * Batch planner: when one exact pass over the raw rows on the tensor cores is estimated cheaper than nq * nprobe list
+ * probes (large batches, skewed lists), the search runs there instead and returns exact results (recall 1,
+ * *out_num_candidates = k).  "exact_batch=0" / "exact_batch=1" in `params` forces the probe / the exact pass. */
 int b200_index_search(b200_index *ix, const float *queries, int64_t nq, int k, const char *params, int first_stage_only,
                       const uint8_t *alive_bits /*nullable*/, float *out_dis, int64_t *out_ids, int64_t *out_num_candidates);
 /* computeTopDistanceSubset: exact distances of candidate ids [nq][ncand] (negative = unused) -> top-k */
