@@ -101,7 +101,7 @@ struct b200_corpus {
     // workspaces
     DevBuf w_raw, w_q32, w_qbf, w_qlo, w_qnorm, w_pk, w_pi, w_lk, w_li, w_alive, w_odis, w_oids, w_stage, w_prog;
     int sync_slack = 2;
-    int gemm_multicast = 1;  // clusters of two CTA pairs sharing the corpus tile (B200_GEMM_MULTICAST=0 disables)
+    int gemm_multicast = 1;  // CTA pairs per cluster sharing each corpus tile: 1 auto (4, else 2), 2, 4; B200_GEMM_MULTICAST=0 disables
     int gemm_ts = 0;  // 0 streaming (default: faster at every measured d), 1 TS when d_pad <= 512, 2 TS whenever it fits
     // optional CUDA-event timing of the dominant kernel (scan or GEMM) for the roofline report
     bool timing = false;
@@ -121,10 +121,23 @@ static void timing_begin(b200_corpus *c, cudaStream_t s, std::pair<cudaEvent_t, 
     }
     cudaEventRecord(ev.first, s);
 }
+// fold the recorded event pairs into the running totals (waits for them) and recycle the events
+static void timing_drain(b200_corpus *c) {
+    for (auto &ev : c->ev_used) {
+        float ms = 0;
+        if (cudaEventSynchronize(ev.second) == cudaSuccess && cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) {
+            c->timed_ms += ms;
+            c->timed_launches++;
+        }
+        c->ev_free.push_back(ev);
+    }
+    c->ev_used.clear();
+}
 static void timing_end(b200_corpus *c, cudaStream_t s, std::pair<cudaEvent_t, cudaEvent_t> &ev) {
     if (!c->timing) return;
     cudaEventRecord(ev.second, s);
     c->ev_used.push_back(ev);
+    if (c->ev_used.size() >= 1024) timing_drain(c);  // nobody asked for the totals for a while: keep the list bounded
 }
 
 namespace b200 {
@@ -344,15 +357,7 @@ extern "C" int b200_corpus_kernel_time(b200_corpus *c, int reset, double *out_to
     if (!c || !out_total_ms || !out_launches) return fail(B200_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lk(c->mu);
     B200_CUDA_OK(cudaSetDevice(c->device));
-    for (auto &ev : c->ev_used) {
-        B200_CUDA_OK(cudaEventSynchronize(ev.second));
-        float ms = 0;
-        B200_CUDA_OK(cudaEventElapsedTime(&ms, ev.first, ev.second));
-        c->timed_ms += ms;
-        c->timed_launches++;
-        c->ev_free.push_back(ev);
-    }
-    c->ev_used.clear();
+    timing_drain(c);
     *out_total_ms = c->timed_ms;
     *out_launches = c->timed_launches;
     if (reset) {
@@ -444,6 +449,7 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
         path = (nq >= min_nq && k <= (c->dtype == B200_DTYPE_BF16 ? 1024 : 256)) ? 2 : 1;
     }
     if (path == 3 || path == 4) { if (c->dtype != B200_DTYPE_BF16) path = 2; }
+    if (c->n == 0) path = 1;  // nothing to tile: the scan kernel exits at once and the merge emits the empty result
     // scan path: queries normalised in fp32 like the reference.  GEMM path: the bf16 operand
     // keeps the caller's values (normalising first would add a bf16 rounding of the unit
     // vector); the positive per-query factor 1/||q|| is applied when the result is emitted.
@@ -681,6 +687,15 @@ struct ScratchCorpus {
     }
 };
 static thread_local ScratchCorpus t_scratch;
+
+// gives this thread's scratch corpus (device buffers sized for the largest part it has scanned) back to the driver
+extern "C" int b200_thread_release(void) {
+    if (t_scratch.c) {
+        b200_corpus_free(t_scratch.c);
+        t_scratch.c = nullptr;
+    }
+    return B200_OK;
+}
 
 static int scratch_corpus(int metric, int dtype, int d, int64_t rows, b200_corpus **out) {
     b200_corpus *c = t_scratch.c;

@@ -133,3 +133,19 @@ def test_residency_cache_holds_real_corpora_and_evicts_by_hbm_bytes():
     S.cache_release("gpu/t/part_b/v1")
     assert S.cache_expire_prefix("gpu/") == 1
     S.cache_set_capacity(2 ** 63)
+
+
+def test_search_on_an_empty_resident_corpus_and_thread_scratch_release():
+    """A FLAT index created but not yet filled answers with empty slots on every path selection; the per-thread scratch
+    of the one-shot entry points can be handed back."""
+    q = np.random.default_rng(1).standard_normal((40, 32)).astype(F32)
+    for dtype in (S.F32, S.BF16):
+        c = b2.Corpus(b2.IP, 32, dtype=dtype)
+        dis, ids = c.search(q, 5)
+        assert (ids == -1).all()
+        c.close()
+    y = np.random.default_rng(2).standard_normal((1000, 32)).astype(F32)
+    d1, i1 = b2.flat_knn(b2.L2, q[:3], y, 4)
+    assert S.lib().b200_thread_release() == 0
+    d2, i2 = b2.flat_knn(b2.L2, q[:3], y, 4)       # scratch is rebuilt on demand
+    assert (i1 == i2).all() and np.array_equal(d1, d2)
