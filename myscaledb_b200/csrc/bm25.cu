@@ -109,15 +109,39 @@ struct Bm25ScoreParams {
     int operator_or;
 };
 
-__device__ __forceinline__ bool list_find(const uint32_t *docs, uint32_t n, uint32_t doc, uint32_t &pos) {
-    uint32_t lo = 0, hi = n;
+// first index in docs[0..n) whose value is >= key, found by the whole warp: every round the 32 lanes probe 32 evenly
+// spaced splitters of the remaining range (one ballot narrows it 33x), the last <= 32 entries are read side by side
+__device__ __forceinline__ uint32_t warp_lower_bound(const uint32_t *docs, uint32_t n, uint32_t key, int lane) {
+    uint32_t lo = 0, hi = n;  // the answer lies in [lo, hi]
+    while (hi - lo > 32) {
+        const uint64_t span = hi - lo;
+        const uint32_t idx = lo + (uint32_t)(span * (uint32_t)(lane + 1) / 33);  // lo < idx < hi, ascending with the lane
+        const unsigned less = __ballot_sync(0xffffffffu, docs[idx] < key);        // a prefix mask: the list is sorted
+        const uint32_t cnt = __popc(less);
+        const uint32_t nlo = cnt ? lo + (uint32_t)(span * cnt / 33) + 1 : lo;
+        const uint32_t nhi = cnt < 32 ? lo + (uint32_t)(span * (cnt + 1) / 33) : hi;
+        lo = nlo;
+        hi = nhi;
+    }
+    const uint32_t j = lo + (uint32_t)lane;
+    const unsigned less = __ballot_sync(0xffffffffu, j < hi && docs[j] < key);
+    return lo + __popc(less);
+}
+// [wlo, whi): the positions in docs[0..n) of every value in [dmin, dmax]
+__device__ __forceinline__ void warp_window(const uint32_t *docs, uint32_t n, uint32_t dmin, uint32_t dmax, int lane,
+                                            uint32_t &wlo, uint32_t &whi) {
+    wlo = warp_lower_bound(docs, n, dmin, lane);
+    whi = wlo + warp_lower_bound(docs + wlo, n - wlo, dmax + 1u, lane);  // doc ordinals stay far below 2^32 - 1
+}
+// private binary search of one lane inside the warp's window
+__device__ __forceinline__ bool window_find(const uint32_t *docs, uint32_t lo, uint32_t hi, uint32_t doc, uint32_t &pos) {
+    const uint32_t end = hi;
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
-        const uint32_t v = docs[mid];
-        if (v < doc) lo = mid + 1; else hi = mid;
+        if (docs[mid] < doc) lo = mid + 1; else hi = mid;
     }
     pos = lo;
-    return lo < n && docs[lo] == doc;
+    return lo < end && docs[lo] == doc;
 }
 
 __global__ void __launch_bounds__(256) bm25_score_kernel(const Bm25ScoreParams p) {
@@ -141,39 +165,57 @@ __global__ void __launch_bounds__(256) bm25_score_kernel(const Bm25ScoreParams p
         // warp-uniform trip count
         for (uint32_t base = (blockIdx.x * 8 + warp) * 32; base < df; base += gridDim.x * 256) {
             const uint32_t i = base + lane;
+            const bool valid = i < df;
             bool cand = false;
             float key = FLT_MAX;
-            uint32_t doc = 0;
-            if (i < df) {
-                doc = docs[i];
-                bool owner = true;
-                uint32_t pos;
-                for (uint32_t e = 0; e < c && owner; e++)
-                    if (cl[e].df && list_find(p.post_docs + cl[e].offset, cl[e].df, doc, pos)) owner = false;
-                bool all = owner && (p.operator_or || c == 0);  // AND: only clause 0 can own a full match
-                if (owner && all) {
-                    const float tf = (float)tfs[i];
-                    const float norm = p.caches[(size_t)cl[c].cache * 256 + p.fieldnorm[(size_t)cl[c].field * p.n_docs + doc]];
-                    // explicit rn ops: no FMA contraction, so sums equal the reference's fp32 arithmetic bit for bit
-                    float score = __fmul_rn(cl[c].weight, __fdiv_rn(tf, __fadd_rn(tf, norm)));
-                    for (uint32_t e = c + 1; e < nc; e++) {
-                        bool found = cl[e].df && list_find(p.post_docs + cl[e].offset, cl[e].df, doc, pos);
-                        if (found) {
-                            const float tf2 = (float)p.post_tfs[cl[e].offset + pos];
-                            const float n2 = p.caches[(size_t)cl[e].cache * 256 + p.fieldnorm[(size_t)cl[e].field * p.n_docs + doc]];
-                            score = __fadd_rn(score, __fmul_rn(cl[e].weight, __fdiv_rn(tf2, __fadd_rn(tf2, n2))));
-                        } else if (!p.operator_or) {
-                            all = false;
-                            break;
-                        }
-                    }
-                    if (all) {
-                        const uint32_t rid = p.row_id[doc];
-                        const bool live = !p.alive || ((p.alive[rid >> 3] >> (rid & 7)) & 1);
-                        key = -score;
-                        cand = live && list.passes(key, doc);
+            // the 32 postings of this step are consecutive in a sorted list: their counterparts in another clause's
+            // list lie in one narrow window, which the warp brackets together (32-ary search, 3 probes for 32 K
+            // postings) before each lane finishes with a short private binary search inside it
+            const uint32_t doc = valid ? docs[i] : 0u;
+            const uint32_t n_valid = min(32u, df - base);
+            const uint32_t dmin = __shfl_sync(0xffffffffu, doc, 0);
+            const uint32_t dmax = __shfl_sync(0xffffffffu, doc, (int)n_valid - 1);
+            bool active = valid;  // no earlier clause owns this document
+            uint32_t pos;
+            for (uint32_t e = 0; e < c; e++) {
+                if (!cl[e].df) continue;
+                const uint32_t *od = p.post_docs + cl[e].offset;
+                uint32_t wlo, whi;
+                warp_window(od, cl[e].df, dmin, dmax, lane, wlo, whi);
+                if (active && window_find(od, wlo, whi, doc, pos)) active = false;
+            }
+            bool all = active && (p.operator_or || c == 0);  // AND: only clause 0 can own a full match
+            float score = 0.f;
+            if (all) {
+                const float tf = (float)tfs[i];
+                const float norm = p.caches[(size_t)cl[c].cache * 256 + p.fieldnorm[(size_t)cl[c].field * p.n_docs + doc]];
+                // explicit rn ops: no FMA contraction, so sums equal the reference's fp32 arithmetic bit for bit
+                score = __fmul_rn(cl[c].weight, __fdiv_rn(tf, __fadd_rn(tf, norm)));
+            }
+            for (uint32_t e = c + 1; e < nc; e++) {
+                if (!__any_sync(0xffffffffu, all)) break;
+                if (!cl[e].df) {
+                    if (!p.operator_or) all = false;
+                    continue;
+                }
+                const uint32_t *od = p.post_docs + cl[e].offset;
+                uint32_t wlo, whi;
+                warp_window(od, cl[e].df, dmin, dmax, lane, wlo, whi);
+                if (all) {
+                    if (window_find(od, wlo, whi, doc, pos)) {
+                        const float tf2 = (float)p.post_tfs[cl[e].offset + pos];
+                        const float n2 = p.caches[(size_t)cl[e].cache * 256 + p.fieldnorm[(size_t)cl[e].field * p.n_docs + doc]];
+                        score = __fadd_rn(score, __fmul_rn(cl[e].weight, __fdiv_rn(tf2, __fadd_rn(tf2, n2))));
+                    } else if (!p.operator_or) {
+                        all = false;
                     }
                 }
+            }
+            if (all) {
+                const uint32_t rid = p.row_id[doc];
+                const bool live = !p.alive || ((p.alive[rid >> 3] >> (rid & 7)) & 1);
+                key = -score;
+                cand = live && list.passes(key, doc);
             }
             unsigned m = __ballot_sync(0xffffffffu, cand);
             while (m) {
