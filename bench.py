@@ -53,10 +53,10 @@ def parse():
 
 def config_of(a, n):
     return {"workload": f"FLAT brute-force IP, {a.rows} x {a.dim}-d bf16, batch {a.nq} queries, top-{a.k} "
-                        "(BASELINE.json configs[1])",
+                        + ("(BASELINE.json configs[1])" if (a.rows, a.dim, a.nq, a.k) == (10_000_000, 768, 1024, 10) else "(non-default size)"),
             "rows": a.rows, "dim": a.dim, "batch_queries": a.nq, "k": a.k,
             "sharding": f"rows/{n} per GPU, NCCL all-gather of per-shard top-k + merge kernel" if n > 1 else "single GPU",
-            "cache": "inputs (15.4 GB corpus) larger than L2; no flush needed"}
+            "cache": f"inputs ({a.rows * a.dim * 2 / n / 1e9:.1f} GB of corpus rows per GPU) larger than the 126 MB L2; no flush needed"}
 
 
 _NVML_LOOP = r"""
