@@ -38,3 +38,36 @@ def assign_parts(part_rows, world: int):
         out[g].append(i)
         load[g] += part_rows[i]
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# Text side: BM25 scores must not depend on how documents are spread over GPUs.  The reference sums
+# total_num_docs / total_num_tokens / doc_freq over parts before scoring
+# (ReadWithHybridSearch::getStatisticForTextSearch, src/VectorIndex/Processors/ReadWithHybridSearch.cpp:89-209,
+# BM25InfoInDataParts.cpp:40-94); across GPUs that is ONE all-reduce(sum) of a small int64 vector per batch.
+# ----------------------------------------------------------------------------------------------
+def bm25_stats_layout(n_fields: int, query_terms, fields):
+    """Order of the counters in the exchanged vector: [total_docs, tokens(field 0..n_fields-1), df(field, term) ...]."""
+    keys = [("docs",)] + [("tokens", f) for f in range(n_fields)]
+    keys += [("df", f, t) for f in fields for t in query_terms]
+    return keys
+
+
+def bm25_local_stats(index, n_fields: int, query_terms, fields):
+    """int64 counters of ONE shard's BM25 index (anything with total_docs / total_tokens(f) / doc_freq(t, f))."""
+    total_docs = index.total_docs() if callable(index.total_docs) else index.total_docs
+    out = [int(total_docs)] + [int(index.total_tokens(f)) for f in range(n_fields)]
+    out += [int(index.doc_freq(t, f)) for f in fields for t in query_terms]
+    return out
+
+
+def bm25_global_stats(summed, n_fields: int, query_terms, fields):
+    """Summed counter vector -> the `stats` dict BM25Index.search(..., stats=) takes (table-wide N, tokens, df)."""
+    summed = [int(v) for v in summed]
+    stats = {"total_docs": summed[0], "total_tokens": {f: summed[1 + f] for f in range(n_fields)}, "doc_freq": {}}
+    pos = 1 + n_fields
+    for f in fields:
+        for t in query_terms:
+            stats["doc_freq"][(f, t)] = summed[pos]
+            pos += 1
+    return stats
