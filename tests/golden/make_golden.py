@@ -233,6 +233,16 @@ def main():
         "rsf_after_lwd": pr("hybrid search rsf on part with index after LWD"),
     }
 
+    # 00029: MSTG on a part below min_bytes_to_build -> fallback to FLAT; cosine distances down at 1e-4 (1 - ip in fp32)
+    r = [x for x in rows(read("00029_mqvs_fallback_to_flat.reference")) if len(x) == 2 and re.match(r"^\d+$", x[0])]
+    g["00029_fallback_to_flat_cosine"] = {
+        "source": "tests/queries/2_vector_search/00029_mqvs_fallback_to_flat.{sql,reference}",
+        "corpus": "row n = [n, n+7, n+6, n+5, n+4, n+3, n+2, n+1] for n in range(1000)",
+        "query": [8.0, 15, 14, 13, 12, 11, 10, 9], "metric": "COSINE", "k": 5,
+        "expect": [[int(x[0]), float(x[1])] for x in r[:5]],
+        "expect_after_reload": [[int(x[0]), float(x[1])] for x in r[5:10]],
+    }
+
     with open(os.path.join(OUT, "reference_goldens.json"), "w") as f:
         json.dump(g, f, indent=1)
     print("wrote", os.path.join(OUT, "reference_goldens.json"), "cases:", list(g))

@@ -341,3 +341,15 @@ def test_00040_hybrid_with_lightweight_delete_bitexact(goldens):
     txt = [(0, 0, int(r), float(x)) for r, x in zip(rows, sc)]
     rsf = orc.hybrid_fusion("rsf", vec, txt, 5)
     assert [[i, float(F32(x))] for i, x in _order_by_score_desc_id(rsf)] == [[e[0], float(F32(e[1]))] for e in g["rsf_after_lwd"]]
+
+
+def test_00029_fallback_to_flat_cosine_small_distances(goldens):
+    """Cosine distances of 1e-4 are a difference of two numbers next to 1.0: ids must match exactly, values to the last
+    ulp or two of 1.0 (the closed library's summation order inside an 8-float row is not known)."""
+    g = goldens["00029_fallback_to_flat_cosine"]
+    n = np.arange(1000, dtype=F32)[:, None]
+    y = n + np.array([0, 7, 6, 5, 4, 3, 2, 1], F32)[None, :]
+    dis, ids = orc.search_without_index(orc.COSINE, np.array([g["query"]], F32), y, g["k"])
+    for exp in (g["expect"], g["expect_after_reload"]):
+        assert ids[0].tolist() == [e[0] for e in exp]
+        np.testing.assert_allclose(dis[0], [e[1] for e in exp], rtol=0, atol=2.4e-7)
