@@ -72,9 +72,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Experiment knob (default 0 = plain spin, identical code): `make EXTRA=-DB200_MBAR_BACKOFF_NS=64` inserts a nanosleep
+// between failed try_waits.  The committed ncu capture attributes ~30 % of the bf16 kernel's issued instructions to these
+// spin loops; on a power-capped kernel that is worth measuring.
+#ifndef B200_MBAR_BACKOFF_NS
+#define B200_MBAR_BACKOFF_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     while (!mbar_try_wait(addr, parity)) {
+#if B200_MBAR_BACKOFF_NS > 0
+        __nanosleep(B200_MBAR_BACKOFF_NS);
+#endif
     }
 }
 
