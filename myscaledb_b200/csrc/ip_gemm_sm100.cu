@@ -250,7 +250,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
+#if defined(B200_EPI_SINGLE_POLL) && B200_EPI_SINGLE_POLL
+            // experiment (make EXTRA=-DB200_EPI_SINGLE_POLL=1): one lane per epilogue warp polls the accumulator barrier
+            if (lane == 0) mbar_wait(&tmem_full_bar[as], aphase);
+            __syncwarp();
+#else
             mbar_wait(&tmem_full_bar[as], aphase);
+#endif
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
             // Chunks of 32 columns; the TMEM load of chunk c+1 is in flight while chunk c is
