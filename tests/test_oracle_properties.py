@@ -119,3 +119,53 @@ def test_bm25_two_shards_with_summed_statistics_equal_one_index(n_docs, seed):
         rows, sc = ix.search(query, n_docs, stats=stats)
         merged.update({int(r): float(s) for r, s in zip(rows, sc)})
     assert merged == {int(r): float(s) for r, s in zip(rows1, sc1)}
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 20), st.integers(1, 20), st.integers(0, 2 ** 31), st.sampled_from([1, -1]), st.floats(0.0, 1.0))
+def test_relative_score_fusion_formula(nv, nt, seed, direction, w):
+    """RelativeScoreFusion: each list min-max normalised ((s - min) / (max - min), all-equal -> 1.0), then
+    text * w + (direction == -1 ? vec : 1 - vec) * (1 - w), fp32 throughout (HybridSearchUtils.cpp:212-314)."""
+    rng = np.random.default_rng(seed)
+    vs = np.sort(rng.integers(0, 50, nv).astype(F32))
+    if direction == -1:
+        vs = vs[::-1]
+    ts = np.sort(rng.integers(0, 50, nt).astype(F32))[::-1]
+    vl = rng.permutation(60)[:nv]; tl = rng.permutation(60)[:nt]
+    vec = [(0, 0, int(l), float(s)) for l, s in zip(vl, vs)]
+    txt = [(0, 0, int(l), float(s)) for l, s in zip(tl, ts)]
+    got = {r[2]: F32(r[3]) for r in orc.hybrid_fusion("rsf", vec, txt, 200, fusion_weight=w, vector_scan_direction=direction)}
+
+    def norm(scores):
+        lo, hi = F32(min(scores)), F32(max(scores))
+        return [F32(1.0) if hi == lo else F32(F32(s - lo) / F32(hi - lo)) for s in map(F32, scores)]
+    w32 = F32(w)
+    exp = {}
+    for l, s in zip(tl, norm(ts)):
+        exp[int(l)] = F32(exp.get(int(l), F32(0)) + F32(s * w32))
+    for l, s in zip(vl, norm(vs)):
+        v = s if direction == -1 else F32(F32(1.0) - s)
+        exp[int(l)] = F32(exp.get(int(l), F32(0)) + F32(v * F32(F32(1.0) - w32)))
+    assert set(got) == set(exp)
+    for l in exp:
+        assert abs(float(got[l]) - float(exp[l])) <= 1.2e-7 * max(1.0, abs(float(exp[l]))), (l, got[l], exp[l])
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 200), st.integers(1, 8), st.integers(1, 15), st.integers(0, 2 ** 31), st.sampled_from([3, 4]))
+def test_binary_metrics_against_python_popcounts(n, nbytes, k, seed, metric):
+    """Hamming = popcount(x ^ y); Jaccard distance = (|x or y| - |x and y|) / |x or y| (0 for two empty sets);
+    ties -> smaller id."""
+    rng = np.random.default_rng(seed)
+    y = rng.integers(0, 256, (n, nbytes), dtype=np.uint8)
+    x = rng.integers(0, 256, (1, nbytes), dtype=np.uint8)
+    dis, ids = orc.knn_binary(metric, x, y, k)
+    pc = lambda a: int(np.unpackbits(a).sum())
+    if metric == orc.HAMMING:
+        s = [float(pc(x[0] ^ r)) for r in y]
+    else:
+        s = [0.0 if pc(x[0] | r) == 0 else float(F32(F32(pc(x[0] | r) - pc(x[0] & r)) / F32(pc(x[0] | r)))) for r in y]
+    order = sorted(range(n), key=lambda i: (s[i], i))[:k]
+    got = [int(i) for i in ids[0] if i >= 0]
+    assert got == order
+    assert [float(v) for v in dis[0][:len(got)]] == [s[i] for i in order]
