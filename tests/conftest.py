@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "gpu_extra: extra GPU property tests, opt-in: B200_RUN_EXTRA=1 pytest -m gpu_extra")
 
 
 @pytest.fixture(scope="session")
