@@ -223,6 +223,88 @@ def reference_arm(a):
                       "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def _agree(d_a, i_a, d_b, i_b, rtol):
+    """Two top-k answers of the same queries agree: distances elementwise within rtol, ids identical except where two
+    candidates are closer than the tolerance (a swap of near ties or a different pick at the k-th boundary)."""
+    import numpy as np
+    scale = np.maximum(np.abs(d_b), 1.0)
+    err = float((np.abs(d_a - d_b) / scale).max())
+    if err > rtol:
+        return False, err, 0.0
+    same = i_a == i_b
+    for q, j in np.argwhere(~same):
+        hit = np.flatnonzero(i_b[q] == i_a[q, j])
+        ref = d_b[q, hit[0]] if hit.size else d_b[q, -1]
+        if abs(d_a[q, j] - ref) > rtol * max(1.0, abs(ref)):
+            return False, err, float(same.mean())
+    return True, err, float(same.mean())
+
+
+def verify_results(a, index, corpus, q_host, q_dev, d_res, i_res, row0, shard_rows, N, rank, dev):
+    """(1) 16 sampled queries re-answered by the fp32 FMA scan kernel (path 1, an independent kernel) over every shard
+    and merged on the host; (2) 2 of them re-answered by the CPU oracle over the full corpus (rows read back from HBM).
+    Both must agree with what the timed tensor-core path (+ all-gather + merge kernel at N > 1) returned."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import oracle as orc
+    k, nq = a.k, a.nq
+    rng = np.random.default_rng(12345)
+    sample = np.sort(rng.choice(nq, size=min(16, nq), replace=False))
+    qs = q_dev[torch.as_tensor(sample, device=dev)].contiguous()
+    sd = torch.empty((len(sample), k), dtype=torch.float32, device=dev)
+    si = torch.empty((len(sample), k), dtype=torch.int64, device=dev)
+    index.set_path(1)
+    index.search_device(qs.data_ptr(), len(sample), k, sd.data_ptr(), si.data_ptr(), id_offset=row0,
+                        stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    index.set_path(0)
+    # CPU oracle on 2 of the sampled queries over this rank's rows
+    two = sample[:2]
+    xq = np.ascontiguousarray(q_host.numpy()[two])
+    od = np.full((len(two), 0), 0, np.float32); oi = np.zeros((len(two), 0), np.int64)
+    for off in range(0, shard_rows, 500_000):
+        m = min(500_000, shard_rows - off)
+        rows = corpus[off:off + m].to(torch.float32).cpu().numpy()
+        cd, ci = orc.knn_flat(orc.IP, xq, rows, k)
+        od = np.concatenate([od, cd], axis=1); oi = np.concatenate([oi, np.where(ci >= 0, ci + row0 + off, -1)], axis=1)
+    cpu_d = torch.tensor(od, device=dev); cpu_i = torch.tensor(oi, device=dev)
+    if N > 1:
+        def gather(t):
+            parts = [torch.empty_like(t) for _ in range(N)]
+            dist.all_gather(parts, t.contiguous())
+            return torch.cat(parts, dim=1)
+        # every rank holds the same number of chunk candidates only if shards are equal: pad to the max width
+        width = torch.tensor([cpu_d.shape[1]], device=dev); dist.all_reduce(width, op=dist.ReduceOp.MAX)
+        pad = int(width.item()) - cpu_d.shape[1]
+        if pad:
+            cpu_d = torch.cat([cpu_d, torch.full((cpu_d.shape[0], pad), -3e38, device=dev)], dim=1)
+            cpu_i = torch.cat([cpu_i, torch.full((cpu_i.shape[0], pad), -1, device=dev, dtype=torch.int64)], dim=1)
+        sd, si, cpu_d, cpu_i = gather(sd), gather(si), gather(cpu_d), gather(cpu_i)
+
+    def host_topk(d, i):
+        d, i = d.cpu().numpy(), i.cpu().numpy()
+        out_d = np.empty((d.shape[0], k), np.float32); out_i = np.empty((d.shape[0], k), np.int64)
+        for q in range(d.shape[0]):
+            ok = i[q] >= 0
+            order = np.lexsort((i[q][ok], -d[q][ok]))[:k]
+            out_d[q], out_i[q] = d[q][ok][order], i[q][ok][order]
+        return out_d, out_i
+    scan_d, scan_i = host_topk(sd, si)
+    cpu_d, cpu_i = host_topk(cpu_d, cpu_i)
+    ok1, err1, same1 = _agree(d_res[sample], i_res[sample], scan_d, scan_i, 2e-4)
+    ok2, err2, same2 = _agree(d_res[two], i_res[two], cpu_d, cpu_i, 2e-4)
+    if not (ok1 and ok2):
+        raise AssertionError(f"timed path disagrees with its checkers: scan kernel ok={ok1} (max rel err {err1:.2e}, ids "
+                             f"{same1:.3f}), CPU oracle ok={ok2} (max rel err {err2:.2e}, ids {same2:.3f})")
+    return {"scan_kernel_queries": int(len(sample)), "scan_kernel_ids_identical": same1, "scan_kernel_max_rel_err": err1,
+            "cpu_oracle_queries": int(len(two)), "cpu_oracle_ids_identical": same2, "cpu_oracle_max_rel_err": err2,
+            "rows_checked": a.rows, "shards": N,
+            "what": "results of the timed path (tensor-core top-k" + (", NCCL all-gather, merge kernel" if N > 1 else "")
+                    + ") vs the fp32 scan kernel over every shard merged on the host, and vs oracle/vs_oracle.c over all rows"}
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -397,10 +479,12 @@ def main():
         except Exception as e:
             fp32_batch = {"error": f"{type(e).__name__}: {e}"[:300]}
 
-    # ---- sanity: results are sane (sorted, ids in range); parity proper lives in tests/ ----
+    # ---- verification of the TIMED path's results (the run fails on a mismatch) ----
     d_res, i_res = res
+    verified = None
     if not os.environ.get("B200_GEMM_DEBUG"):  # kernel experiments produce garbage on purpose
         assert (np.diff(d_res, axis=1) <= 0).all() and (i_res >= 0).all() and (i_res < a.rows).all()
+        verified = verify_results(a, index, corpus, q_host, q_dev, d_res, i_res, row0, shard_rows, N, rank, dev)
 
     if rank == 0:
         peaks = {}
@@ -420,7 +504,7 @@ def main():
                     "d2h_bytes_per_step": nq * k * 12,
                     "note": "b200_corpus_search(): pinned host queries -> H2D -> kernels -> D2H results; corpus resident "
                             "(index state)"},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "verified": verified,
             "roofline": {"bound": "tensor", "kernel": "b200::gemm::gemm_topk_kernel (tcgen05 bf16 GEMM + fused top-k)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None,

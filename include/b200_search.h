@@ -112,10 +112,19 @@ int b200_corpus_search(b200_corpus *c, const float *queries, int64_t nq, int k, 
 int b200_corpus_search_device(b200_corpus *c, const float *d_queries, int64_t nq, int k,
                               const uint8_t *d_alive_bits /*nullable*/, int64_t id_offset, float *d_out_dis,
                               int64_t *d_out_ids, void *stream);
-/* Force a search path: 0 = auto, 1 = memory-bound scan kernel, 2 = tcgen05 bf16 GEMM
- * (CTA pairs when there are >= 2 query tiles; queries stationary in TMEM when d <= 768),
- * 3 = tcgen05 GEMM restricted to single-CTA MMAs, 4 = CTA pairs with both operands streamed. */
+/* Force a search path (tests, A/B measurements; production leaves 0):
+ *   0 auto | 1 memory-bound scan kernel | 2 tensor cores, exactly the variant auto picks for a batch (operands
+ *   streamed through shared memory, CTA pairs from 2 query tiles up, TMA multicast in clusters of 2 / 4 pairs when
+ *   the batch has a multiple of 4 / 8 query tiles; fp32 corpora: the 3xTF32 kernel) | 3 single-CTA MMAs <1,1> |
+ *   4 CTA pairs, no multicast <2,1> | 5 at most two pairs per cluster <2,2> | 6 up to four pairs per cluster <2,4>
+ *   (same as 2, explicit) | 7 queries stationary in TMEM ("TS" form; k <= 30, d <= 768, bf16 corpora). */
 int b200_corpus_set_path(b200_corpus *c, int path);
+/* which kernel the last search on this corpus launched (so a test can prove it exercised the variant it meant to) */
+#define B200_KERNEL_SCAN 1
+#define B200_KERNEL_GEMM_BF16 2   /* gemm_topk_kernel<cta_group, pairs_per_cluster> */
+#define B200_KERNEL_GEMM_TS 3     /* gemm_topk_ts_kernel */
+#define B200_KERNEL_GEMM_TF32X3 4 /* gemm3_topk_kernel */
+int b200_corpus_last_variant(b200_corpus *c, int *kernel, int *cta_group, int *pairs_per_cluster, int *grid);
 /* CUDA-event timing of the dominant kernel (scan or GEMM) of every search on this corpus,
  * recorded on the launching stream; used by bench.py for the roofline report. */
 int b200_corpus_enable_timing(b200_corpus *c, int on);
@@ -141,6 +150,16 @@ int b200_topk_merge_device(const float *d_dis, const int64_t *d_ids, int n_lists
 int b200_topk_merge_device_strided(const float *d_dis, const int64_t *d_ids, int n_lists, int64_t dis_list_stride,
                                    int64_t ids_list_stride, int64_t nq, int k, int descending, float *d_out_dis,
                                    int64_t *d_out_ids, void *stream);
+/* General form.  Input lists hold k_in entries per query (list l, query q at d_dis + l * dis_list_stride + q * k_in),
+ * sorted best first, ids < 0 = unused slot; ids are full 64-bit values (shard base + row, any magnitude).
+ * tie_mode 0: equal scores -> smaller id first (this library's contract everywhere else).
+ * tie_mode 1: the reference's own order -- std::multimap insertion order of getTotalTopSearchResultImpl
+ *   (list 0's entries first, each list in its own order): ascending walks return the earlier-inserted of two equal
+ *   scores, the reverse walk used for IP / BM25 returns the later-inserted one (MergeTreeBaseSearchManager.cpp:271).
+ *   d_out_list (nullable) receives the list (part) index of every output entry, -1 for unused slots. */
+int b200_topk_merge_device_ex(const float *d_dis, const int64_t *d_ids, int n_lists, int64_t dis_list_stride,
+                              int64_t ids_list_stride, int64_t nq, int k_in, int k, int descending, int tie_mode,
+                              float *d_out_dis, int64_t *d_out_ids, int32_t *d_out_list /*nullable*/, void *stream);
 
 /* ------------------------------------------------------------------------------------
  * Vector indexes.  Replaces Search::createVectorIndex / VectorIndex::{build, search,

@@ -103,6 +103,8 @@ struct b200_corpus {
     int sync_slack = 2;
     int gemm_multicast = 1;  // CTA pairs per cluster sharing each corpus tile: 1 auto (4, else 2), 2, 4; B200_GEMM_MULTICAST=0 disables
     int gemm_ts = 0;  // 0 streaming (default: faster at every measured d), 1 TS when d_pad <= 512, 2 TS whenever it fits
+    // what the last tensor-core launch really was (tests assert on it): cta_group, pairs per cluster, TS form, grid, kernel id
+    int last_cg = 0, last_mc = 0, last_ts = 0, last_grid = 0, last_kernel = 0;
     // optional CUDA-event timing of the dominant kernel (scan or GEMM) for the roofline report
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_used, ev_free;
@@ -338,11 +340,29 @@ extern "C" int b200_corpus_size(const b200_corpus *c, int64_t *out_rows) {
 }
 
 extern "C" int b200_corpus_set_path(b200_corpus *c, int path) {
-    if (!c || path < 0 || path > 4) return fail(B200_ERR_INVALID, "path must be 0..4");
-    c->path = path >= 3 ? 2 : path;
+    if (!c || path < 0 || path > 7) return fail(B200_ERR_INVALID, "path must be 0..7");
+    std::lock_guard<std::mutex> lk(c->mu);
+    // 0 auto | 1 scan | 2 tensor cores, the variant auto picks (streaming operands, TMA multicast in the largest cluster
+    // the batch allows) | 3 single-CTA MMAs <1,1> | 4 CTA pairs without multicast <2,1> | 5 at most two pairs per
+    // cluster <2,2> | 6 up to four pairs per cluster <2,4> (= 2, explicit) | 7 queries stationary in TMEM (TS form)
+    c->path = path >= 2 ? 2 : path;
     c->gemm_cta_group = path == 3 ? 1 : 0;
-    if (path == 4) { c->gemm_ts = 0; c->gemm_multicast = 0; }
-    if (path == 2) c->gemm_ts = 2;
+    c->gemm_ts = path == 7 ? 2 : 0;
+    c->gemm_multicast = path == 4 ? 0 : path == 5 ? 2 : 1;
+    if (path == 0) {  // auto honours the environment overrides again
+        if (const char *ev = getenv("B200_GEMM_TS")) c->gemm_ts = atoi(ev);
+        if (const char *ev = getenv("B200_GEMM_MULTICAST")) c->gemm_multicast = atoi(ev);
+    }
+    return B200_OK;
+}
+
+extern "C" int b200_corpus_last_variant(b200_corpus *c, int *kernel, int *cta_group, int *pairs_per_cluster, int *grid) {
+    if (!c) return fail(B200_ERR_INVALID, "null corpus");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (kernel) *kernel = c->last_kernel;
+    if (cta_group) *cta_group = c->last_cg;
+    if (pairs_per_cluster) *pairs_per_cluster = c->last_mc;
+    if (grid) *grid = c->last_grid;
     return B200_OK;
 }
 
@@ -448,7 +468,6 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
         const int64_t min_nq = c->metric == B200_METRIC_L2 ? 20 : (c->dtype == B200_DTYPE_BF16 ? 2 : 5);
         path = (nq >= min_nq && k <= (c->dtype == B200_DTYPE_BF16 ? 1024 : 256)) ? 2 : 1;
     }
-    if (path == 3 || path == 4) { if (c->dtype != B200_DTYPE_BF16) path = 2; }
     if (c->n == 0) path = 1;  // nothing to tile: the scan kernel exits at once and the merge emits the empty result
     // scan path: queries normalised in fp32 like the reference.  GEMM path: the bf16 operand
     // keeps the caller's values (normalising first would add a bf16 rounding of the unit
@@ -493,6 +512,7 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
         timing_begin(c, s, ev);
         B200_CUDA_OK(launch_flat_scan(sp, qt, blocks_x, s));
         timing_end(c, s, ev);
+        c->last_kernel = B200_KERNEL_SCAN; c->last_cg = 0; c->last_mc = 0; c->last_grid = blocks_x;
         MergeParams mp{};
         mp.in_keys = sp.part_keys;
         mp.in_ids = sp.part_ids;
@@ -610,6 +630,8 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
         cudaError_t e = f32 ? launch_gemm3_topk(gp, grid, s, &detail)
                             : use_ts ? launch_gemm_topk_ts(gp, grid, s, &detail) : launch_gemm_topk(gp, grid, s, &detail);
         timing_end(c, s, ev);
+        c->last_kernel = f32 ? B200_KERNEL_GEMM_TF32X3 : use_ts ? B200_KERNEL_GEMM_TS : B200_KERNEL_GEMM_BF16;
+        c->last_cg = cta_group; c->last_mc = (f32 || use_ts) ? 1 : pairs; c->last_grid = grid;
         if (e != cudaSuccess)
             return fail(B200_ERR_CUDA, std::string("gemm_topk launch: ") + (detail ? detail : cudaGetErrorString(e)));
         MergeParams mp{};
@@ -806,7 +828,14 @@ extern "C" int b200_topk_merge_device(const float *d_dis, const int64_t *d_ids, 
 extern "C" int b200_topk_merge_device_strided(const float *d_dis, const int64_t *d_ids, int n_lists,
                                               int64_t dis_list_stride, int64_t ids_list_stride, int64_t nq, int k,
                                               int descending, float *d_out_dis, int64_t *d_out_ids, void *stream) {
-    if (!d_dis || !d_ids || !d_out_dis || !d_out_ids || n_lists <= 0 || nq < 0 || k <= 0)
+    return b200_topk_merge_device_ex(d_dis, d_ids, n_lists, dis_list_stride, ids_list_stride, nq, k, k, descending, 0, d_out_dis,
+                                     d_out_ids, nullptr, stream);
+}
+
+extern "C" int b200_topk_merge_device_ex(const float *d_dis, const int64_t *d_ids, int n_lists, int64_t dis_list_stride,
+                                         int64_t ids_list_stride, int64_t nq, int k_in, int k, int descending, int tie_mode,
+                                         float *d_out_dis, int64_t *d_out_ids, int32_t *d_out_list, void *stream) {
+    if (!d_dis || !d_ids || !d_out_dis || !d_out_ids || n_lists <= 0 || nq < 0 || k <= 0 || k_in <= 0 || tie_mode < 0 || tie_mode > 1)
         return fail(B200_ERR_INVALID, "bad arguments");
     if (k > 2048) return fail(B200_ERR_UNSUPPORTED, "k > 2048 not supported by the merge kernel");
     B200_TRY(ensure_device());
@@ -816,13 +845,14 @@ extern "C" int b200_topk_merge_device_strided(const float *d_dis, const int64_t 
     mp.in_ids = d_ids;
     mp.list_stride = dis_list_stride;
     mp.id_list_stride = ids_list_stride;
-    mp.q_stride = k;
+    mp.q_stride = k_in;
     mp.n_lists = n_lists;
-    mp.k_in = k;
+    mp.k_in = k_in;
     mp.k = k;
     mp.nq = nq;
     mp.descending = descending;
-    mp.out_mode = descending ? kOutNeg : kOutKey;
+    mp.tie_mode = tie_mode;
+    mp.out_list = d_out_list;
     mp.out_dis = d_out_dis;
     mp.out_ids = d_out_ids;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

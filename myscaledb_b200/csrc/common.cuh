@@ -34,12 +34,19 @@ __host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { retur
 __host__ __device__ static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
 constexpr uint32_t kNoId = 0xffffffffu;
+constexpr uint64_t kNoId64 = ~0ull;
+template <typename IdT> struct NoId;
+template <> struct NoId<uint32_t> { static constexpr uint32_t value = kNoId; };
+template <> struct NoId<uint64_t> { static constexpr uint64_t value = kNoId64; };
 
 // ----------------------------------------------------------------------------------
 // ordering: smaller key is better, ties -> smaller id.  All metrics are mapped to
 // such a key (IP: -score, cosine: -cos) so one top-k serves every metric.
 // ----------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ bool better(float ka, uint32_t ia, float kb, uint32_t ib) {
+    return ka < kb || (ka == kb && ia < ib);
+}
+__host__ __device__ __forceinline__ bool better(float ka, uint64_t ia, float kb, uint64_t ib) {
     return ka < kb || (ka == kb && ia < ib);
 }
 
@@ -55,15 +62,16 @@ __device__ __forceinline__ int warp_sum(int v) {
 // Warp-cooperative sorted top-k list living in shared (or global) memory.
 // keys/ids: k slots, sorted best-first, `n` valid.  All 32 lanes call with the same
 // (key,id); n/thr are warp-uniform registers.
-struct WarpTopK {
+template <typename IdT>
+struct WarpTopKT {
     float *keys;
-    uint32_t *ids;
+    IdT *ids;
     int k;
     int n;
     float thr_key;      // key of the current k-th (FLT_MAX while n < k)
-    uint32_t thr_id;
+    IdT thr_id;
 
-    __device__ __forceinline__ void init(float *keys_, uint32_t *ids_, int k_) {
+    __device__ __forceinline__ void init(float *keys_, IdT *ids_, int k_) {
         keys = keys_;
         ids = ids_;
         k = k_;
@@ -75,11 +83,11 @@ struct WarpTopK {
     }
 
     // cheap pre-test usable per lane on its own candidate
-    __device__ __forceinline__ bool passes(float key, uint32_t id) const {
+    __device__ __forceinline__ bool passes(float key, IdT id) const {
         return better(key, id, thr_key, thr_id);
     }
 
-    __device__ __forceinline__ void insert(float key, uint32_t id) {
+    __device__ __forceinline__ void insert(float key, IdT id) {
         if (!passes(key, id)) return;
         const int lane = lane_id();
         int cnt = 0;
@@ -93,7 +101,7 @@ struct WarpTopK {
             for (int base = pos + ((last - pos) / 32) * 32; base >= pos; base -= 32) {
                 const int j = base + lane;
                 float kv = 0.f;
-                uint32_t iv = 0;
+                IdT iv = 0;
                 const bool mv = j <= last;
                 if (mv) {
                     kv = keys[j];
@@ -119,6 +127,7 @@ struct WarpTopK {
         }
     }
 };
+using WarpTopK = WarpTopKT<uint32_t>;
 
 // Rank-merge of L sorted lists (best-first, unused tail slots hold FLT_MAX keys) of k entries each, list l at
 // keys + l * list_stride, into out[0..k): the rank of an element in the union is its own index plus, for every other
@@ -126,23 +135,24 @@ struct WarpTopK {
 // Every thread of the CTA calls it after a __syncthreads() that completes the lists; out may be shared or global
 // (distinct from the inputs).  Replaces "warp 0 inserts the other warps' lists one element at a time", which is
 // O(L k^2 / 32) and dominated IVF probes with k in the hundreds (2 ms per query at k = 160).
-__device__ __forceinline__ void block_rank_merge(const float *keys, const uint32_t *ids, int L, int list_stride, int k,
-                                                 float *out_keys, uint32_t *out_ids) {
+template <typename IdT>
+__device__ __forceinline__ void block_rank_merge(const float *keys, const IdT *ids, int L, int list_stride, int k,
+                                                 float *out_keys, IdT *out_ids) {
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
         out_keys[j] = FLT_MAX;
-        out_ids[j] = kNoId;
+        out_ids[j] = NoId<IdT>::value;
     }
     __syncthreads();
     for (int e = threadIdx.x; e < L * k; e += blockDim.x) {
         const int l = e / k, j = e - l * k;
         const float key = keys[(size_t)l * list_stride + j];
         if (!(key < FLT_MAX)) continue;
-        const uint32_t id = ids[(size_t)l * list_stride + j];
+        const IdT id = ids[(size_t)l * list_stride + j];
         int rank = j;
         for (int l2 = 0; l2 < L && rank < k; l2++) {
             if (l2 == l) continue;
             const float *k2 = keys + (size_t)l2 * list_stride;
-            const uint32_t *i2 = ids + (size_t)l2 * list_stride;
+            const IdT *i2 = ids + (size_t)l2 * list_stride;
             int lo = 0, hi = k;  // first index whose entry is NOT better than (key, id)
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;

@@ -247,8 +247,8 @@ __global__ void __launch_bounds__(kScanThreads) binary_scan_kernel(const BinaryS
 // K7: merge.  One block per query; 8 warps filter slices of the candidate set into warp
 // lists, warp 0 merges them and writes the final, converted result.
 // ------------------------------------------------------------------------------------
-template <typename IdT, bool EXTERNAL>
 __global__ void __launch_bounds__(kScanThreads) topk_merge_kernel(const MergeParams p) {
+    using IdT = uint32_t;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *lk = reinterpret_cast<float *>(smem_raw);
     uint32_t *li = reinterpret_cast<uint32_t *>(lk + (size_t)kScanWarps * p.k);
@@ -272,8 +272,7 @@ __global__ void __launch_bounds__(kScanThreads) topk_merge_kernel(const MergePar
             const int64_t off = (int64_t)l * p.list_stride + q * p.q_stride + (p.k - 1);
             const int64_t ioff = (int64_t)l * (p.id_list_stride ? p.id_list_stride : p.list_stride) + q * p.q_stride + (p.k - 1);
             float v = keys[off];
-            if (EXTERNAL) v = (int64_t)ids[ioff] < 0 ? FLT_MAX : (p.descending ? -v : v);
-            else if ((uint32_t)ids[ioff] == kNoId) v = FLT_MAX;
+            if ((uint32_t)ids[ioff] == kNoId) v = FLT_MAX;
             b = fminf(b, v);
         }
 #pragma unroll
@@ -297,22 +296,9 @@ __global__ void __launch_bounds__(kScanThreads) topk_merge_kernel(const MergePar
             const int64_t l = c / p.k_in, j = c - l * p.k_in;
             const int64_t off = l * p.list_stride + q * p.q_stride + j;
             const int64_t ioff = l * (p.id_list_stride ? p.id_list_stride : p.list_stride) + q * p.q_stride + j;
-            const float v = keys[off];
-            if (EXTERNAL) {
-                // external lists carry 64-bit ids (negative = empty slot); row ids are
-                // UInt32 labels in the reference (ColumnUInt32, MergeTreeVSManager.cpp:469),
-                // shard offsets keep them < 2^32 - 1
-                const int64_t full = (int64_t)ids[ioff];
-                if (full >= 0) {
-                    key = p.descending ? -v : v;
-                    id = (uint32_t)full;
-                    cand = list.passes(key, id);
-                }
-            } else {
-                id = (uint32_t)ids[ioff];
-                key = v;
-                cand = id != kNoId && list.passes(key, id);
-            }
+            id = (uint32_t)ids[ioff];
+            key = keys[off];
+            cand = id != kNoId && list.passes(key, id);
         }
         unsigned m = __ballot_sync(0xffffffffu, cand);
         while (m) {
@@ -353,6 +339,98 @@ __global__ void __launch_bounds__(kScanThreads) topk_merge_kernel(const MergePar
             p.out_dis[q * p.k + j] = dis;
             p.out_ids[q * p.k + j] = id;
         }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------
+// K7 (external form): merge of per-part / per-GPU lists that carry 64-bit ids.  Entries are ordered by
+// (key, order word): tie_mode 0 -> the 64-bit id itself (contract: better score, then smaller id);
+// tie_mode 1 -> the insertion sequence l * k_in + j of std::multimap::emplace in
+// getTotalTopSearchResultImpl (MergeTreeBaseSearchManager.cpp:207-299): ascending walks give the
+// earlier-inserted equal key first, the reverse walk (IP / BM25) the later-inserted one (:271).
+// ------------------------------------------------------------------------------------
+constexpr uint64_t kSeqFlip = 0x7fffffffffffffffull;
+
+__global__ void __launch_bounds__(kScanThreads) topk_merge_ext_kernel(const MergeParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *li = reinterpret_cast<uint64_t *>(smem_raw);                       // [warps + 1][k] order words
+    float *lk = reinterpret_cast<float *>(li + (size_t)(kScanWarps + 1) * p.k);  // [warps + 1][k] keys
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t q = blockIdx.x;
+    WarpTopKT<uint64_t> list;
+    list.init(lk + (size_t)warp * p.k, li + (size_t)warp * p.k, p.k);
+    for (int j = lane; j < p.k; j += 32) list.keys[j] = FLT_MAX;
+    __syncwarp();
+    const float *keys = reinterpret_cast<const float *>(p.in_keys);
+    const int64_t *ids = reinterpret_cast<const int64_t *>(p.in_ids);
+    const int64_t id_stride = p.id_list_stride ? p.id_list_stride : p.list_stride;
+    const int64_t ncand = (int64_t)p.n_lists * p.k_in;
+    if (p.k_in >= p.k) {  // same bound as the internal merge: the k-th entry of any full sorted list
+        __shared__ float bound_s[kScanWarps];
+        float b = FLT_MAX;
+        for (int l = threadIdx.x; l < p.n_lists; l += kScanThreads) {
+            const float v = keys[(int64_t)l * p.list_stride + q * p.q_stride + (p.k - 1)];
+            const bool have = ids[(int64_t)l * id_stride + q * p.q_stride + (p.k - 1)] >= 0;
+            b = fminf(b, have ? (p.descending ? -v : v) : FLT_MAX);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) b = fminf(b, __shfl_xor_sync(0xffffffffu, b, o));
+        if (lane == 0) bound_s[warp] = b;
+        __syncthreads();
+        b = bound_s[0];
+#pragma unroll
+        for (int w = 1; w < kScanWarps; w++) b = fminf(b, bound_s[w]);
+        if (b < FLT_MAX) {
+            list.thr_key = b;
+            list.thr_id = kNoId64;
+        }
+    }
+    for (int64_t c0 = (int64_t)warp * 32; c0 < ncand; c0 += kScanThreads) {
+        const int64_t c = c0 + lane;
+        float key = FLT_MAX;
+        uint64_t ord = kNoId64;
+        bool cand = false;
+        if (c < ncand) {
+            const int64_t l = c / p.k_in, j = c - l * p.k_in;
+            const int64_t full = ids[l * id_stride + q * p.q_stride + j];
+            if (full >= 0) {
+                const float v = keys[l * p.list_stride + q * p.q_stride + j];
+                key = p.descending ? -v : v;
+                ord = p.tie_mode == 0 ? (uint64_t)full : (p.descending ? kSeqFlip - (uint64_t)c : (uint64_t)c);
+                cand = list.passes(key, ord);
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, cand);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            list.insert(__shfl_sync(0xffffffffu, key, src), __shfl_sync(0xffffffffu, ord, src));
+        }
+    }
+    __syncthreads();
+    float *fk = lk + (size_t)kScanWarps * p.k;
+    uint64_t *fi = li + (size_t)kScanWarps * p.k;
+    block_rank_merge(lk, li, kScanWarps, p.k, p.k, fk, fi);
+    __syncthreads();
+    for (int j = threadIdx.x; j < p.k; j += kScanThreads) {
+        float dis = p.descending ? -FLT_MAX : FLT_MAX;
+        int64_t id = -1;
+        int32_t src_list = -1;
+        if (fi[j] != kNoId64) {
+            dis = p.descending ? -fk[j] : fk[j];
+            if (p.tie_mode == 0) {
+                id = (int64_t)fi[j];
+            } else {
+                const int64_t c = (int64_t)(p.descending ? kSeqFlip - fi[j] : fi[j]);
+                const int64_t l = c / p.k_in, jj = c - l * p.k_in;
+                id = ids[l * id_stride + q * p.q_stride + jj];
+                src_list = (int32_t)l;
+            }
+        }
+        p.out_dis[q * p.k + j] = dis;
+        p.out_ids[q * p.k + j] = id;
+        if (p.out_list) p.out_list[q * p.k + j] = src_list;
     }
 }
 
@@ -407,7 +485,7 @@ cudaError_t launch_binary_scan(const BinaryScanParams &p, int blocks_x, cudaStre
 }
 
 cudaError_t launch_topk_merge(const MergeParams &p, bool external, cudaStream_t s) {
-    const size_t smem = (size_t)(kScanWarps + 1) * p.k * 8;
+    const size_t smem = (size_t)(kScanWarps + 1) * p.k * (external ? 12 : 8);
     auto go = [&](auto kern) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -415,7 +493,7 @@ cudaError_t launch_topk_merge(const MergeParams &p, bool external, cudaStream_t 
         g_launches++;
         return cudaGetLastError();
     };
-    return external ? go(topk_merge_kernel<int64_t, true>) : go(topk_merge_kernel<uint32_t, false>);
+    return external ? go(topk_merge_ext_kernel) : go(topk_merge_kernel);
 }
 
 }  // namespace b200

@@ -38,6 +38,8 @@ struct MergeParams {
     int n_lists, k_in, k;
     int64_t nq;
     int descending;          // external only
+    int tie_mode;            // external only: 0 = smaller 64-bit id first, 1 = the reference's multimap insertion order
+    int32_t *out_list;       // external, tie_mode 1: source list of every output entry (nullable)
     int out_mode;            // kOut*
     int ip_min_quirk;        // part-scan IP: drop scores <= FLT_MIN
     const float *q_add;      // kOutAddQ: ||q||^2 per query; kOutCosQ: -(1/||q||) per query

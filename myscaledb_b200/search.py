@@ -22,6 +22,9 @@ from ._lib import lib
 L2, IP, COSINE, HAMMING, JACCARD = 0, 1, 2, 3, 4
 METRIC_NAMES = {"L2": L2, "IP": IP, "COSINE": COSINE, "HAMMING": HAMMING, "JACCARD": JACCARD}
 F32, BF16, BIN = 0, 1, 2
+# b200_corpus_set_path codes and b200_corpus_last_variant kernel ids
+PATH_AUTO, PATH_SCAN, PATH_TENSOR, PATH_CG1, PATH_CG2, PATH_CG2_MC2, PATH_CG2_MC4, PATH_TS = range(8)
+KERNEL_SCAN, KERNEL_GEMM_BF16, KERNEL_GEMM_TS, KERNEL_GEMM_TF32X3 = 1, 2, 3, 4
 
 
 class B200Error(RuntimeError):
@@ -121,6 +124,12 @@ class Corpus:
         _check(lib().b200_corpus_set_path(self._h, C.c_int(path)))
         return self
 
+    def last_variant(self):
+        """(kernel, cta_group, pairs_per_cluster, grid) of the last search: KERNEL_SCAN / _GEMM_BF16 / _GEMM_TS / _GEMM_TF32X3."""
+        kern, cg, mc, grid = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _check(lib().b200_corpus_last_variant(self._h, C.byref(kern), C.byref(cg), C.byref(mc), C.byref(grid)))
+        return kern.value, cg.value, mc.value, grid.value
+
     @property
     def size(self):
         n = C.c_int64()
@@ -177,6 +186,16 @@ def topk_merge_device_strided(dis_ptr, ids_ptr, n_lists, dis_stride, ids_stride,
                                                 C.c_int64(dis_stride), C.c_int64(ids_stride), C.c_int64(nq), C.c_int(k),
                                                 C.c_int(1 if descending else 0), C.c_void_p(out_dis_ptr),
                                                 C.c_void_p(out_ids_ptr), C.c_void_p(stream or None)))
+
+
+def topk_merge_device_ex(dis_ptr, ids_ptr, n_lists, dis_stride, ids_stride, nq, k_in, k, descending, tie_mode, out_dis_ptr,
+                         out_ids_ptr, out_list_ptr=0, stream=0):
+    """getTotalTopSearchResultImpl on device; tie_mode 1 reproduces the reference's multimap order (and reports the
+    source list / part of every winner in out_list)."""
+    _check(lib().b200_topk_merge_device_ex(C.c_void_p(dis_ptr), C.c_void_p(ids_ptr), C.c_int(n_lists), C.c_int64(dis_stride),
+                                           C.c_int64(ids_stride), C.c_int64(nq), C.c_int(k_in), C.c_int(k),
+                                           C.c_int(1 if descending else 0), C.c_int(tie_mode), C.c_void_p(out_dis_ptr),
+                                           C.c_void_p(out_ids_ptr), C.c_void_p(out_list_ptr or None), C.c_void_p(stream or None)))
 
 
 def launch_count(reset=False) -> int:

@@ -210,12 +210,15 @@ def test_scan_bf16_corpus():
 # ------------------------------------------------------------------ tcgen05 GEMM path vs oracle
 @pytest.mark.parametrize("metric", [b2.IP, b2.L2, b2.COSINE])
 @pytest.mark.parametrize("n,d,nq,k,path", [(20000, 768, 128, 10, 2), (5000, 64, 37, 30, 2), (70001, 128, 300, 10, 2),
-                                           (70001, 128, 300, 10, 3), (70001, 128, 300, 10, 4), (1000, 96, 20, 50, 2),
-                                           (33333, 768, 1024, 10, 2), (33333, 768, 1024, 10, 4), (33333, 768, 512, 10, 2), (257, 64, 129, 5, 2),
-                                           (9000, 512, 256, 10, 2), (9000, 832, 256, 10, 2)])
+                                           (70001, 128, 300, 10, 3), (70001, 128, 300, 10, 4), (70001, 128, 300, 10, 7), (1000, 96, 20, 50, 2),
+                                           (33333, 768, 1024, 10, 2), (33333, 768, 1024, 10, 4), (33333, 768, 1024, 10, 5),
+                                           (33333, 768, 1024, 10, 6), (33333, 768, 1024, 10, 7), (33333, 768, 512, 10, 2),
+                                           (33333, 768, 512, 30, 7), (257, 64, 129, 5, 2), (9000, 512, 256, 10, 2), (9000, 512, 256, 10, 7),
+                                           (9000, 832, 256, 10, 2)])
 def test_gemm_path_matches_oracle(metric, n, d, nq, k, path):
-    """path 2 = auto (CTA pairs, queries stationary in TMEM when d <= 768), 3 = single-CTA MMAs only,
-    4 = CTA pairs with both operands streamed through shared memory."""
+    """b200_corpus_set_path codes: 2 = the tensor-core variant auto picks (streaming + TMA multicast), 3 = single-CTA MMAs
+    <1,1>, 4 = CTA pairs without multicast <2,1>, 5 = <2,2>, 6 = <2,4>, 7 = queries stationary in TMEM (TS form).
+    The same variants at >= 2 M rows: tests/test_gpu_gemm_scale.py."""
     rng = np.random.default_rng(n + d + nq + metric)
     y = to_bf16_values(rng.standard_normal((n, d)).astype(F32))
     x = to_bf16_values(rng.standard_normal((nq, d)).astype(F32))
@@ -310,25 +313,52 @@ def test_gemm_equals_scan_large_property():
 
 
 def test_topk_merge_device_matches_oracle_merge():
+    """b200_topk_merge_device_ex against the oracle of getTotalTopSearchResultImpl (orc.merge_parts,
+    MergeTreeBaseSearchManager.cpp:207-299) on integer scores, i.e. with ties everywhere: tie_mode 1 must reproduce the
+    multimap order exactly (ascending: earlier part first; reverse walk for IP / BM25: later-inserted first) including the
+    part index of every winner; tie_mode 0 is this library's (score, smaller id) contract; ids are full 64-bit values."""
     torch = pytest.importorskip("torch")
     rng = np.random.default_rng(3)
-    L, nq, k = 8, 33, 10
+    for L, nq, k_in, k in ((8, 33, 10, 10), (3, 5, 30, 7), (16, 9, 100, 100), (2, 4, 5, 8)):
+        for desc in (False, True):
+            sc = rng.integers(-6, 7, (L, nq, k_in)).astype(F32)
+            sc = -np.sort(-sc, axis=2) if desc else np.sort(sc, axis=2)     # each part's list is sorted best-first
+            ids = (rng.permutation(L * nq * k_in).reshape(L, nq, k_in).astype(np.int64) + (1 << 33)) * 3   # beyond 2^32
+            ids[L - 1, nq - 1, k_in // 2:] = -1                           # a part that returned fewer than k rows
+            td, ti = torch.tensor(sc).cuda(), torch.tensor(ids).cuda()
+            od = torch.empty((nq, k), dtype=torch.float32, device="cuda"); oi = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+            ol = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+            for tie_mode in (0, 1):
+                S.topk_merge_device_ex(td.data_ptr(), ti.data_ptr(), L, nq * k_in, nq * k_in, nq, k_in, k, desc, tie_mode,
+                                       od.data_ptr(), oi.data_ptr(), ol.data_ptr())
+                torch.cuda.synchronize()
+                gd, gi, gl = od.cpu().numpy(), oi.cpu().numpy(), ol.cpu().numpy()
+                for q in range(nq):
+                    m = ids[:, q, :].reshape(-1) >= 0
+                    s1 = sc[:, q, :].reshape(-1)[m]; lab = ids[:, q, :].reshape(-1)[m]
+                    part = np.repeat(np.arange(L), k_in)[m]
+                    if tie_mode == 1:
+                        es, ep, el = orc.merge_parts(s1, part, lab, k, desc)
+                        n = len(es)
+                        assert gi[q, :n].tolist() == el.tolist() and gl[q, :n].tolist() == ep.tolist(), (L, nq, k_in, k, desc, q)
+                        np.testing.assert_array_equal(gd[q, :n], es)
+                    else:
+                        order = np.lexsort((lab, -s1 if desc else s1))[:k]
+                        n = len(order)
+                        assert gi[q, :n].tolist() == lab[order].tolist()
+                        np.testing.assert_array_equal(gd[q, :n], s1[order])
+                    assert (gi[q, n:] == -1).all()
+    # the plain entry points (tie_mode 0) still work on the [L][nq][k] layout
+    L, nq, k = 4, 6, 10
     dis = np.sort(rng.standard_normal((L, nq, k)).astype(F32), axis=2)
     ids = rng.permutation(L * nq * k).reshape(L, nq, k).astype(np.int64)
-    ids[3, 5, 7:] = -1
-    for desc in (False, True):
-        d_in = dis[:, :, ::-1].copy() if desc else dis
-        td, ti = torch.tensor(d_in).cuda(), torch.tensor(ids).cuda()
-        od = torch.empty((nq, k), dtype=torch.float32, device="cuda"); oi = torch.empty((nq, k), dtype=torch.int64, device="cuda")
-        torch.cuda.synchronize()
-        b2.topk_merge_device(td.data_ptr(), ti.data_ptr(), L, nq, k, desc, od.data_ptr(), oi.data_ptr())
-        torch.cuda.synchronize()
-        for q in range(nq):
-            m = ids[:, q, :].reshape(-1) >= 0
-            sc = d_in[:, q, :].reshape(-1)[m]; lab = ids[:, q, :].reshape(-1)[m]
-            order = np.lexsort((lab, -sc if desc else sc))[:k]
-            assert oi[q].cpu().numpy().tolist() == lab[order].tolist()
-            np.testing.assert_array_equal(od[q].cpu().numpy(), sc[order])
+    td, ti = torch.tensor(dis).cuda(), torch.tensor(ids).cuda()
+    od = torch.empty((nq, k), dtype=torch.float32, device="cuda"); oi = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    b2.topk_merge_device(td.data_ptr(), ti.data_ptr(), L, nq, k, False, od.data_ptr(), oi.data_ptr())
+    torch.cuda.synchronize()
+    for q in range(nq):
+        order = np.lexsort((ids[:, q].reshape(-1), dis[:, q].reshape(-1)))[:k]
+        assert oi[q].cpu().numpy().tolist() == ids[:, q].reshape(-1)[order].tolist()
 
 
 def test_concurrent_searches_are_reentrant():

@@ -1,10 +1,7 @@
 """Randomised GPU-vs-oracle properties (hypothesis) on small integer-valued inputs, where fp32 / bf16 / tf32 sums are
 exact and ties are everywhere, so every path of the library must return EXACTLY the oracle's ids and distances.
 
-Opt-in (written after round 1's GPU budget was spent, not yet run on a GPU):
-    B200_RUN_EXTRA=1 python -m pytest tests/test_gpu_properties.py -m gpu_extra -q
-They are neither `gpu` (the round-end suite) nor run on CPU (skipped without the env switch)."""
-import os
+Part of the `gpu` suite since round 2."""
 
 import numpy as np
 import pytest
@@ -12,8 +9,7 @@ from hypothesis import given, settings, strategies as st
 
 import oracle as orc
 
-pytestmark = [pytest.mark.gpu_extra,
-              pytest.mark.skipif(os.environ.get("B200_RUN_EXTRA") != "1", reason="opt-in: B200_RUN_EXTRA=1 on a GPU box")]
+pytestmark = pytest.mark.gpu
 F32 = np.float32
 
 
@@ -50,7 +46,7 @@ def test_bf16_corpus_paths_are_exact_on_integer_data(n, d, nq, k, seed, metric):
     y = rng.integers(-4, 5, (n, d)).astype(F32)   # exactly representable in bf16
     x = rng.integers(-4, 5, (nq, d)).astype(F32)
     do, io = orc.knn_flat(metric, x, y, k)
-    for path in (1, 2):
+    for path in (1, 2, 3, 4, 7):
         c = b2.Corpus(metric, d, dtype=S.BF16).append(y)
         c.set_path(path)
         dg, ig = c.search(x, k)
