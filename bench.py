@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample duration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--headline-only", action="store_true", help="A/B runs: skip verification and the extra keys")
     return ap.parse_args()
 
 
@@ -425,7 +426,7 @@ def main():
 
     # ---- the memory-bound FLAT scan on the same resident shard (BASELINE metric: "brute-force GB/s vs HBM peak")
     flat_scan = []
-    if rank == 0 or N > 1:
+    if (rank == 0 or N > 1) and not a.headline_only:
         try:  # an extra as well: a failure here must not cost the headline line
             for nq_s in (1, 8):
                 index.set_path(1)
@@ -451,7 +452,7 @@ def main():
     # ---- fp32 rows (the reference's native column type) on the tensor cores: 3xTF32 split GEMM, same batch, a
     #      2M-row fp32 copy of the shard's head (an extra, not the headline)
     fp32_batch = None
-    if N == 1 and rank == 0:
+    if N == 1 and rank == 0 and not a.headline_only:
         try:  # an extra: never lose the headline line to it (e.g. no HBM left next to a 100M-row corpus)
             m = int(min(shard_rows, 2_000_000))
             y32 = corpus[:m].to(torch.float32)
@@ -482,7 +483,7 @@ def main():
     # ---- verification of the TIMED path's results (the run fails on a mismatch) ----
     d_res, i_res = res
     verified = None
-    if not os.environ.get("B200_GEMM_DEBUG"):  # kernel experiments produce garbage on purpose
+    if not os.environ.get("B200_GEMM_DEBUG") and not a.headline_only:  # kernel experiments produce garbage on purpose
         assert (np.diff(d_res, axis=1) <= 0).all() and (i_res >= 0).all() and (i_res < a.rows).all()
         verified = verify_results(a, index, corpus, q_host, q_dev, d_res, i_res, row0, shard_rows, N, rank, dev)
 
@@ -526,7 +527,7 @@ def main():
         out["flat_scan"] = flat_scan
         if fp32_batch:
             out["fp32_batch"] = fp32_batch
-        if N == 1 and not a.no_cpu_baseline:
+        if N == 1 and not a.no_cpu_baseline and not a.headline_only:
             try:
                 out["cpu_baseline"] = cpu_baseline(a)
             except Exception as e:  # never lose the GPU line to a host-side problem

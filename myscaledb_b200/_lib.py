@@ -7,7 +7,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200search.so")
+# B200_LIB_PATH: an A/B build of the same library (tools/build_variant.sh); never a different implementation
+LIB_PATH = os.environ.get("B200_LIB_PATH") or os.path.join(_HERE, "libb200search.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "b200_search.h")
 
 _lib = None

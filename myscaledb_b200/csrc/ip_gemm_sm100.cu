@@ -29,6 +29,8 @@
 //   filtered / out-of-range rows: scale 0, bias +inf.
 //
 // Tensor-bound: 2 * 128 * 256 * d FLOP per tile; algorithmic HBM bytes = N * d * 2 once.
+#include <cstdlib>
+
 #include "gemm_common.cuh"
 
 namespace b200 {
@@ -70,6 +72,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     const int W = gridDim.x / p.q_tiles;  // the host launches a multiple of q_tiles CTAs
     const int64_t n_tiles = (p.n + BN - 1) / BN;
     const int kb_count = p.d_pad / BK;
+    const int KPS = p.kps;            // k-blocks per barrier stage (1 or 2; kb_count % KPS == 0)
+    const int NST = STAGES / KPS;     // barrier stages
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
@@ -133,35 +137,39 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 pacing = __shfl_sync(0xffffffffu, ok, 0) != 0;
             }
             __syncwarp();
-            for (int kb = 0; kb < kb_count; kb++) {
+            // KPS k-blocks share one full / empty barrier pair (slot = stage * KPS + sub): half the barrier round trips
+            // and polls of the producer and issuer warps at KPS = 2 for the same bytes in flight
+            for (int kb0 = 0; kb0 < kb_count; kb0 += KPS) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (p.debug & 4) {  // experiment: no TMA traffic, operands are whatever is in smem
                     if (is_leader && elect_one()) mbar_arrive(&full_bar[stage]);
                 } else if (elect_one()) {
-                    if (CG == 1) {
-                        mbar_arrive_expect_tx(&full_bar[stage], C::TX_BYTES);
-                        tma_load_2d(&map_q, &full_bar[stage], sA + stage * A_BYTES, kb * BK, qt * BM);
-                        tma_load_2d(&map_c, &full_bar[stage], sB + stage * C::B_BYTES, kb * BK, (int)(t * BN));
-                    } else {
-                        if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], C::TX_BYTES);
-                        tma_load_2d_cg2(&map_q, &full_bar[stage], sA + stage * A_BYTES, kb * BK, qt * BM);
-                        if (MC == 1) {
-                            tma_load_2d_cg2(&map_c, &full_bar[stage], sB + stage * C::B_BYTES, kb * BK,
-                                            (int)(t * BN + half * C::B_ROWS));
+                    if (CG == 1 || is_leader) mbar_arrive_expect_tx(&full_bar[stage], C::TX_BYTES * KPS);
+                    for (int sub = 0; sub < KPS; sub++) {
+                        const int kb = kb0 + sub, slot = stage * KPS + sub;
+                        if (CG == 1) {
+                            tma_load_2d(&map_q, &full_bar[stage], sA + slot * A_BYTES, kb * BK, qt * BM);
+                            tma_load_2d(&map_c, &full_bar[stage], sB + slot * C::B_BYTES, kb * BK, (int)(t * BN));
                         } else {
-                            // this CTA fetches slice `pair_in_cluster` of its half and multicasts it to the CTAs of
-                            // the same half in every pair of the cluster (ranks half, half + 2, ...)
-                            constexpr int SLICE_ROWS = C::B_ROWS / MC;
-                            uint16_t mask = 0;
-                            for (int pp = 0; pp < MC; pp++) mask |= (uint16_t)(1u << (pp * 2 + half));
-                            tma_load_2d_cg2_mc(&map_c, &full_bar[stage],
-                                               sB + stage * C::B_BYTES + pair_in_cluster * (SLICE_ROWS * BK * 2), kb * BK,
-                                               (int)(t * BN + half * C::B_ROWS + pair_in_cluster * SLICE_ROWS), mask);
+                            tma_load_2d_cg2(&map_q, &full_bar[stage], sA + slot * A_BYTES, kb * BK, qt * BM);
+                            if (MC == 1) {
+                                tma_load_2d_cg2(&map_c, &full_bar[stage], sB + slot * C::B_BYTES, kb * BK,
+                                                (int)(t * BN + half * C::B_ROWS));
+                            } else {
+                                // this CTA fetches slice `pair_in_cluster` of its half and multicasts it to the CTAs of
+                                // the same half in every pair of the cluster (ranks half, half + 2, ...)
+                                constexpr int SLICE_ROWS = C::B_ROWS / MC;
+                                uint16_t mask = 0;
+                                for (int pp = 0; pp < MC; pp++) mask |= (uint16_t)(1u << (pp * 2 + half));
+                                tma_load_2d_cg2_mc(&map_c, &full_bar[stage],
+                                                   sB + slot * C::B_BYTES + pair_in_cluster * (SLICE_ROWS * BK * 2), kb * BK,
+                                                   (int)(t * BN + half * C::B_ROWS + pair_in_cluster * SLICE_ROWS), mask);
+                            }
                         }
                     }
                 }
                 __syncwarp();
-                if (++stage == STAGES) {
+                if (++stage == NST) {
                     stage = 0;
                     phase ^= 1;
                 }
@@ -181,29 +189,32 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-                for (int kb = 0; kb < kb_count; kb++) {
+                for (int kb0 = 0; kb0 < kb_count; kb0 += KPS) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint64_t adesc = adesc0 + (uint64_t)(stage * (A_BYTES >> 4));
-                        const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (C::B_BYTES >> 4));
+                        for (int sub = 0; sub < KPS; sub++) {
+                            const int slot = stage * KPS + sub;
+                            const uint64_t adesc = adesc0 + (uint64_t)(slot * (A_BYTES >> 4));
+                            const uint64_t bdesc = bdesc0 + (uint64_t)(slot * (C::B_BYTES >> 4));
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; k++) {
-                            const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
-                            if (CG == 1) umma(tmem_d, adesc + k * (UMMA_K * 2 >> 4), bdesc + k * (UMMA_K * 2 >> 4), idesc, acc);
-                            else umma_cg2(tmem_d, adesc + k * (UMMA_K * 2 >> 4), bdesc + k * (UMMA_K * 2 >> 4), idesc, acc);
+                            for (int k = 0; k < BK / UMMA_K; k++) {
+                                const uint32_t acc = (kb0 | sub | k) != 0 ? 1u : 0u;
+                                if (CG == 1) umma(tmem_d, adesc + k * (UMMA_K * 2 >> 4), bdesc + k * (UMMA_K * 2 >> 4), idesc, acc);
+                                else umma_cg2(tmem_d, adesc + k * (UMMA_K * 2 >> 4), bdesc + k * (UMMA_K * 2 >> 4), idesc, acc);
+                            }
                         }
-                        // smem slot free (in both CTAs) once these MMAs retire
+                        // smem slots free (in both CTAs) once these MMAs retire
                         if (CG == 1) umma_commit(&empty_bar[stage]);
                         else umma_commit_cg2(&empty_bar[stage], (uint16_t)((1u << (CG * MC)) - 1));  // every CTA of the cluster
                         // accumulator ready for the epilogue (of both CTAs)
-                        if (kb == kb_count - 1) {
+                        if (kb0 + KPS >= kb_count) {
                             if (CG == 1) umma_commit(&tmem_full_bar[as]);
                             else umma_commit_cg2(&tmem_full_bar[as], (uint16_t)(3u << leader_rank));  // own pair
                         }
                     }
                     __syncwarp();
-                    if (++stage == STAGES) {
+                    if (++stage == NST) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -332,6 +343,10 @@ static cudaError_t launch_cg(const CUtensorMap &map_q, const CUtensorMap &map_c,
     p.lists_in_smem = Cfg<CG>::lists_fit(p.k) ? 1 : 0;
     const int k_smem = p.lists_in_smem ? p.k : 0;
     p.stages = Cfg<CG>::stages_for(k_smem);
+    {
+        static const int env_kps = getenv("B200_GEMM_KPS") ? atoi(getenv("B200_GEMM_KPS")) : 1;
+        p.kps = (env_kps == 2 && (p.d_pad / BK) % 2 == 0 && p.stages >= 4) ? 2 : 1;
+    }
     const size_t smem = (size_t)Cfg<CG>::off_list(p.stages) + (size_t)k_smem * EPI_THREADS * 8 + SMEM_ALIGN_SLACK;
     auto kern = gemm_topk_kernel<CG, MC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

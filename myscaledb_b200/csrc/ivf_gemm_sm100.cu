@@ -1,0 +1,400 @@
+// ivf_gemm_sm100.cu -- K5: the inverted-file scan as a GROUPED tensor-core top-k.
+//
+// Replaces the list scan inside Search::VectorIndex<...>::search for the IVF family (IVFFLAT / IVFSQ / IVFPQ / the
+// two-stage "MSTG"-class index), reached from VIWithColumnInPart::search (reference:
+// src/VectorIndex/Common/VIWithDataPart.cpp:926).  The reference's Faiss scans one (query, list) pair at a time on one
+// core.  Here the (query, probed list) pairs of a whole batch are first sorted BY LIST (ivf.cu), so that a list's rows
+// are streamed from HBM once for ALL queries that probe it, and the distances of <= 128 such queries x 256 rows are one
+// tcgen05.mma tile (M = 128 queries on the TMEM lanes, N = 256 rows, K = d): the same fused top-k epilogue as
+// ip_gemm_sm100.cu keeps one private k-list per query and the [queries x rows] scores never reach memory.
+//
+// Work item = (queries [q_begin, q_begin + q_count) of the list-sorted pair array) x (pages [page_begin, +page_count) of
+// one list).  Inverted lists are PAGED: a page is 256 consecutive pool rows = exactly one MMA tile, lists grow by
+// appending pages (streamed build, no compaction), long lists are split over several items / SMs.
+// Persistent CTAs walk items blockIdx.x, blockIdx.x + grid, ... (items are ordered by decreasing work on the host):
+//   warp 0      TMA producer: A = 128 gathered bf16 query rows (k-block of 64), B = one page's k-block
+//               (PRODUCER_TMA: bf16 rows as stored)
+//   warps 0+6..9 (PRODUCER_PQ / PRODUCER_SQ8) decoder warps: read the page's codes, look the sub-vectors up in the
+//               shared-memory codebook (PQ) or widen int8 (SQ8) and write the 128-byte-swizzled bf16 B tile themselves
+//   warp 1      MMA issuer (tcgen05.mma cta_group::1 kind::f16), accumulators double-buffered in TMEM
+//   warps 2..5  epilogue: thread t = query slot t; key = acc * scale + bias (L2: ||y||^2 - 2 q.y; IP / cosine: -q.y);
+//               rows beyond the page fill, filtered rows -> +inf
+// HBM-bound by design: algorithmic bytes = (rows of the probed pages) x payload bytes per row, once per item.
+#include <cstdlib>
+
+#include "gemm_common.cuh"
+#include "ivf_gemm.h"
+
+namespace b200 {
+namespace gemm {
+
+constexpr int IVF_THREADS_TMA = 192;       // producer, issuer, 4 epilogue warps
+constexpr int IVF_DEC_WARPS = 4;           // extra decoder warps of the code payloads
+constexpr int IVF_THREADS_DEC = IVF_THREADS_TMA + IVF_DEC_WARPS * 32;
+
+// smem (PRODUCER_TMA): the Cfg<1> layout of ip_gemm_sm100.cu.  Code payloads add a codebook region behind the lists.
+template <int PRODUCER, int DSUB>
+__global__ void __launch_bounds__(PRODUCER == IVF_PRODUCER_TMA ? IVF_THREADS_TMA : IVF_THREADS_DEC, 1)
+ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c, const IvfGemmParams p) {
+    using C = Cfg<1>;
+    const int STAGES = p.stages;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char *sA = smem + C::off_a();
+    unsigned char *sB = smem + C::off_b(STAGES);
+    float *side_scale = reinterpret_cast<float *>(smem + C::off_side(STAGES));
+    float *side_bias = side_scale + BN;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + C::off_bar(STAGES));
+    uint64_t *empty_bar = full_bar + MAX_STAGES;
+    uint64_t *tmem_full_bar = empty_bar + MAX_STAGES;
+    uint64_t *tmem_empty_bar = tmem_full_bar + ACC_STAGES;
+    uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kb_count = p.d_pad / BK;
+    constexpr bool DEC = PRODUCER != IVF_PRODUCER_TMA;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
+        if (!DEC) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_c)) : "memory");
+        for (int i = 0; i < STAGES; i++) {
+            // full: the TMA transaction (+ one arrival per decoder warp that wrote its quarter of the B tile)
+            mbar_init(&full_bar[i], DEC ? 1 + IVF_DEC_WARPS : 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < ACC_STAGES; i++) {
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (DEC) {
+        // codebook -> shared memory (behind the per-thread lists): PQ [m][256][dsub] bf16; SQ8 has none
+        if (PRODUCER == IVF_PRODUCER_PQ) {
+            uint4 *dst = reinterpret_cast<uint4 *>(smem + p.codebook_smem_off);
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.codebook_bf16);
+            for (int i = threadIdx.x; i < p.codebook_bytes / 16; i += blockDim.x) dst[i] = src[i];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+            const IvfGemmItem item = p.items[it];
+            for (uint32_t j = 0; j < item.page_count; j++) {
+                const uint32_t page = p.list_pages[item.page_begin + j];
+                for (int kb = 0; kb < kb_count; kb++) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&full_bar[stage], DEC ? A_BYTES : C::TX_BYTES);
+                        tma_load_2d(&map_q, &full_bar[stage], sA + stage * A_BYTES, kb * BK, (int)item.q_begin);
+                        if (!DEC) tma_load_2d(&map_c, &full_bar[stage], sB + stage * C::B_BYTES, kb * BK, (int)(page * (uint32_t)BN));
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc(1);
+        const uint64_t adesc0 = make_smem_desc(smem_u32(sA));
+        const uint64_t bdesc0 = make_smem_desc(smem_u32(sB));
+        int stage = 0, as = 0;
+        uint32_t phase = 0, aphase = 0;
+        for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+            const uint32_t page_count = p.items[it].page_count;
+            for (uint32_t j = 0; j < page_count; j++) {
+                mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < kb_count; kb++) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t adesc = adesc0 + (uint64_t)(stage * (A_BYTES >> 4));
+                        const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (C::B_BYTES >> 4));
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; k++)
+                            umma(tmem_d, adesc + k * (UMMA_K * 2 >> 4), bdesc + k * (UMMA_K * 2 >> 4), idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == kb_count - 1) umma_commit(&tmem_full_bar[as]);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                if (++as == ACC_STAGES) {
+                    as = 0;
+                    aphase ^= 1;
+                }
+            }
+        }
+    } else if (warp < 6) {
+        // ===================== epilogue: fused top-k, one list per (item, query slot) =====================
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;          // query slot inside the item
+        const int et = threadIdx.x - 64;
+        float *scratch = reinterpret_cast<float *>(smem + C::off_scratch(STAGES)) + et;
+        ThreadTopK list;
+        list.k = p.k;
+        if (p.lists_in_smem) {
+            list.keys = reinterpret_cast<float *>(smem + C::off_list(STAGES)) + row;
+            list.ids = reinterpret_cast<uint32_t *>(smem + C::off_list(STAGES) + (size_t)p.k * EPI_THREADS * 4) + row;
+        } else {
+            list.keys = p.list_keys_gmem + (size_t)blockIdx.x * p.k * EPI_THREADS + row;
+            list.ids = p.list_ids_gmem + (size_t)blockIdx.x * p.k * EPI_THREADS + row;
+        }
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+            const IvfGemmItem item = p.items[it];
+            list.n = 0;
+            list.worst = 0;
+            list.thr_key = ((uint32_t)row < item.q_count) ? FLT_MAX : -FLT_MAX;   // padding slots never enter the slow path
+            list.thr_id = 0;
+            for (uint32_t j = 0; j < item.page_count; j++) {
+                const uint32_t page = p.list_pages[item.page_begin + j];
+                const uint32_t row0 = page * (uint32_t)BN;
+                const uint32_t valid = item.row_limit - j * (uint32_t)BN;   // rows of the list left from this page on (>= 1)
+                asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers done
+                for (int c = et; c < BN; c += EPI_THREADS) {
+                    bool ok = (uint32_t)c < valid;
+                    if (ok && p.alive) {
+                        const uint32_t id = p.row_ids[row0 + c];
+                        ok = (p.alive[id >> 3] >> (id & 7)) & 1;
+                    }
+                    side_scale[c] = ok ? p.scale_const : 0.f;
+                    side_bias[c] = ok ? (p.row_bias ? p.row_bias[row0 + c] : 0.f) : __int_as_float(0x7f800000);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                mbar_wait(&tmem_full_bar[as], aphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
+                float va[32], vb[32];
+                __syncwarp();
+                tmem_ld32_issue(taddr, va);
+                tmem_ld_wait();
+#pragma unroll 1
+                for (int chunk = 0; chunk < BN / 32; chunk += 2) {
+                    __syncwarp();
+                    tmem_ld32_issue(taddr + (chunk + 1) * 32, vb);
+                    epilogue_chunk(list, va, true, side_scale + chunk * 32, side_bias + chunk * 32, row0 + chunk * 32, false, 0, scratch);
+                    tmem_ld_wait();
+                    __syncwarp();
+                    if (chunk + 2 < BN / 32) tmem_ld32_issue(taddr + (chunk + 2) * 32, va);
+                    epilogue_chunk(list, vb, true, side_scale + (chunk + 1) * 32, side_bias + (chunk + 1) * 32,
+                                   row0 + (chunk + 1) * 32, false, 0, scratch);
+                    tmem_ld_wait();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+                if (++as == ACC_STAGES) {
+                    as = 0;
+                    aphase ^= 1;
+                }
+            }
+            // publish this (item, query slot)'s partial list: unsorted, pool rows mapped to row ids, worst kept key aside
+            if ((uint32_t)row < item.q_count) {
+                const size_t part = (size_t)p.pair_part_base[item.q_begin + row] + item.chunk;
+                float *ok = p.part_keys + part * p.k;
+                uint32_t *oi = p.part_ids + part * p.k;
+                for (int e = 0; e < p.k; e++) {
+                    const bool have = e < list.n;
+                    ok[e] = have ? list.keys[e * EPI_THREADS] : FLT_MAX;
+                    oi[e] = have ? p.row_ids[list.ids[e * EPI_THREADS]] : kNoId;
+                }
+                p.part_worst[part] = list.n == p.k ? list.thr_key : FLT_MAX;
+            }
+        }
+    } else if (DEC) {
+        // ===================== decoder warps: codes -> bf16 B tile (128-byte swizzled, K-major) =====================
+        // warp w decodes rows [w * 64, w * 64 + 64) of the page; a lane owns one row per pass and writes its 8 16-byte
+        // chunks of the k-block: chunk c of row r lives at r * 128 + ((c ^ (r & 7)) << 4) inside the 8-row / 1024-byte atoms
+        const int dw = warp - 6;
+        int stage = 0;
+        uint32_t phase = 0;
+        const unsigned char *cb = smem + p.codebook_smem_off;
+        for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+            const IvfGemmItem item = p.items[it];
+            for (uint32_t j = 0; j < item.page_count; j++) {
+                const uint32_t page = p.list_pages[item.page_begin + j];
+                const uint8_t *codes = p.codes + (size_t)page * BN * p.code_bytes;
+                for (int kb = 0; kb < kb_count; kb++) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char *bt = sB + stage * C::B_BYTES;
+#pragma unroll 1
+                    for (int rr = 0; rr < 2; rr++) {
+                        const int r = dw * 64 + rr * 32 + lane;
+                        unsigned char *rowp = bt + (r >> 3) * 1024 + (r & 7) * 128;
+                        const uint8_t *code_r = codes + (size_t)r * p.code_bytes;
+                        if (PRODUCER == IVF_PRODUCER_SQ8) {
+                            // 64 int8 codes of this k-block -> 64 bf16 (exact: |code| <= 127); query side carries the scales
+                            const uint4 *src = reinterpret_cast<const uint4 *>(code_r + kb * BK);
+#pragma unroll
+                            for (int c4 = 0; c4 < 4; c4++) {
+                                const bool in = kb * BK + c4 * 16 < p.code_bytes;
+                                const uint4 w = in ? src[c4] : make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+                                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+                                uint32_t o[8];
+#pragma unroll
+                                for (int h = 0; h < 4; h++) {
+                                    // bytes are offset-binary (value + 128): subtract in fp32, pack two bf16 per word
+                                    const float f0 = (float)(int)(ww[h] & 255) - 128.f, f1 = (float)(int)((ww[h] >> 8) & 255) - 128.f;
+                                    const float f2 = (float)(int)((ww[h] >> 16) & 255) - 128.f, f3 = (float)(int)(ww[h] >> 24) - 128.f;
+                                    o[h * 2] = (__float_as_uint(f0) >> 16) | (__float_as_uint(f1) & 0xffff0000u);
+                                    o[h * 2 + 1] = (__float_as_uint(f2) >> 16) | (__float_as_uint(f3) & 0xffff0000u);
+                                }
+                                const int c0 = c4 * 2;
+                                *reinterpret_cast<uint4 *>(rowp + (((c0) ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                                *reinterpret_cast<uint4 *>(rowp + (((c0 + 1) ^ (r & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+                            }
+                        } else {
+                            // PQ: dims [kb * 64, kb * 64 + 64) = sub-quantisers [kb * 64 / DSUB, ...), each code byte selects
+                            // DSUB bf16 values of the shared-memory codebook [m][256][DSUB]; the codes of one k-block are
+                            // NSUB consecutive bytes of the row (row stride and offsets are multiples of 16 / NSUB)
+                            constexpr int NSUB = BK / (DSUB > 0 ? DSUB : 1);   // 64, 32, 16, 8 codes per k-block
+                            constexpr int BYTES_PER = (DSUB > 0 ? DSUB : 1) * 2;
+                            const int j0 = kb * NSUB;
+                            uint32_t cw[NSUB / 4];
+                            if (NSUB >= 16) {
+#pragma unroll
+                                for (int t = 0; t < NSUB / 16; t++) {
+                                    const uint4 v = (j0 + t * 16 < p.code_bytes) ? *reinterpret_cast<const uint4 *>(code_r + j0 + t * 16)
+                                                                                 : make_uint4(0, 0, 0, 0);
+                                    cw[t * 4] = v.x; cw[t * 4 + 1] = v.y; cw[t * 4 + 2] = v.z; cw[t * 4 + 3] = v.w;
+                                }
+                            } else {
+                                const uint2 v = (j0 < p.code_bytes) ? *reinterpret_cast<const uint2 *>(code_r + j0) : make_uint2(0, 0);
+                                cw[0] = v.x; cw[1] = v.y;
+                            }
+                            uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+                            for (int s = 0; s < NSUB; s++) {
+                                const int jj = j0 + s;
+                                const uint32_t code = (cw[s >> 2] >> ((s & 3) * 8)) & 255u;
+                                constexpr int PER_CHUNK = 16 / BYTES_PER;      // look-ups per 16-byte chunk
+                                const int slot = s % PER_CHUNK;
+                                if (jj < p.m) {
+                                    const unsigned char *e = cb + ((size_t)jj * 256 + code) * BYTES_PER;
+                                    if (DSUB == 8) {
+                                        const uint4 v = *reinterpret_cast<const uint4 *>(e);
+                                        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+                                    } else if (DSUB == 4) {
+                                        const uint2 v = *reinterpret_cast<const uint2 *>(e);
+                                        w[slot * 2] = v.x; w[slot * 2 + 1] = v.y;
+                                    } else if (DSUB == 2) {
+                                        w[slot] = *reinterpret_cast<const uint32_t *>(e);
+                                    } else {
+                                        const uint32_t v = *reinterpret_cast<const uint16_t *>(e);
+                                        if (slot & 1) w[slot >> 1] |= v << 16; else w[slot >> 1] = v;
+                                    }
+                                }
+                                if (slot == PER_CHUNK - 1) {
+                                    const int chunk = s / PER_CHUNK;
+                                    *reinterpret_cast<uint4 *>(rowp + ((chunk ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                                    w[0] = w[1] = w[2] = w[3] = 0;
+                                }
+                            }
+                        }
+                    }
+                    // generic-proxy writes -> visible to the async proxy (tcgen05.mma reads smem through it)
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[stage]);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+template <int PRODUCER, int DSUB>
+static cudaError_t launch_ivf(const CUtensorMap &map_q, const CUtensorMap &map_c, IvfGemmParams p, int grid, cudaStream_t s) {
+    constexpr bool DEC = PRODUCER != IVF_PRODUCER_TMA;
+    // ring depth: as deep as the per-thread lists (and the PQ codebook) leave room for
+    const int extra = PRODUCER == IVF_PRODUCER_PQ ? (int)round_up(p.codebook_bytes, 1024) : 0;
+    int stages = 4;
+    auto need = [&](int st, int k_smem) { return Cfg<1>::off_list(st) + k_smem * EPI_THREADS * 8 + extra + SMEM_ALIGN_SLACK; };
+    p.lists_in_smem = 0;
+    for (int st = 4; st >= 2; st--)
+        if (p.k <= kGemmSmemK && need(st, p.k) <= 232448) {
+            stages = st;
+            p.lists_in_smem = 1;
+            break;
+        }
+    if (!p.lists_in_smem) {
+        stages = 4;
+        while (stages > 2 && need(stages, 0) > 232448) stages--;
+        if (need(stages, 0) > 232448) return cudaErrorInvalidValue;
+    }
+    p.stages = stages;
+    const int k_smem = p.lists_in_smem ? p.k : 0;
+    p.codebook_smem_off = Cfg<1>::off_list(stages) + k_smem * EPI_THREADS * 8;
+    p.codebook_smem_off = (int)round_up(p.codebook_smem_off, 16);
+    const size_t smem = (size_t)need(stages, k_smem) + 16;
+    auto kern = ivf_gemm_topk_kernel<PRODUCER, DSUB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, DEC ? IVF_THREADS_DEC : IVF_THREADS_TMA, smem, s>>>(map_q, map_c, p);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace gemm
+
+cudaError_t launch_ivf_gemm_topk(const IvfGemmParams &p, const void *queries_bf16, int64_t n_query_rows, const void *pool_bf16,
+                                 int64_t pool_rows, int grid, cudaStream_t s, const char **err_detail) {
+    *err_detail = nullptr;
+    CUtensorMap map_q, map_c;
+    if (!gemm::encode_rows_map(&map_q, queries_bf16, n_query_rows, p.d_pad, gemm::BM)) {
+        *err_detail = "cuTensorMapEncodeTiled failed (queries)";
+        return cudaErrorInvalidValue;
+    }
+    if (p.producer == IVF_PRODUCER_TMA) {
+        if (!gemm::encode_rows_map(&map_c, pool_bf16, pool_rows, p.d_pad, gemm::BN)) {
+            *err_detail = "cuTensorMapEncodeTiled failed (pool)";
+            return cudaErrorInvalidValue;
+        }
+        return gemm::launch_ivf<IVF_PRODUCER_TMA, 0>(map_q, map_c, p, grid, s);
+    }
+    map_c = map_q;  // unused by the decoding producers
+    if (p.producer == IVF_PRODUCER_SQ8) return gemm::launch_ivf<IVF_PRODUCER_SQ8, 0>(map_q, map_c, p, grid, s);
+    switch (p.dsub) {
+        case 1: return gemm::launch_ivf<IVF_PRODUCER_PQ, 1>(map_q, map_c, p, grid, s);
+        case 2: return gemm::launch_ivf<IVF_PRODUCER_PQ, 2>(map_q, map_c, p, grid, s);
+        case 4: return gemm::launch_ivf<IVF_PRODUCER_PQ, 4>(map_q, map_c, p, grid, s);
+        case 8: return gemm::launch_ivf<IVF_PRODUCER_PQ, 8>(map_q, map_c, p, grid, s);
+    }
+    *err_detail = "PQ decode producer needs dsub in {1, 2, 4, 8}";
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace b200

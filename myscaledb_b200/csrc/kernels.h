@@ -74,6 +74,7 @@ struct GemmTopkParams {
     int pairs_per_cluster;     // 1, or 2: two CTA pairs share (TMA-multicast) every corpus tile; q_tiles % 4 == 0
     int *progress;             // [grid / q_tiles][q_tiles] zeroed pacing counters, or null
     int stages;                // smem ring depth (filled in by the launcher)
+    int kps;                   // k-blocks per full/empty barrier stage (1 or 2; filled in by the launcher)
     int lists_in_smem;         // per-thread top-k lists in shared memory (else global scratch); set by the launcher
     int debug;                 // experiments only (B200_GEMM_DEBUG): 1 no epilogue, 2 TMEM loads only, 4 no TMA
     int sync_slack;            // tiles a CTA may run ahead of the slowest sharer of its corpus tiles
