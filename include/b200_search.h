@@ -164,28 +164,59 @@ int b200_topk_merge_device_ex(const float *d_dis, const int64_t *d_ids, int n_li
 /* ------------------------------------------------------------------------------------
  * Vector indexes.  Replaces Search::createVectorIndex / VectorIndex::{build, search,
  * computeTopDistanceSubset} (VectorIndex/Common/VIWithDataPart.cpp:416-430, :131, :926, :838-856).
- * type: "FLAT", "IVFFLAT", "IVFPQ", "MSTG" (MSTG is closed source upstream; here it names our
- * two-stage index: IVFPQ first stage + exact fp32 re-rank).  params: the
- * reference's key=value / JSON parameter string ("ncentroids=1024, M=32", "nprobe=64",
- * "refine_factor=8").  Parts smaller than max(2000, 8 * nlist) rows are served by an exact FLAT
- * scan (the reference's fallback_to_flat, test 00029).
+ * type (the reference's index type names, VectorIndex/Common/VICommon.h:178-180 and the 2_vector_search tests):
+ *   "FLAT"                      exact scan of the resident rows;
+ *   "IVFFLAT"                   inverted lists holding bf16 rows, candidates re-ranked exactly against the fp32 rows;
+ *   "IVFSQ"                     lists of 8-bit scalar-quantised rows (one byte per dimension);
+ *   "IVFPQ"                     lists of m-byte product-quantiser codes of the residual (d / M in {1, 2, 4, 8}, d <= 320);
+ *   "MSTG"                      closed source upstream; here the two-stage index of SURVEY 2.5 K6: bf16 lists + exact
+ *                               fp32 second stage (supportTwoStageSearch, first_stage_only, computeTopDistanceSubset);
+ *   "SCANN", "HNSWFLAT", "HNSWSQ", "HNSWPQ"   accepted and SERVED BY THE INVERTED-FILE ENGINE with the payload their
+ *                               name implies (PQ + re-rank, bf16, 8-bit, PQ): there is no graph traversal and no
+ *                               anisotropic quantiser in this library; the contract for every ANN type is recall against
+ *                               FLAT, not traversal order (parity unpinned for ANN at large N).
+ * params: the reference's key=value / JSON parameter string: "ncentroids=1024" (or nlist), "M=32", "nprobe=64",
+ * "refine_factor=8" (candidates per returned row handed to the exact second stage; 1 = first-stage distances),
+ * "keep_raw=0" (do not keep the fp32 rows: no second stage, half the memory).  Parts smaller than
+ * max(2000, 8 * nlist) rows are served by an exact FLAT scan (the reference's fallback_to_flat, test 00029).
+ *
+ * Build = the reference's reader-driven build (VIPartReader train block / add blocks, VIWithDataPart.cpp:131):
+ *   b200_index_reserve(total rows)  -- createVectorIndex's total_vec: sizes the page pool
+ *   b200_index_train(sample)        -- coarse k-means (+ PQ codebooks / SQ ranges) on a sample
+ *   b200_index_add(chunk) ...       -- any number of chunks, row ids continue from the rows already added
+ *   b200_index_finalize()
+ * b200_index_build(rows, n) does all four from one host array.  *_device variants take fp32 rows already in HBM.
  * ---------------------------------------------------------------------------------- */
 typedef struct b200_index b200_index;
 int b200_index_create(const char *type, int metric, int d, const char *params, b200_index **out);
 int b200_index_build(b200_index *ix, const float *rows, int64_t n);
+int b200_index_reserve(b200_index *ix, int64_t total_rows);
+int b200_index_train(b200_index *ix, const float *rows, int64_t n);
+int b200_index_train_device(b200_index *ix, const float *d_rows, int64_t n);
+int b200_index_add(b200_index *ix, const float *rows, int64_t n);
+int b200_index_add_device(b200_index *ix, const float *d_rows, int64_t n);
+int b200_index_finalize(b200_index *ix);
 int b200_index_info(const b200_index *ix, int64_t *n, int *nlist, int *m, int *uses_ivf);
-/* first_stage_only (MSTG): return the first-stage candidates with approximate distances;
+/* first_stage_only (two-stage types): return the first-stage candidates with first-stage distances;
  * out_num_candidates receives the width the first stage ran with (SearchResult::getNumCandidates).
- * Batch planner: when one exact pass over the raw rows on the tensor cores is estimated cheaper than nq * nprobe list
- * probes (large batches, skewed lists), the search runs there instead and returns exact results (recall 1,
- * *out_num_candidates = k).  "exact_batch=0" / "exact_batch=1" in `params` forces the probe / the exact pass. */
+ * "exact_batch=1" in `params` answers by an exact pass over the fp32 rows instead (recall 1). */
 int b200_index_search(b200_index *ix, const float *queries, int64_t nq, int k, const char *params, int first_stage_only,
                       const uint8_t *alive_bits /*nullable*/, float *out_dis, int64_t *out_ids, int64_t *out_num_candidates);
+/* same with device buffers, asynchronous on `stream` (NULL = the index's own stream, synchronised); id_offset is added to
+ * every returned id (shard base for multi-GPU merges) */
+int b200_index_search_device(b200_index *ix, const float *d_queries, int64_t nq, int k, const char *params, int first_stage_only,
+                             const uint8_t *d_alive_bits /*nullable*/, int64_t id_offset, float *d_out_dis, int64_t *d_out_ids,
+                             void *stream);
+/* roofline inputs of the list scan: CUDA-event time of the grouped scan kernel since the last reset, bytes per list row,
+ * and an upper bound of the work items of the last search */
+int b200_index_enable_timing(b200_index *ix, int on);
+int b200_index_last_scan(b200_index *ix, int64_t *rows_streamed, int64_t *payload_row_bytes, int64_t *work_items,
+                         double *kernel_ms_total, int64_t *kernel_launches, int reset);
 /* computeTopDistanceSubset: exact distances of candidate ids [nq][ncand] (negative = unused) -> top-k */
 int b200_index_refine(b200_index *ix, const float *queries, int64_t nq, const int64_t *cand_ids, int64_t ncand, int k,
                       float *out_dis, int64_t *out_ids);
 /* VIWithColumnInPart::serialize / load (VIWithDataPart.cpp:451-525, :578-764): one self-describing file
- * ("B2IX" v1; the closed library's .vidx3 payload cannot be reproduced). */
+ * ("B2IX" v2; the closed library's .vidx3 payload cannot be reproduced).  load validates every size it derives. */
 int b200_index_save(b200_index *ix, const char *path);
 int b200_index_load(const char *path, b200_index **out);
 int b200_index_free(b200_index *ix);

@@ -142,9 +142,30 @@ static void timing_end(b200_corpus *c, cudaStream_t s, std::pair<cudaEvent_t, cu
     if (c->ev_used.size() >= 1024) timing_drain(c);  // nobody asked for the totals for a while: keep the list bounded
 }
 
+static int corpus_alloc(b200_corpus *c, int64_t rows);
+static int corpus_norms(b200_corpus *c, int64_t first, int64_t n);
+
 namespace b200 {
 // hooks for the index layer (ivf.cu): device view of the rows / in-place row normalisation
 const void *corpus_device_rows(const b200_corpus *c) { return c->data; }
+// append fp32 rows [n][d] that already live on the device (index build, centroid tables); asynchronous on s except for
+// a reallocation, synchronised before returning so that the caller may reuse d_rows
+int corpus_append_device(b200_corpus *c, const float *d_rows, int64_t n, cudaStream_t s) {
+    if (!c || (!d_rows && n > 0) || n < 0) return fail(B200_ERR_INVALID, "bad arguments");
+    if (c->dtype == B200_DTYPE_BIN) return fail(B200_ERR_UNSUPPORTED, "device append: float corpora only");
+    if (n == 0) return B200_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    B200_CUDA_OK(cudaSetDevice(c->device));
+    B200_TRY(corpus_alloc(c, std::max(c->n + n, c->cap)));
+    char *dst = reinterpret_cast<char *>(c->data) + c->n * c->row_bytes;
+    if (c->dtype == B200_DTYPE_BF16) B200_CUDA_OK(launch_f32_to_bf16_rows(d_rows, c->d, dst, c->d_pad, n, s));
+    else B200_CUDA_OK(launch_pad_rows_f32(d_rows, c->d, reinterpret_cast<float *>(dst), c->d_pad, n, s));
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    B200_TRY(corpus_norms(c, c->n, n));
+    B200_CUDA_OK(cudaStreamSynchronize(c->stream));
+    c->n += n;
+    return B200_OK;
+}
 int corpus_normalize_rows(b200_corpus *c) {
     if (c->dtype != B200_DTYPE_F32) return fail(B200_ERR_UNSUPPORTED, "normalise: fp32 corpora only");
     B200_CUDA_OK(cudaSetDevice(c->device));

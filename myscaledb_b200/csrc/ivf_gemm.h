@@ -19,7 +19,7 @@ struct IvfGemmItem {
 
 struct IvfGemmParams {
     const IvfGemmItem *items;
-    int n_items;
+    const int *n_items_ptr;           // device scalar written by the planning kernel
     const uint32_t *list_pages;       // page ids, list after list
     const float *row_bias;            // [pool rows] L2: ||y||^2 (PQ: 2<c, r^> + ||r^||^2); null for IP / cosine
     const uint32_t *row_ids;          // [pool rows] row id inside the part

@@ -53,6 +53,7 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kb_count = p.d_pad / BK;
     constexpr bool DEC = PRODUCER != IVF_PRODUCER_TMA;
+    const int n_items = *p.n_items_ptr;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
@@ -90,7 +91,7 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         // ===================== TMA producer =====================
         int stage = 0;
         uint32_t phase = 0;
-        for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
             const IvfGemmItem item = p.items[it];
             for (uint32_t j = 0; j < item.page_count; j++) {
                 const uint32_t page = p.list_pages[item.page_begin + j];
@@ -116,7 +117,7 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const uint64_t bdesc0 = make_smem_desc(smem_u32(sB));
         int stage = 0, as = 0;
         uint32_t phase = 0, aphase = 0;
-        for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
             const uint32_t page_count = p.items[it].page_count;
             for (uint32_t j = 0; j < page_count; j++) {
                 mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
@@ -163,7 +164,7 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         }
         int as = 0;
         uint32_t aphase = 0;
-        for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
             const IvfGemmItem item = p.items[it];
             list.n = 0;
             list.worst = 0;
@@ -232,7 +233,7 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         int stage = 0;
         uint32_t phase = 0;
         const unsigned char *cb = smem + p.codebook_smem_off;
-        for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
             const IvfGemmItem item = p.items[it];
             for (uint32_t j = 0; j < item.page_count; j++) {
                 const uint32_t page = p.list_pages[item.page_begin + j];

@@ -322,7 +322,7 @@ def hybrid_fusion_batch(fusion_type, vec_lists, txt_lists, top_k, fusion_weight=
 
 class VectorIndex:
     """Mirror of Search::VectorIndex as driven by VIWithColumnInPart (build / search / computeTopDistanceSubset,
-    src/VectorIndex/Common/VIWithDataPart.cpp:131, :926, :838-856).  type: FLAT, IVFFLAT, IVFPQ, MSTG."""
+    src/VectorIndex/Common/VIWithDataPart.cpp:131, :926, :838-856).  type: FLAT, IVFFLAT, IVFSQ, IVFPQ, MSTG, SCANN, HNSW*."""
 
     def __init__(self, index_type, metric, d, params=""):
         self._h = C.c_void_p()
@@ -333,6 +333,54 @@ class VectorIndex:
         rows = np.ascontiguousarray(rows, np.float32)
         _check(lib().b200_index_build(self._h, _p(rows, C.c_float), C.c_int64(rows.shape[0])))
         return self
+
+    # streamed build (VIPartReader: train block, then add blocks)
+    def reserve(self, total_rows):
+        _check(lib().b200_index_reserve(self._h, C.c_int64(total_rows)))
+        return self
+
+    def train(self, rows):
+        rows = np.ascontiguousarray(rows, np.float32)
+        _check(lib().b200_index_train(self._h, _p(rows, C.c_float), C.c_int64(rows.shape[0])))
+        return self
+
+    def add(self, rows):
+        rows = np.ascontiguousarray(rows, np.float32)
+        _check(lib().b200_index_add(self._h, _p(rows, C.c_float), C.c_int64(rows.shape[0])))
+        return self
+
+    def train_device(self, ptr: int, n: int):
+        _check(lib().b200_index_train_device(self._h, C.c_void_p(ptr), C.c_int64(n)))
+        return self
+
+    def add_device(self, ptr: int, n: int):
+        _check(lib().b200_index_add_device(self._h, C.c_void_p(ptr), C.c_int64(n)))
+        return self
+
+    def finalize(self):
+        _check(lib().b200_index_finalize(self._h))
+        return self
+
+    def search_device(self, q_ptr: int, nq: int, k: int, out_dis_ptr: int, out_ids_ptr: int, params="", first_stage_only=False,
+                      id_offset=0, alive_ptr: int = 0, stream: int = 0):
+        _check(lib().b200_index_search_device(self._h, C.c_void_p(q_ptr), C.c_int64(nq), C.c_int(k), params.encode(),
+                                              C.c_int(1 if first_stage_only else 0), C.c_void_p(alive_ptr or None),
+                                              C.c_int64(id_offset), C.c_void_p(out_dis_ptr), C.c_void_p(out_ids_ptr),
+                                              C.c_void_p(stream or None)))
+
+    def enable_timing(self, on=True):
+        _check(lib().b200_index_enable_timing(self._h, C.c_int(1 if on else 0)))
+
+    def last_scan(self, reset=False):
+        rows, rb, items, ms, nl = C.c_int64(), C.c_int64(), C.c_int64(), C.c_double(), C.c_int64()
+        _check(lib().b200_index_last_scan(self._h, C.byref(rows), C.byref(rb), C.byref(items), C.byref(ms), C.byref(nl),
+                                          C.c_int(1 if reset else 0)))
+        return dict(rows_streamed=rows.value, payload_row_bytes=rb.value, work_items=items.value, kernel_ms=ms.value, launches=nl.value)
+
+    def memory_bytes(self):
+        b = C.c_uint64()
+        _check(lib().b200_index_memory_bytes(self._h, C.byref(b)))
+        return b.value
 
     def info(self):
         n, nl, m, ivf = C.c_int64(), C.c_int(), C.c_int(), C.c_int()

@@ -1,4 +1,5 @@
-"""IVFFLAT / IVFPQ / two-stage (MSTG-type) indexes and computeTopDistanceSubset on the GPU.
+"""IVFFLAT / IVFSQ / IVFPQ / two-stage (MSTG-type) indexes (paged lists, grouped tensor-core scan) and
+computeTopDistanceSubset on the GPU.
 There is no runnable reference for ANN behaviour (closed / un-vendored libraries): "parity unpinned"
 for large-N recall; the contract is recall vs the exact FLAT answer (validated against the oracle)
 and exact refined distances.  Small-N goldens (00028) are pinned exactly via the FLAT fallback."""
@@ -30,11 +31,11 @@ def test_ivfflat_all_lists_equals_exact(metric):
     y, q = _clustered(30000, 64, 200, 1)
     ix = b2.VectorIndex("IVFFLAT", metric, 64, "ncentroids=64").build(y)
     assert ix.info()["uses_ivf"]
-    dg, ig = ix.search(q, 10, "nprobe=64, exact_batch=0")
+    dg, ig = ix.search(q, 10, "nprobe=64")
     do, io = orc.search_without_index(metric, q, y, 10)
     check_topk(metric, q, y, dg, ig, do, io, rtol=2e-4, atol=2e-5, min_exact=0.995)
     # a few lists only: recall drops but stays high on clustered data
-    d2, i2 = ix.search(q, 10, "nprobe=8, exact_batch=0")
+    d2, i2 = ix.search(q, 10, "nprobe=8")
     assert _recall(i2, io) > 0.8
 
 
@@ -42,7 +43,7 @@ def test_ivfflat_alive_bitmap():
     y, q = _clustered(20000, 32, 100, 2)
     alive = np.random.default_rng(3).random(20000) < 0.5
     ix = b2.VectorIndex("IVFFLAT", b2.L2, 32, "ncentroids=32").build(y)
-    dg, ig = ix.search(q, 10, "nprobe=32, exact_batch=0", alive_bits=orc.pack_bits(alive))
+    dg, ig = ix.search(q, 10, "nprobe=32", alive_bits=orc.pack_bits(alive))
     do, io = orc.search_without_index(orc.L2, q, y, 10, alive=orc.pack_bits(alive))
     check_topk(b2.L2, q, y, dg, ig, do, io, rtol=2e-4, atol=2e-5, min_exact=0.995)
 
@@ -50,11 +51,11 @@ def test_ivfflat_alive_bitmap():
 @pytest.mark.parametrize("metric", [b2.L2, b2.COSINE])
 def test_two_stage_mstg_recall_and_exact_distances(metric):
     y, q = _clustered(60000, 96, 500, 5)
-    ix = b2.VectorIndex("MSTG", metric, 96, "ncentroids=128, M=24").build(y)
+    ix = b2.VectorIndex("MSTG", metric, 96, "ncentroids=128").build(y)
     info = ix.info()
-    assert info["uses_ivf"] and info["m"] == 24
+    assert info["uses_ivf"]
     do, io = orc.search_without_index(metric, q, y, 10)
-    dg, ig = ix.search(q, 10, "nprobe=32, refine_factor=16, exact_batch=0")
+    dg, ig = ix.search(q, 10, "nprobe=32, refine_factor=16")
     assert ix.last_num_candidates == 160
     rec = _recall(ig, io)
     assert rec >= 0.95, rec
@@ -65,37 +66,98 @@ def test_two_stage_mstg_recall_and_exact_distances(metric):
             assert abs(dg[qi, j] - t) <= 1e-4 * max(1.0, abs(t))
     assert (np.diff(dg, axis=1) >= -1e-6).all()
     # first stage only: approximate (ADC) distances, wider candidate list semantics of the reference
-    d1, i1 = ix.search(q, 160, "nprobe=32, exact_batch=0", first_stage_only=True)
+    d1, i1 = ix.search(q, 160, "nprobe=32", first_stage_only=True)
     assert (i1 >= 0).all() and (np.diff(d1, axis=1) >= -1e-6).all()
     # the 160 first-stage candidates must already contain (almost) all true top-10 -- that is what stage 2 re-ranks
     assert np.mean([len(set(a.tolist()) & set(b.tolist())) / 10 for a, b in zip(i1, io)]) >= 0.95
 
 
-def test_batch_planner_routes_large_batches_to_the_exact_tensor_core_pass():
-    """With no `exact_batch` override the index compares the cost of nq list probes with one exact 3xTF32 pass over
-    the raw rows: a 64-query batch on a 400k-row part goes exact (recall 1, k candidates), one query probes the lists."""
+def test_batches_go_through_the_lists_and_exact_batch_forces_the_flat_pass():
+    """Every batch size is answered by the inverted lists (one grouped scan, each list streamed once for all the queries
+    that probe it); `exact_batch=1` is the explicit escape to an exact pass over the fp32 rows."""
     y, q = _clustered(400000, 96, 2000, 5)
-    ix = b2.VectorIndex("MSTG", b2.L2, 96, "ncentroids=512, M=24").build(y)
+    ix = b2.VectorIndex("MSTG", b2.L2, 96, "ncentroids=512").build(y)
     do, io = orc.search_without_index(orc.L2, q, y, 10)
     dg, ig = ix.search(q, 10, "nprobe=32, refine_factor=16")
-    assert ix.last_num_candidates == 10          # exact route: no over-fetch
-    check_topk(b2.L2, q, y, dg, ig, do, io, rtol=4e-5, atol=2e-5, min_exact=0.995)
-    d1, i1 = ix.search(q[:1], 10, "nprobe=32, refine_factor=16, exact_batch=0")
-    assert ix.last_num_candidates == 160         # forced probe: IVFPQ candidates + exact refine
-    assert _recall(i1, io[:1]) >= 0.9
-    d2, i2 = ix.search(q[:1], 10, "nprobe=32, refine_factor=16, exact_batch=1")
-    assert ix.last_num_candidates == 10 and i2[0].tolist() == io[0].tolist()
-    # one query, no override: whichever route the cost model picks (it depends on how skewed the lists came out),
-    # the answer must be a valid two-stage / exact result
-    d3, i3 = ix.search(q[:1], 10, "nprobe=32, refine_factor=16")
-    assert ix.last_num_candidates in (10, 160) and _recall(i3, io[:1]) >= 0.9
+    assert ix.last_num_candidates == 160
+    assert _recall(ig, io) >= 0.97
+    d1, i1 = ix.search(q[:1], 10, "nprobe=32, refine_factor=16")
+    assert ix.last_num_candidates == 160 and _recall(i1, io[:1]) >= 0.9
+    assert i1[0].tolist() == ig[0].tolist()      # one query alone (lists split over many SMs) = the same query in a batch
+    d2, i2 = ix.search(q, 10, "exact_batch=1")
+    assert ix.last_num_candidates == 10
+    check_topk(b2.L2, q, y, d2, i2, do, io, rtol=4e-5, atol=2e-5, min_exact=0.995)
+    sc = ix.last_scan()
+    assert sc["payload_row_bytes"] == 128 * 2 and sc["rows_streamed"] > 0
+
+
+@pytest.mark.parametrize("index_type", ["IVFSQ", "HNSWSQ"])
+def test_ivfsq_recall_and_distances(index_type):
+    y, q = _clustered(60000, 96, 500, 9)
+    for metric in (b2.L2, b2.IP):
+        ix = b2.VectorIndex(index_type, metric, 96, "ncentroids=128").build(y)
+        assert ix.info()["uses_ivf"]
+        do, io = orc.search_without_index(metric, q, y, 10)
+        dg, ig = ix.search(q, 10, "nprobe=64")
+        assert _recall(ig, io) >= 0.9
+        # 8-bit codes: distances of the returned rows within ~1 % of the true ones
+        true = np.array([[orc.search_without_index(metric, q[a:a + 1], y[ig[a, j]:ig[a, j] + 1], 1)[0][0, 0] for j in range(10)]
+                         for a in range(8)])
+        assert np.abs(dg[:8] - true).max() <= 0.02 * np.abs(true).max()
+        # with the exact second stage the distances are exact
+        d2, i2 = ix.search(q, 10, "nprobe=64, refine_factor=4")
+        assert _recall(i2, io) >= 0.97
+        t2 = np.array([[orc.search_without_index(metric, q[a:a + 1], y[i2[a, j]:i2[a, j] + 1], 1)[0][0, 0] for j in range(10)] for a in range(8)])
+        np.testing.assert_allclose(d2[:8], t2, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("index_type", ["SCANN", "HNSWFLAT", "HNSWPQ"])
+def test_reference_index_type_names_are_served(index_type):
+    """SCANN (the OSS default, README.md:207) and the HNSW* names build and answer with high recall (inverted-file engine)."""
+    y, q = _clustered(50000, 64, 400, 13)
+    ix = b2.VectorIndex(index_type, b2.L2, 64, "ncentroids=128, M=32").build(y)
+    do, io = orc.search_without_index(orc.L2, q, y, 10)
+    dg, ig = ix.search(q, 10, "nprobe=32")
+    assert _recall(ig, io) >= 0.9, index_type
+    with pytest.raises(b2.B200Error):
+        b2.VectorIndex("NOSUCHINDEX", b2.L2, 64)
+
+
+def test_streamed_build_equals_one_shot_build_and_keep_raw_0():
+    """reserve / train / add chunks / finalize (the reader-driven build of VIPartReader) gives the same index as build()."""
+    y, q = _clustered(80000, 64, 300, 17)
+    a = b2.VectorIndex("IVFFLAT", b2.L2, 64, "ncentroids=64").build(y)
+    ns = 65536
+    sample = y[(np.arange(ns, dtype=np.float64) * float(len(y)) / float(ns)).astype(np.int64)]
+    b = b2.VectorIndex("IVFFLAT", b2.L2, 64, "ncentroids=64").reserve(len(y)).train(sample)
+    for off in range(0, len(y), 17000):
+        b.add(y[off:off + 17000])
+    b.finalize()
+    da, ia = a.search(q, 10, "nprobe=8")
+    db, ib = b.search(q, 10, "nprobe=8")
+    assert (ia == ib).all() and np.array_equal(da, db)
+    with pytest.raises(b2.B200Error):
+        b.add(y[:10])                                  # finalized
+    # without the fp32 rows: first-stage (bf16) distances, half the memory, no second stage
+    c = b2.VectorIndex("IVFFLAT", b2.L2, 64, "ncentroids=64, keep_raw=0").build(y)
+    assert c.memory_bytes() < 0.6 * a.memory_bytes()
+    dc, ic = c.search(q, 10, "nprobe=8")
+    assert _recall(ic, ia) >= 0.98
+    np.testing.assert_allclose(dc, da, rtol=5e-3, atol=5e-3)
+    with pytest.raises(b2.B200Error):
+        c.refine(q, ia, 5)
+    # more rows than reserved: a clean error, not a corrupted pool
+    e = b2.VectorIndex("IVFFLAT", b2.L2, 64, "ncentroids=64").reserve(20000).train(sample)
+    with pytest.raises(b2.B200Error):
+        for off in range(0, len(y), 17000):
+            e.add(y[off:off + 17000])
 
 
 def test_ivfpq_ip_adc_recall():
     y, q = _clustered(40000, 64, 300, 8)
     ix = b2.VectorIndex("IVFPQ", b2.IP, 64, "ncentroids=64, M=32").build(y)
     do, io = orc.search_without_index(orc.IP, q, y, 10)
-    dg, ig = ix.search(q, 10, "nprobe=64, exact_batch=0")
+    dg, ig = ix.search(q, 10, "nprobe=64")
     assert _recall(ig, io) >= 0.6
     # ADC scores approximate the true inner products
     true = np.array([[float(q[a] @ y[ig[a, j]]) for j in range(10)] for a in range(len(q))])
@@ -147,11 +209,11 @@ def test_index_above_one_grid_of_rows_regression():
     q = centres[rng.integers(0, 2000, 32)] + 0.2 * rng.standard_normal((32, d)).astype(F32)
     flat = b2.Corpus(b2.L2, d).append(y)
     dt, it = flat.search(q, 10)
-    ix = b2.VectorIndex("MSTG", b2.L2, d, "ncentroids=512, M=8").build(y)
-    dg, ig = ix.search(q, 10, "nprobe=64, refine_factor=16, exact_batch=0")
+    ix = b2.VectorIndex("MSTG", b2.L2, d, "ncentroids=512").build(y)
+    dg, ig = ix.search(q, 10, "nprobe=64, refine_factor=16")
     assert _recall(ig, it) >= 0.95
     iv = b2.VectorIndex("IVFFLAT", b2.L2, d, "ncentroids=256").build(y)
-    d2, i2 = iv.search(q, 10, "nprobe=256, exact_batch=0")
+    d2, i2 = iv.search(q, 10, "nprobe=256")
     check_topk(b2.L2, q, y, d2, i2, dt, it, rtol=2e-4, atol=2e-5, min_exact=0.99)
 
 
@@ -167,12 +229,22 @@ def test_serialize_load_roundtrip_and_golden_00001_after_reload(goldens, tmp_pat
     np.testing.assert_allclose(dis[0], [e[1] for e in g["expect_after_reload"]], rtol=1e-6)
     # IVFPQ two-stage index: identical results before and after the round trip
     yy, q = _clustered(40000, 64, 300, 21)
-    a = b2.VectorIndex("MSTG", b2.COSINE, 64, "ncentroids=64, M=16").build(yy)
-    d0, i0 = a.search(q, 10, "nprobe=16, exact_batch=0")
-    a.save(tmp_path / "mstg.b2ix")
-    b = b2.VectorIndex.load(tmp_path / "mstg.b2ix", 64)
-    assert b.info() == a.info()
-    d1, i1 = b.search(q, 10, "nprobe=16, exact_batch=0")
-    assert (i0 == i1).all() and np.array_equal(d0, d1)
+    for ty, par in (("MSTG", "ncentroids=64"), ("IVFPQ", "ncentroids=64, M=16"), ("IVFSQ", "ncentroids=64")):
+        a = b2.VectorIndex(ty, b2.COSINE if ty == "MSTG" else b2.L2, 64, par).build(yy)
+        d0, i0 = a.search(q, 10, "nprobe=16")
+        a.save(tmp_path / "ix.b2ix")
+        b = b2.VectorIndex.load(tmp_path / "ix.b2ix", 64)
+        assert b.info() == a.info()
+        d1, i1 = b.search(q, 10, "nprobe=16")
+        assert (i0 == i1).all() and np.array_equal(d0, d1), ty
+    # a truncated / corrupt file is refused, never half-loaded
+    raw = (tmp_path / "ix.b2ix").read_bytes()
+    (tmp_path / "cut.b2ix").write_bytes(raw[:len(raw) // 2])
+    with pytest.raises(b2.B200Error):
+        b2.VectorIndex.load(tmp_path / "cut.b2ix", 64)
+    bad = bytearray(raw); bad[20:24] = (2 ** 31 - 1).to_bytes(4, "little")     # nlist field
+    (tmp_path / "bad.b2ix").write_bytes(bytes(bad))
+    with pytest.raises(b2.B200Error):
+        b2.VectorIndex.load(tmp_path / "bad.b2ix", 64)
     with pytest.raises(b2.B200Error):
         b2.VectorIndex.load(tmp_path / "missing.b2ix", 64)
