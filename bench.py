@@ -40,7 +40,7 @@ CHUNK = 250_000
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=10_000_000)
@@ -57,7 +57,8 @@ def config_of(a, n):
     return {"workload": f"FLAT brute-force IP, {a.rows} x {a.dim}-d bf16, batch {a.nq} queries, top-{a.k} "
                         + ("(BASELINE.json configs[1])" if (a.rows, a.dim, a.nq, a.k) == (10_000_000, 768, 1024, 10) else "(non-default size)"),
             "rows": a.rows, "dim": a.dim, "batch_queries": a.nq, "k": a.k,
-            "sharding": f"rows/{n} per GPU, NCCL all-gather of per-shard top-k + merge kernel" if n > 1 else "single GPU",
+            "sharding": (f"rows/{n} per GPU; b200_sharded_corpus_search(): tensor-core scan -> one ncclAllGather of the packed per-shard "
+                         "top-k -> merge kernel, replayed as one CUDA graph per step") if n > 1 else "single GPU",
             "cache": f"inputs ({a.rows * a.dim * 2 / n / 1e9:.1f} GB of corpus rows per GPU) larger than the 126 MB L2; no flush needed"}
 
 
@@ -345,7 +346,10 @@ def main():
 
     index = b2.Corpus(b2.IP, a.dim, dtype=S.BF16)
     index.adopt_device(corpus.data_ptr(), shard_rows)
-    index.enable_timing(True)
+    # per-launch CUDA events for the roofline at N = 1 (the step is one 12 ms kernel); at N > 1 the step runs as one CUDA
+    # graph and the kernel is timed in a separate short loop after the timed region
+    index_timing = [N == 1]
+    index.enable_timing(index_timing[0])
 
     k, nq = a.k, a.nq
     # one packed record per rank {float dis[nq*k]; int64 ids[nq*k]} -> a single NCCL all-gather
@@ -359,35 +363,68 @@ def main():
     h_dis = torch.empty((nq, k), dtype=torch.float32).pin_memory()
     h_ids = torch.empty((nq, k), dtype=torch.int64).pin_memory()
 
+    # N > 1: the communicator below the C ABI (csrc/comm.cu): shard scan -> ONE ncclAllGather of the packed per-shard
+    # top-k -> merge kernel, the whole step replayed as one CUDA graph; Python only carried the 128-byte NCCL id
+    comm = None
+    if N > 1:
+        from myscaledb_b200.sharding import Comm
+        comm = Comm.from_torch_distributed(dev)
+    side = torch.cuda.Stream(device=dev)   # the sharded steps want a real (non-default) stream
+
     def step_device():
-        s = torch.cuda.current_stream().cuda_stream
-        index.search_device(q_dev.data_ptr(), nq, k, o_dis.data_ptr(), o_ids.data_ptr(), id_offset=row0, stream=s)
-        if N > 1:
-            dist.all_gather_into_tensor(gathered, packed)
-            S.topk_merge_device_strided(gathered.data_ptr(), gathered.data_ptr() + nq * k * 4, N, rec // 4, rec // 8, nq, k,
-                                        True, f_dis.data_ptr(), f_ids.data_ptr(), stream=s)
+        if N == 1:
+            index.search_device(q_dev.data_ptr(), nq, k, o_dis.data_ptr(), o_ids.data_ptr(), id_offset=row0,
+                                stream=torch.cuda.current_stream().cuda_stream)
+        else:
+            comm.sharded_corpus_search(index, q_dev.data_ptr(), nq, k, f_dis.data_ptr(), f_ids.data_ptr(), row0,
+                                       torch.cuda.current_stream().cuda_stream, use_graph=not index_timing[0])
+
+    q_np, hd_np, hi_np = q_host.numpy(), h_dis.numpy(), h_ids.numpy()
 
     def step_e2e():
+        # the reference-facing C-ABI call with host buffers: H2D of the queries, kernels (+ all-gather + merge), D2H of the
+        # results and the synchronise are all inside the call
         if N == 1:
-            # the reference-facing C-ABI call with host buffers (H2D + kernels + D2H inside)
-            d, i = index.search(q_host.numpy(), k)
-            return d, i
-        s = torch.cuda.current_stream().cuda_stream
-        q_dev.copy_(q_host, non_blocking=True)
-        step_device()
-        h_dis.copy_(f_dis, non_blocking=True)
-        h_ids.copy_(f_ids, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return h_dis.numpy(), h_ids.numpy()
+            return index.search(q_np, k)
+        return comm.sharded_corpus_search_host(index, q_np, k, row0, torch.cuda.current_stream().cuda_stream, use_graph=True,
+                                               out=(hd_np, hi_np))
 
     def barrier():
         if N > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- the memory-bound FLAT scan on the same resident shard (BASELINE metric: "brute-force GB/s vs HBM peak"),
+    #      measured FIRST, on a cool GPU: after the power-capped GEMM loop the same kernel reads 15-20 % slower
+    flat_scan = []
+    if (rank == 0 or N > 1) and not a.headline_only:
+        try:  # an extra as well: a failure here must not cost the headline line
+            index.enable_timing(True)
+            for nq_s in (1, 8):
+                index.set_path(1)
+                for _ in range(3):
+                    index.search_device(q_dev.data_ptr(), nq_s, k, o_dis.data_ptr(), o_ids.data_ptr(), id_offset=row0,
+                                        stream=torch.cuda.current_stream().cuda_stream)
+                torch.cuda.synchronize()
+                index.kernel_time(reset=True)
+                reps = 10
+                for _ in range(reps):
+                    index.search_device(q_dev.data_ptr(), nq_s, k, o_dis.data_ptr(), o_ids.data_ptr(), id_offset=row0,
+                                        stream=torch.cuda.current_stream().cuda_stream)
+                torch.cuda.synchronize()
+                kms, kn = index.kernel_time(reset=True)
+                gbs = shard_rows * a.dim * 2 / (kms / max(kn, 1) * 1e-3) / 1e9
+                flat_scan.append({"kernel": "flat_scan_kernel (bf16 rows, fp32 FMA)", "queries_per_pass": nq_s,
+                                  "ms_per_launch": kms / max(kn, 1), "GB_per_s": gbs, "bytes_per_launch": shard_rows * a.dim * 2})
+        except Exception as e:
+            flat_scan = [{"error": f"{type(e).__name__}: {e}"[:300]}]
+        index.set_path(0)
+        index.enable_timing(index_timing[0])
+
     # ---- device-resident timing (value) ----
     sampler = ClockSampler(local)
     sampler.launch()
+    torch.cuda.set_stream(side)
     for _ in range(max(a.warmup, 3)):
         step_device()
     barrier()
@@ -405,6 +442,15 @@ def main():
     launches = S.launch_count()
     kern_ms, kern_n = index.kernel_time(reset=True)
     clocks = sampler.stop()
+    if N > 1:  # kernel time for the roofline: a few eager steps with per-launch events, outside the timed region
+        index_timing[0] = True
+        index.enable_timing(True)
+        for _ in range(5):
+            step_device()
+        torch.cuda.synchronize()
+        kern_ms, kern_n = index.kernel_time(reset=True)
+        index.enable_timing(False)
+        index_timing[0] = False
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if N > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -423,31 +469,6 @@ def main():
     if N > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_qps = nq / (float(te.item()) / a.steps)
-
-    # ---- the memory-bound FLAT scan on the same resident shard (BASELINE metric: "brute-force GB/s vs HBM peak")
-    flat_scan = []
-    if (rank == 0 or N > 1) and not a.headline_only:
-        try:  # an extra as well: a failure here must not cost the headline line
-            for nq_s in (1, 8):
-                index.set_path(1)
-                for _ in range(3):
-                    index.search_device(q_dev.data_ptr(), nq_s, k, o_dis.data_ptr(), o_ids.data_ptr(), id_offset=row0,
-                                        stream=torch.cuda.current_stream().cuda_stream)
-                torch.cuda.synchronize()
-                index.kernel_time(reset=True)
-                reps = 10
-                for _ in range(reps):
-                    index.search_device(q_dev.data_ptr(), nq_s, k, o_dis.data_ptr(), o_ids.data_ptr(), id_offset=row0,
-                                        stream=torch.cuda.current_stream().cuda_stream)
-                torch.cuda.synchronize()
-                kms, kn = index.kernel_time(reset=True)
-                gbs = shard_rows * a.dim * 2 / (kms / max(kn, 1) * 1e-3) / 1e9
-                flat_scan.append({"kernel": "flat_scan_kernel (bf16 rows, fp32 FMA)", "queries_per_pass": nq_s,
-                                  "ms_per_launch": kms / max(kn, 1), "GB_per_s": gbs, "bytes_per_launch": shard_rows * a.dim * 2})
-            index.set_path(0)
-        except Exception as e:
-            flat_scan = [{"error": f"{type(e).__name__}: {e}"[:300]}]
-            index.set_path(0)
 
     # ---- fp32 rows (the reference's native column type) on the tensor cores: 3xTF32 split GEMM, same batch, a
     #      2M-row fp32 copy of the shard's head (an extra, not the headline)

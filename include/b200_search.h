@@ -209,6 +209,7 @@ int b200_index_search_device(b200_index *ix, const float *d_queries, int64_t nq,
                              void *stream);
 /* roofline inputs of the list scan: CUDA-event time of the grouped scan kernel since the last reset, bytes per list row,
  * and an upper bound of the work items of the last search */
+int b200_index_list_sizes(const b200_index *ix, uint32_t *out_sizes /*[nlist]*/, int capacity);
 int b200_index_enable_timing(b200_index *ix, int on);
 int b200_index_last_scan(b200_index *ix, int64_t *rows_streamed, int64_t *payload_row_bytes, int64_t *work_items,
                          double *kernel_ms_total, int64_t *kernel_launches, int reset);
@@ -219,7 +220,44 @@ int b200_index_refine(b200_index *ix, const float *queries, int64_t nq, const in
  * ("B2IX" v2; the closed library's .vidx3 payload cannot be reproduced).  load validates every size it derives. */
 int b200_index_save(b200_index *ix, const char *path);
 int b200_index_load(const char *path, b200_index **out);
+/* the same through the host's own streams (Search::IndexDataFileWriter / Reader over ClickHouse disks,
+ * VectorIndex/Common/VectorIndexIO.h:33-164): the callbacks return 0 when every byte was written / read */
+int b200_index_save_cb(b200_index *ix, int (*write)(void *ctx, const void *data, size_t bytes), void *ctx);
+int b200_index_load_cb(int (*read)(void *ctx, void *data, size_t bytes), void *ctx, b200_index **out);
 int b200_index_free(b200_index *ix);
+
+/* ------------------------------------------------------------------------------------
+ * Multi-GPU: parts / row ranges shard over the GPUs of one box, one communicator rank per GPU (one process per GPU, or
+ * one host thread per device).  The reference merges per-part top-k lists on the host
+ * (MergeTreeBaseSearchManager::getTotalTopSearchResultImpl, VectorIndex/Storages/MergeTreeBaseSearchManager.cpp:207-299)
+ * and sums BM25 statistics over parts (ReadWithHybridSearch::getStatisticForTextSearch,
+ * VectorIndex/Processors/ReadWithHybridSearch.cpp:89-209); across GPUs these are ONE ncclAllGather of the packed
+ * per-shard top-k + the merge kernel, and ONE ncclAllReduce(sum) of a few counters.  NCCL is resolved with dlopen
+ * (nccl_lib_path, $B200_NCCL_LIB, or the libnccl.so.2 already in the process); rank 0 creates the 128-byte unique id and
+ * the host distributes it (any side channel: MPI, a file, torch.distributed.broadcast).
+ * ---------------------------------------------------------------------------------- */
+typedef struct b200_comm b200_comm;
+int b200_comm_unique_id(const char *nccl_lib_path /*nullable*/, void *out_id_128_bytes);
+int b200_comm_create(const char *nccl_lib_path /*nullable*/, const void *unique_id_128_bytes, int rank, int world, b200_comm **out);
+int b200_comm_info(const b200_comm *c, int *rank, int *world);
+int b200_comm_free(b200_comm *c);
+/* building blocks: device buffers a shard search writes its [nq][k] result to, then all-gather + merge on `stream` */
+int b200_comm_local_buffers(b200_comm *c, int64_t nq, int k, float **d_dis, int64_t **d_ids);
+int b200_comm_gather_merge(b200_comm *c, int64_t nq, int k, int descending, float *d_out_dis, int64_t *d_out_ids, void *stream);
+/* in-place sum over the ranks of n host-resident uint64 counters (total_docs, total_tokens[field], doc_freq[...]) */
+int b200_comm_allreduce_sum_u64(b200_comm *c, uint64_t *host_counters, int64_t n);
+/* whole steps.  Every rank passes its own shard and the same queries; every rank receives the global top-k.
+ * id_offset = first global row id of this rank's shard.  `stream` must be a real stream.  use_graph != 0 replays the step
+ * (query conversion, tensor-core scan, all-gather, merge) as ONE CUDA graph from the second call with the same arguments. */
+int b200_sharded_corpus_search(b200_comm *cm, b200_corpus *corpus, const float *d_queries, int64_t nq, int k,
+                               const uint8_t *d_alive_bits /*nullable*/, int64_t id_offset, float *d_out_dis, int64_t *d_out_ids,
+                               void *stream, int use_graph);
+/* host queries in, host results out (H2D, scan, all-gather, merge, D2H, synchronise inside) */
+int b200_sharded_corpus_search_host(b200_comm *cm, b200_corpus *corpus, const float *queries, int64_t nq, int d, int k,
+                                    int64_t id_offset, float *out_dis, int64_t *out_ids, void *stream, int use_graph);
+int b200_sharded_index_search(b200_comm *cm, b200_index *ix, int metric, const float *d_queries, int64_t nq, int k, const char *params,
+                              const uint8_t *d_alive_bits /*nullable*/, int64_t id_offset, float *d_out_dis, int64_t *d_out_ids,
+                              void *stream);
 
 /* ------------------------------------------------------------------------------------
  * HBM residency cache: the device-side VICacheManager (VectorIndex/Cache/VICacheManager.cpp:65-157, an
@@ -241,7 +279,10 @@ int b200_cache_get(const char *key, void **handle, int *kind);
  * it does not fit even after evicting every unpinned entry (ownership stays with the caller). */
 int b200_cache_put(const char *key, int kind, void *handle, uint64_t bytes, void **resident);
 int b200_cache_put_opaque(const char *key, void *handle, uint64_t bytes, void (*deleter)(void *), void **resident);
-/* drop one pin taken by get / put */
+/* drop one pin taken by get / put.  Pass the handle that get / put returned: if the key was expired while pinned and put
+ * again (index rebuilt under the same CacheKey), two generations exist, and only the handle tells whose pin this is.
+ * b200_cache_release(key) without a handle releases the live entry first and is only safe without such re-puts. */
+int b200_cache_release_handle(const char *key, const void *handle);
 int b200_cache_release(const char *key);
 /* VICacheManager::forceExpire -> tryRemove: freed now, or at the last release if pinned */
 int b200_cache_expire(const char *key);

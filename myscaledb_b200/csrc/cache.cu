@@ -140,7 +140,11 @@ extern "C" int b200_cache_put_opaque(const char *key, void *handle, uint64_t byt
     return put_impl(key, B200_CACHE_OPAQUE, handle, bytes, deleter, resident);
 }
 
-extern "C" int b200_cache_release(const char *key) {
+// One pin is dropped from the entry that holds `handle` under `key`: the live entry if it is that generation, else the
+// expired-but-still-pinned one.  handle == nullptr keeps the round-1 behaviour (live entry first) for callers that never
+// re-put a key while an older generation is still held.  The reference's LRUResourceCache hands out shared_ptr holders,
+// so a release can never hit another generation there; matching on the handle gives the same guarantee here.
+static int release_impl(const char *key, const void *handle) {
     if (!key) return fail(B200_ERR_INVALID, "b200_cache_release: bad arguments");
     std::list<Entry> doomed;
     int rc = B200_OK;
@@ -148,12 +152,12 @@ extern "C" int b200_cache_release(const char *key) {
         Cache &c = cache();
         std::lock_guard<std::mutex> lk(c.mu);
         auto f = c.map.find(key);
-        if (f != c.map.end() && f->second->pins > 0) {
+        if (f != c.map.end() && f->second->pins > 0 && (!handle || f->second->handle == handle)) {
             f->second->pins--;
         } else {
             // an expired entry keeps its pins in the zombie list (oldest first)
             auto z = c.zombies.begin();
-            while (z != c.zombies.end() && z->key != key) ++z;
+            while (z != c.zombies.end() && !(z->key == key && (!handle || z->handle == handle))) ++z;
             if (z == c.zombies.end()) {
                 rc = fail(B200_ERR_INVALID, std::string("cache release without a pin: ") + key);
             } else if (--z->pins == 0) {
@@ -164,6 +168,13 @@ extern "C" int b200_cache_release(const char *key) {
     }
     for (auto &e : doomed) destroy(e);
     return rc;
+}
+
+extern "C" int b200_cache_release(const char *key) { return release_impl(key, nullptr); }
+
+extern "C" int b200_cache_release_handle(const char *key, const void *handle) {
+    if (!handle) return fail(B200_ERR_INVALID, "b200_cache_release_handle: null handle");
+    return release_impl(key, handle);
 }
 
 static void expire_locked(Cache &c, std::list<Entry>::iterator it, std::list<Entry> &doomed) {

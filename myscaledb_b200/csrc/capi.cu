@@ -146,6 +146,9 @@ static int corpus_alloc(b200_corpus *c, int64_t rows);
 static int corpus_norms(b200_corpus *c, int64_t first, int64_t n);
 
 namespace b200 {
+// hooks for comm.cu
+int corpus_metric(const b200_corpus *c) { return c->metric; }
+bool corpus_timing_enabled(const b200_corpus *c) { return c->timing; }
 // hooks for the index layer (ivf.cu): device view of the rows / in-place row normalisation
 const void *corpus_device_rows(const b200_corpus *c) { return c->data; }
 // append fp32 rows [n][d] that already live on the device (index build, centroid tables); asynchronous on s except for

@@ -28,9 +28,12 @@ struct Stager {
     char *pinned = nullptr;
     cudaEvent_t ev[kSlots] = {};
     bool tried = false;
-    bool init() {
+    // events belong to the device that is current when they are created: one stager per device, created with that
+    // device current (round 1 kept one process-wide event set and failed on the second GPU of a multi-device process)
+    bool init(int device) {
         if (tried) return pinned != nullptr;
         tried = true;
+        if (cudaSetDevice(device) != cudaSuccess) return false;
         if (cudaHostAlloc(reinterpret_cast<void **>(&pinned), kChunk * kSlots, cudaHostAllocDefault) != cudaSuccess) {
             cudaGetLastError();
             pinned = nullptr;
@@ -40,7 +43,8 @@ struct Stager {
         return true;
     }
 };
-Stager g_stager;
+constexpr int kMaxDevices = 64;
+Stager g_stagers[kMaxDevices];
 
 int stager_threads() {
     if (const char *ev = getenv("B200_INGEST_THREADS")) return std::max(0, atoi(ev));
@@ -59,8 +63,13 @@ int staged_h2d(void *dst, const void *src, size_t bytes, int device, cudaStream_
         B200_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
         return B200_OK;
     }
+    if (device < 0 || device >= kMaxDevices) {
+        B200_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+        return B200_OK;
+    }
+    Stager &g_stager = g_stagers[device];
     std::lock_guard<std::mutex> lk(g_stager.mu);
-    if (!g_stager.init()) {
+    if (!g_stager.init(device)) {
         B200_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
         return B200_OK;
     }

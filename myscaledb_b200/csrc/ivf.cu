@@ -1392,6 +1392,15 @@ extern "C" int b200_index_last_scan(b200_index *ix, int64_t *rows_streamed, int6
     return B200_OK;
 }
 
+// rows per inverted list (diagnostics: balance of the coarse quantiser); out_sizes[nlist]
+extern "C" int b200_index_list_sizes(const b200_index *ix, uint32_t *out_sizes, int capacity) {
+    if (!ix || !out_sizes) return fail(B200_ERR_INVALID, "bad arguments");
+    if (!ix->built || !ix->use_ivf) return fail(B200_ERR_INVALID, "no inverted lists (FLAT index or not finalized)");
+    if (capacity < ix->nlist) return fail(B200_ERR_INVALID, "buffer too small");
+    memcpy(out_sizes, ix->list_len.data(), (size_t)ix->nlist * 4);
+    return B200_OK;
+}
+
 extern "C" int b200_index_enable_timing(b200_index *ix, int on) {
     if (!ix) return fail(B200_ERR_INVALID, "null index");
     std::lock_guard<std::mutex> lk(ix->mu);
@@ -1748,17 +1757,23 @@ struct IxHeader {
     int64_t n;
     uint32_t pages_used, reserved0;
 };
-bool wr(FILE *f, const void *p, size_t bytes) { return bytes == 0 || fwrite(p, 1, bytes, f) == bytes; }
-bool rd(FILE *f, void *p, size_t bytes) { return bytes == 0 || fread(p, 1, bytes, f) == bytes; }
+// the byte stream is the caller's: a FILE (b200_index_save / _load) or the host's own stream objects
+// (b200_index_save_cb / _load_cb: Search::IndexDataFileWriter / Reader over ClickHouse disks, VectorIndexIO.h:33-164)
+struct Io {
+    int (*write)(void *, const void *, size_t) = nullptr;
+    int (*read)(void *, void *, size_t) = nullptr;
+    void *ctx = nullptr;
+};
+bool wr(Io *f, const void *p, size_t bytes) { return bytes == 0 || (f->write && f->write(f->ctx, p, bytes) == 0); }
+bool rd(Io *f, void *p, size_t bytes) { return bytes == 0 || (f->read && f->read(f->ctx, p, bytes) == 0); }
+int file_write(void *ctx, const void *p, size_t bytes) { return fwrite(p, 1, bytes, reinterpret_cast<FILE *>(ctx)) == bytes ? 0 : 1; }
+int file_read(void *ctx, void *p, size_t bytes) { return fread(p, 1, bytes, reinterpret_cast<FILE *>(ctx)) == bytes ? 0 : 1; }
 }  // namespace
 
-extern "C" int b200_index_save(b200_index *ix, const char *path) {
-    if (!ix || !path) return fail(B200_ERR_INVALID, "bad arguments");
+static int index_save_io(b200_index *ix, Io *f) {
     if (!ix->built) return fail(B200_ERR_INVALID, "index not built");
     std::lock_guard<std::mutex> lk(ix->mu);
     B200_CUDA_OK(cudaSetDevice(ix->device));
-    FILE *f = fopen(path, "wb");
-    if (!f) return fail(B200_ERR_INVALID, std::string("cannot open ") + path);
     IxHeader h{};
     memcpy(h.magic, "B2IX", 4);
     h.version = 2;
@@ -1800,38 +1815,45 @@ extern "C" int b200_index_save(b200_index *ix, const char *path) {
     } catch (const std::bad_alloc &) {
         ok = false;
     }
-    ok = (fclose(f) == 0) && ok;
-    return ok ? B200_OK : fail(B200_ERR_INVALID, std::string("write failed: ") + path);
+    return ok ? B200_OK : fail(B200_ERR_INVALID, "index serialisation: write failed");
 }
 
-extern "C" int b200_index_load(const char *path, b200_index **out) {
-    if (!path || !out) return fail(B200_ERR_INVALID, "bad arguments");
+extern "C" int b200_index_save(b200_index *ix, const char *path) {
+    if (!ix || !path) return fail(B200_ERR_INVALID, "bad arguments");
+    FILE *fp = fopen(path, "wb");
+    if (!fp) return fail(B200_ERR_INVALID, std::string("cannot open ") + path);
+    Io io;
+    io.write = file_write;
+    io.ctx = fp;
+    int rc = index_save_io(ix, &io);
+    if (fclose(fp) != 0 && rc == B200_OK) rc = fail(B200_ERR_INVALID, std::string("write failed: ") + path);
+    return rc;
+}
+
+extern "C" int b200_index_save_cb(b200_index *ix, int (*write)(void *ctx, const void *data, size_t bytes), void *ctx) {
+    if (!ix || !write) return fail(B200_ERR_INVALID, "bad arguments");
+    Io io;
+    io.write = write;
+    io.ctx = ctx;
+    return index_save_io(ix, &io);
+}
+
+static int index_load_io(Io *f, b200_index **out) {
     *out = nullptr;
-    FILE *f = fopen(path, "rb");
-    if (!f) return fail(B200_ERR_INVALID, std::string("cannot open ") + path);
     IxHeader h{};
-    if (!rd(f, &h, sizeof(h)) || memcmp(h.magic, "B2IX", 4) != 0 || h.version != 2) {
-        fclose(f);
+    if (!rd(f, &h, sizeof(h)) || memcmp(h.magic, "B2IX", 4) != 0 || h.version != 2)
         return fail(B200_ERR_INVALID, "not a B2IX v2 index file");
-    }
     // a truncated or corrupt file must fail here, not in a kernel: every size below is derived from these fields
     const bool sane = h.type >= 0 && h.type <= 8 && h.metric >= 0 && h.metric <= 2 && h.d > 0 && h.d <= (1 << 16) && h.n >= 0 &&
                       h.n < (int64_t)0xffffffffll && h.payload >= 0 && h.payload <= 2 &&
                       (!h.use_ivf || (h.nlist > 0 && h.nlist <= (1 << 24) && (uint64_t)h.pages_used <= (uint64_t)h.n / kPageRows + (uint64_t)h.nlist + 1)) &&
                       (h.payload != IVF_PRODUCER_PQ || !h.use_ivf || (h.m > 0 && h.dsub > 0 && h.m * h.dsub == h.d && h.code_bytes >= h.m && h.code_bytes % 16 == 0)) &&
                       (h.payload != IVF_PRODUCER_SQ8 || !h.use_ivf || (h.code_bytes >= h.d && h.code_bytes % 16 == 0)) && (h.has_raw || h.use_ivf);
-    if (!sane) {
-        fclose(f);
-        return fail(B200_ERR_INVALID, "corrupt index header");
-    }
+    if (!sane) return fail(B200_ERR_INVALID, "corrupt index header");
     b200_index *ix = nullptr;
     int rc = b200_index_create(kTypeNames[h.type], h.metric, h.d, "", &ix);
-    if (rc != B200_OK) {
-        fclose(f);
-        return rc;
-    }
+    if (rc != B200_OK) return rc;
     auto bail = [&](const std::string &msg) {
-        fclose(f);
         b200_index_free(ix);
         return fail(B200_ERR_INVALID, msg);
     };
@@ -1921,9 +1943,29 @@ extern "C" int b200_index_load(const char *path, b200_index **out) {
     } catch (const std::bad_alloc &) {
         return bail("out of host memory while loading the index");
     }
-    fclose(f);
     ix->trained = true;
     ix->built = true;
     *out = ix;
     return B200_OK;
+}
+
+extern "C" int b200_index_load(const char *path, b200_index **out) {
+    if (!path || !out) return fail(B200_ERR_INVALID, "bad arguments");
+    *out = nullptr;
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return fail(B200_ERR_INVALID, std::string("cannot open ") + path);
+    Io io;
+    io.read = file_read;
+    io.ctx = fp;
+    const int rc = index_load_io(&io, out);
+    fclose(fp);
+    return rc;
+}
+
+extern "C" int b200_index_load_cb(int (*read)(void *ctx, void *data, size_t bytes), void *ctx, b200_index **out) {
+    if (!read || !out) return fail(B200_ERR_INVALID, "bad arguments");
+    Io io;
+    io.read = read;
+    io.ctx = ctx;
+    return index_load_io(&io, out);
 }

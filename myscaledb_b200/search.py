@@ -377,6 +377,12 @@ class VectorIndex:
                                           C.c_int(1 if reset else 0)))
         return dict(rows_streamed=rows.value, payload_row_bytes=rb.value, work_items=items.value, kernel_ms=ms.value, launches=nl.value)
 
+    def list_sizes(self):
+        nl = self.info()["nlist"]
+        out = np.zeros(nl, np.uint32)
+        _check(lib().b200_index_list_sizes(self._h, _p(out, C.c_uint32), C.c_int(nl)))
+        return out
+
     def memory_bytes(self):
         b = C.c_uint64()
         _check(lib().b200_index_memory_bytes(self._h, C.byref(b)))
@@ -517,8 +523,12 @@ def cache_put_opaque(key: str, handle: int, nbytes: int, deleter):
     return res.value
 
 
-def cache_release(key: str):
-    _check(lib().b200_cache_release(key.encode()))
+def cache_release(key: str, handle: int | None = None):
+    """Drop one pin.  Pass the handle address get / put returned when a key may have been expired and put again."""
+    if handle is None:
+        _check(lib().b200_cache_release(key.encode()))
+    else:
+        _check(lib().b200_cache_release_handle(key.encode(), C.c_void_p(handle)))
 
 
 def cache_expire(key: str):

@@ -8,6 +8,8 @@ is pinned to one GPU; queries are broadcast; the only exchange is one all-gather
 """
 from __future__ import annotations
 
+import ctypes as C
+
 
 def shard_range(total_rows: int, world: int, rank: int, align: int = 1):
     """Row range [start, stop) of `rank`: equal shares rounded to `align`, remainder to the last ranks."""
@@ -71,3 +73,80 @@ def bm25_global_stats(summed, n_fields: int, query_terms, fields):
             stats["doc_freq"][(f, t)] = summed[pos]
             pos += 1
     return stats
+
+
+# ----------------------------------------------------------------------------------------------
+# The communicator below the C ABI (csrc/comm.cu): NCCL all-gather of per-shard top-k + merge kernel, BM25 counter
+# all-reduce, whole sharded steps (optionally one CUDA graph per step).  Python only moves the 128-byte NCCL id around.
+# ----------------------------------------------------------------------------------------------
+class Comm:
+    def __init__(self, rank: int, world: int, unique_id: bytes, nccl_lib_path: str | None = None):
+        from ._lib import lib
+        from .search import _check
+        self._h = C.c_void_p()
+        self.rank, self.world = rank, world
+        _check(lib().b200_comm_create(nccl_lib_path.encode() if nccl_lib_path else None, unique_id, C.c_int(rank), C.c_int(world),
+                                      C.byref(self._h)))
+
+    @staticmethod
+    def unique_id(nccl_lib_path: str | None = None) -> bytes:
+        from ._lib import lib
+        from .search import _check
+        buf = C.create_string_buffer(128)
+        _check(lib().b200_comm_unique_id(nccl_lib_path.encode() if nccl_lib_path else None, buf))
+        return buf.raw
+
+    @classmethod
+    def from_torch_distributed(cls, device):
+        """One communicator rank per torch.distributed rank: rank 0 makes the id, a broadcast carries it."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        t = torch.zeros(128, dtype=torch.uint8, device=device)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(cls.unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        return cls(rank, world, bytes(t.cpu().numpy().tobytes()))
+
+    def sharded_corpus_search(self, corpus, q_ptr: int, nq: int, k: int, out_dis_ptr: int, out_ids_ptr: int, id_offset: int, stream: int,
+                              use_graph: bool = True, alive_ptr: int = 0):
+        from ._lib import lib
+        from .search import _check
+        _check(lib().b200_sharded_corpus_search(self._h, corpus._h, C.c_void_p(q_ptr), C.c_int64(nq), C.c_int(k), C.c_void_p(alive_ptr or None),
+                                                C.c_int64(id_offset), C.c_void_p(out_dis_ptr), C.c_void_p(out_ids_ptr), C.c_void_p(stream),
+                                                C.c_int(1 if use_graph else 0)))
+
+    def sharded_corpus_search_host(self, corpus, queries, k: int, id_offset: int, stream: int, use_graph: bool = True, out=None):
+        import numpy as np
+        from ._lib import lib
+        from .search import _check
+        q = np.ascontiguousarray(queries, np.float32)
+        nq, d = q.shape
+        dis, ids = out if out is not None else (np.empty((nq, k), np.float32), np.empty((nq, k), np.int64))
+        _check(lib().b200_sharded_corpus_search_host(self._h, corpus._h, q.ctypes.data_as(C.c_void_p), C.c_int64(nq), C.c_int(d), C.c_int(k),
+                                                     C.c_int64(id_offset), dis.ctypes.data_as(C.c_void_p), ids.ctypes.data_as(C.c_void_p),
+                                                     C.c_void_p(stream), C.c_int(1 if use_graph else 0)))
+        return dis, ids
+
+    def sharded_index_search(self, index, metric: int, q_ptr: int, nq: int, k: int, params: str, out_dis_ptr: int, out_ids_ptr: int,
+                             id_offset: int, stream: int, alive_ptr: int = 0):
+        from ._lib import lib
+        from .search import _check
+        _check(lib().b200_sharded_index_search(self._h, index._h, C.c_int(metric), C.c_void_p(q_ptr), C.c_int64(nq), C.c_int(k), params.encode(),
+                                               C.c_void_p(alive_ptr or None), C.c_int64(id_offset), C.c_void_p(out_dis_ptr),
+                                               C.c_void_p(out_ids_ptr), C.c_void_p(stream)))
+
+    def allreduce_sum_u64(self, counters):
+        """In-place sum over the ranks (BM25 table-wide statistics); counters: list / array of non-negative ints."""
+        import numpy as np
+        from ._lib import lib
+        from .search import _check
+        a = np.ascontiguousarray(counters, np.uint64).copy()
+        _check(lib().b200_comm_allreduce_sum_u64(self._h, a.ctypes.data_as(C.c_void_p), C.c_int64(a.size)))
+        return a
+
+    def close(self):
+        if self._h:
+            from ._lib import lib
+            lib().b200_comm_free(self._h)
+            self._h = C.c_void_p()

@@ -85,3 +85,33 @@ def test_shrinking_capacity_and_prefix_expiry(tracker):
     assert S.cache_expire_prefix("t/db/tbl/") == 2   # dropped table
     assert sorted(freed) == [20, 21, 22, 23, 24]
     assert S.cache_stats()["used"] == 0
+
+
+@pytest.mark.parametrize("old_first", [True, False])
+def test_release_by_handle_never_unpins_another_generation(tracker, old_first):
+    """key K is expired while pinned (zombie), then K is put again (index rebuilt under the same CacheKey).
+    The old holder's release must drop the OLD generation's pin, in either order -- otherwise the new entry reaches 0 pins
+    while its holder still uses it and make_room frees it under the holder's feet."""
+    freed, cb = tracker
+    assert S.cache_put_opaque("t/K", 11, 600, cb) == 11        # generation 1, pinned by holder A
+    S.cache_expire("t/K")                                       # expired while pinned -> zombie
+    assert freed == []
+    assert S.cache_put_opaque("t/K", 12, 600, cb) == 12        # generation 2, pinned by holder B
+    if old_first:
+        S.cache_release("t/K", handle=11)
+        assert freed == [11]                                    # the zombie goes at its last release
+        # B's entry is still pinned: something that needs the room must NOT evict it
+        with pytest.raises(S.B200Error):
+            S.cache_put_opaque("t/other", 13, 600, cb)
+        assert freed == [11]
+        S.cache_release("t/K", handle=12)
+    else:
+        S.cache_release("t/K", handle=12)                       # B is done first; A still holds generation 1
+        assert freed == []
+        S.cache_put_opaque("t/other", 13, 600, cb)              # evicts the unpinned generation 2
+        assert freed == [12]
+        S.cache_release("t/other")
+        S.cache_release("t/K", handle=11)
+        assert freed == [12, 11]
+    with pytest.raises(S.B200Error):
+        S.cache_release("t/K", handle=11)                       # no pin of that generation left
