@@ -97,7 +97,8 @@ int b200_corpus_create(int metric, int dtype, int d, int64_t capacity_rows, b200
 /* append fp32 (or binary bytes for B200_DTYPE_BIN) rows from host memory; converted to the
  * corpus dtype on device; row norms are computed on device. */
 int b200_corpus_append(b200_corpus *c, const void *rows, int64_t n);
-/* adopt rows that already live in HBM in the corpus dtype, row-major [n][d] with
+/* adopt rows that already live in HBM in the corpus dtype (the rows must be COMPLETE when this is called: the row norms
+ * are computed on the corpus' own stream, which is not ordered after the caller's streams), row-major [n][d] with
  * d % 64 == 0 for bf16 (d % 4 == 0 for f32); the memory stays owned by the caller. */
 int b200_corpus_adopt_device(b200_corpus *c, const void *device_rows, int64_t n);
 int b200_corpus_size(const b200_corpus *c, int64_t *out_rows);
@@ -326,6 +327,10 @@ int b200_bm25_free(b200_bm25 *ix);
 int b200_bm25_add_doc(b200_bm25 *ix, uint64_t row_id);
 int b200_bm25_add_text(b200_bm25 *ix, uint32_t field, const char *text);
 int b200_bm25_commit(b200_bm25 *ix);
+/* ffi_load_index_reader / the index files of a part (TantivyIndexStore.cpp:646-686): one self-describing file ("B2TX" v1;
+ * tantivy's segment files cannot be reproduced without the crate); load validates, uploads to HBM and returns a committed index */
+int b200_bm25_save(b200_bm25 *ix, const char *path);
+int b200_bm25_load(const char *path, b200_bm25 **out);
 int b200_bm25_total_docs(const b200_bm25 *ix, uint64_t *out);
 int b200_bm25_total_tokens(const b200_bm25 *ix, uint32_t field, uint64_t *out);
 int b200_bm25_doc_freq(const b200_bm25 *ix, uint32_t field, const char *term, uint64_t *out);

@@ -23,6 +23,7 @@
 // HBM-bound: sum over clauses of df * (8 B posting + 1 B field norm).
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -60,22 +61,83 @@ static uint8_t fieldnorm_to_id(uint32_t n) {
     return (uint8_t)lo;
 }
 
-// tantivy "default" tokenizer
+// tantivy 0.21 "default" analyzer: SimpleTokenizer (maximal runs of char::is_alphanumeric) -> RemoveLongFilter::limit(40)
+// (a token is kept when it has FEWER than 40 bytes) -> LowerCaser (Unicode).  UTF-8 is decoded; the Unicode classes are
+// carried for the blocks that matter in practice: Latin-1 signs, General Punctuation, currency, arrows / technical / box /
+// dingbat symbols, CJK and full-width punctuation separate tokens; Latin-1, Latin Extended-A, Greek, Cyrillic and
+// full-width capitals are lowercased; any other non-ASCII code point counts as a letter.
+static size_t utf8_decode(const unsigned char *s, size_t n, uint32_t &cp) {
+    if (s[0] < 0x80) { cp = s[0]; return 1; }
+    if ((s[0] & 0xE0) == 0xC0 && n >= 2 && (s[1] & 0xC0) == 0x80) { cp = ((s[0] & 0x1Fu) << 6) | (s[1] & 0x3Fu); return 2; }
+    if ((s[0] & 0xF0) == 0xE0 && n >= 3 && (s[1] & 0xC0) == 0x80 && (s[2] & 0xC0) == 0x80) {
+        cp = ((s[0] & 0x0Fu) << 12) | ((s[1] & 0x3Fu) << 6) | (s[2] & 0x3Fu);
+        return 3;
+    }
+    if ((s[0] & 0xF8) == 0xF0 && n >= 4 && (s[1] & 0xC0) == 0x80 && (s[2] & 0xC0) == 0x80 && (s[3] & 0xC0) == 0x80) {
+        cp = ((s[0] & 0x07u) << 18) | ((s[1] & 0x3Fu) << 12) | ((s[2] & 0x3Fu) << 6) | (s[3] & 0x3Fu);
+        return 4;
+    }
+    cp = 0xFFFD;  // invalid byte: treated as a letter, one byte consumed
+    return 1;
+}
+static void utf8_append(uint32_t cp, std::string &out) {
+    if (cp < 0x80) out.push_back((char)cp);
+    else if (cp < 0x800) { out.push_back((char)(0xC0 | (cp >> 6))); out.push_back((char)(0x80 | (cp & 0x3F))); }
+    else if (cp < 0x10000) { out.push_back((char)(0xE0 | (cp >> 12))); out.push_back((char)(0x80 | ((cp >> 6) & 0x3F))); out.push_back((char)(0x80 | (cp & 0x3F))); }
+    else { out.push_back((char)(0xF0 | (cp >> 18))); out.push_back((char)(0x80 | ((cp >> 12) & 0x3F))); out.push_back((char)(0x80 | ((cp >> 6) & 0x3F))); out.push_back((char)(0x80 | (cp & 0x3F))); }
+}
+static bool cp_is_alnum(uint32_t c) {
+    if (c < 0x80) return (c >= '0' && c <= '9') || (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z');
+    if (c <= 0xBF) return c == 0xAA || c == 0xB2 || c == 0xB3 || c == 0xB5 || c == 0xB9 || c == 0xBA || c == 0xBC || c == 0xBD || c == 0xBE;
+    if (c == 0xD7 || c == 0xF7) return false;
+    if (c >= 0x2000 && c <= 0x206F) return false;
+    if (c >= 0x20A0 && c <= 0x20CF) return false;
+    if (c >= 0x2190 && c <= 0x245F) return false;
+    if (c >= 0x2500 && c <= 0x2BFF) return false;
+    if (c >= 0x2E00 && c <= 0x2E7F) return false;
+    if ((c >= 0x3000 && c <= 0x3004) || (c >= 0x3008 && c <= 0x3020) || c == 0x3030 || (c >= 0x303D && c <= 0x303F)) return false;
+    if ((c >= 0xFE10 && c <= 0xFE1F) || (c >= 0xFE30 && c <= 0xFE6F)) return false;
+    if ((c >= 0xFF00 && c <= 0xFF0F) || (c >= 0xFF1A && c <= 0xFF20) || (c >= 0xFF3B && c <= 0xFF40) || (c >= 0xFF5B && c <= 0xFF65) ||
+        (c >= 0xFFE0 && c <= 0xFFEF))
+        return false;
+    return true;
+}
+static uint32_t cp_lower(uint32_t c) {
+    if (c < 0x80) return (c >= 'A' && c <= 'Z') ? c + 32 : c;
+    if (c >= 0xC0 && c <= 0xDE && c != 0xD7) return c + 0x20;
+    if (c >= 0x100 && c <= 0x137) return (c & 1) ? c : c + 1;
+    if (c >= 0x139 && c <= 0x148) return (c & 1) ? c + 1 : c;
+    if (c >= 0x14A && c <= 0x177) return (c & 1) ? c : c + 1;
+    if (c == 0x178) return 0xFF;
+    if (c >= 0x179 && c <= 0x17E) return (c & 1) ? c + 1 : c;
+    if (c >= 0x391 && c <= 0x3A9 && c != 0x3A2) return c + 0x20;
+    if (c >= 0x410 && c <= 0x42F) return c + 0x20;
+    if (c >= 0x400 && c <= 0x40F) return c + 0x50;
+    if (c >= 0xFF21 && c <= 0xFF3A) return c + 0x20;
+    return c;
+}
 template <typename F>
 static void tokenize_default(const char *text, F &&emit) {
+    const unsigned char *t = reinterpret_cast<const unsigned char *>(text);
     const size_t n = strlen(text);
     size_t i = 0;
     std::string tok;
-    auto is_tok = [](unsigned char c) { return (c >= '0' && c <= '9') || (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || c >= 0x80; };
     while (i < n) {
-        while (i < n && !is_tok((unsigned char)text[i])) i++;
+        uint32_t cp;
+        size_t adv = utf8_decode(t + i, n - i, cp);
+        if (!cp_is_alnum(cp)) {
+            i += adv;
+            continue;
+        }
         const size_t s = i;
-        while (i < n && is_tok((unsigned char)text[i])) i++;
-        const size_t len = i - s;
-        if (len == 0 || len > 40) continue;
-        tok.assign(text + s, len);
-        for (auto &ch : tok)
-            if (ch >= 'A' && ch <= 'Z') ch = (char)(ch - 'A' + 'a');
+        tok.clear();
+        while (i < n) {
+            adv = utf8_decode(t + i, n - i, cp);
+            if (!cp_is_alnum(cp)) break;
+            if (tok.size() < 160) utf8_append(cp_lower(cp), tok);
+            i += adv;
+        }
+        if (i - s >= 40) continue;  // RemoveLongFilter::limit(40) keeps len < 40
         emit(tok);
     }
 }
@@ -90,8 +152,10 @@ struct Clause {  // device-side description of one (field, term) of one query
     uint32_t df;
     float weight;
     uint32_t field;
-    uint32_t cache;  // index of the 256-entry norm table
+    uint32_t cache;  // index of the 256-entry norm table (high bits: term index << 24)
 };
+__host__ __device__ static inline uint32_t clause_cache(const Clause &c) { return c.cache & 0xffffffu; }
+__host__ __device__ static inline uint32_t clause_term(const Clause &c) { return c.cache >> 24; }
 
 struct Bm25ScoreParams {
     const uint32_t *post_docs;
@@ -101,6 +165,7 @@ struct Bm25ScoreParams {
     const uint8_t *alive;      // LSB-first over row ids, or null
     const Clause *clauses;     // all queries
     const uint32_t *clause_begin;  // [nq + 1]
+    const uint64_t *term_mask;     // [nq] AND: bit per query term that must be matched (in any searched field)
     const float *caches;       // [n_caches][256]
     float *part_keys;          // [nq][gridDim.x][k]
     uint32_t *part_ids;
@@ -184,33 +249,32 @@ __global__ void __launch_bounds__(256) bm25_score_kernel(const Bm25ScoreParams p
                 warp_window(od, cl[e].df, dmin, dmax, lane, wlo, whi);
                 if (active && window_find(od, wlo, whi, doc, pos)) active = false;
             }
-            bool all = active && (p.operator_or || c == 0);  // AND: only clause 0 can own a full match
+            // The first clause (in clause order) that contains a document owns it and sums every clause's contribution in
+            // clause order.  AND = every query TERM matched in at least one searched field (tantivy's QueryParser: AND over
+            // terms of OR over fields): the owner collects a bit per matched term.
+            bool all = active;
+            uint64_t seen = 1ull << clause_term(cl[c]);
             float score = 0.f;
             if (all) {
                 const float tf = (float)tfs[i];
-                const float norm = p.caches[(size_t)cl[c].cache * 256 + p.fieldnorm[(size_t)cl[c].field * p.n_docs + doc]];
+                const float norm = p.caches[(size_t)clause_cache(cl[c]) * 256 + p.fieldnorm[(size_t)cl[c].field * p.n_docs + doc]];
                 // explicit rn ops: no FMA contraction, so sums equal the reference's fp32 arithmetic bit for bit
                 score = __fmul_rn(cl[c].weight, __fdiv_rn(tf, __fadd_rn(tf, norm)));
             }
             for (uint32_t e = c + 1; e < nc; e++) {
                 if (!__any_sync(0xffffffffu, all)) break;
-                if (!cl[e].df) {
-                    if (!p.operator_or) all = false;
-                    continue;
-                }
+                if (!cl[e].df) continue;
                 const uint32_t *od = p.post_docs + cl[e].offset;
                 uint32_t wlo, whi;
                 warp_window(od, cl[e].df, dmin, dmax, lane, wlo, whi);
-                if (all) {
-                    if (window_find(od, wlo, whi, doc, pos)) {
-                        const float tf2 = (float)p.post_tfs[cl[e].offset + pos];
-                        const float n2 = p.caches[(size_t)cl[e].cache * 256 + p.fieldnorm[(size_t)cl[e].field * p.n_docs + doc]];
-                        score = __fadd_rn(score, __fmul_rn(cl[e].weight, __fdiv_rn(tf2, __fadd_rn(tf2, n2))));
-                    } else if (!p.operator_or) {
-                        all = false;
-                    }
+                if (all && window_find(od, wlo, whi, doc, pos)) {
+                    const float tf2 = (float)p.post_tfs[cl[e].offset + pos];
+                    const float n2 = p.caches[(size_t)clause_cache(cl[e]) * 256 + p.fieldnorm[(size_t)cl[e].field * p.n_docs + doc]];
+                    score = __fadd_rn(score, __fmul_rn(cl[e].weight, __fdiv_rn(tf2, __fadd_rn(tf2, n2))));
+                    seen |= 1ull << clause_term(cl[e]);
                 }
             }
+            if (all && !p.operator_or && seen != p.term_mask[q]) all = false;
             if (all) {
                 const uint32_t rid = p.row_id[doc];
                 const bool live = !p.alive || ((p.alive[rid >> 3] >> (rid & 7)) & 1);
@@ -278,7 +342,7 @@ struct b200_bm25 {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::mutex mu;
-    DevVec d_docs, d_tfs, d_fn, d_rows, d_clauses, d_begin, d_caches, d_pk, d_pi, d_alive, d_odis, d_oids, d_score, d_row64, d_cnt;
+    DevVec d_docs, d_tfs, d_fn, d_rows, d_clauses, d_begin, d_caches, d_pk, d_pi, d_alive, d_odis, d_oids, d_score, d_row64, d_cnt, d_masks;
 };
 
 static int bm25_device_ok() {
@@ -313,7 +377,7 @@ extern "C" int b200_bm25_free(b200_bm25 *ix) {
     if (!ix) return B200_OK;
     cudaSetDevice(ix->device);
     for (DevVec *v : {&ix->d_docs, &ix->d_tfs, &ix->d_fn, &ix->d_rows, &ix->d_clauses, &ix->d_begin, &ix->d_caches, &ix->d_pk,
-                      &ix->d_pi, &ix->d_alive, &ix->d_odis, &ix->d_oids, &ix->d_score, &ix->d_row64, &ix->d_cnt})
+                      &ix->d_pi, &ix->d_alive, &ix->d_odis, &ix->d_oids, &ix->d_score, &ix->d_row64, &ix->d_cnt, &ix->d_masks})
         v->release();
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
@@ -456,15 +520,16 @@ extern "C" int b200_bm25_search_batch(b200_bm25 *ix, const char *const *sentence
     std::vector<Clause> clauses;
     std::vector<uint32_t> begin(nq + 1, 0);
     std::vector<float> caches;
+    std::vector<uint64_t> term_masks(nq, 0);
     for (int64_t q = 0; q < nq; q++) {
         begin[q] = (uint32_t)clauses.size();
         std::vector<std::string> terms;
         tokenize_default(sentences[q], [&](const std::string &t) {
             if (terms.size() < 64 && std::find(terms.begin(), terms.end(), t) == terms.end()) terms.push_back(t);
         });
-        bool dead = false;  // AND with an unknown term matches nothing
         std::vector<Clause> mine;
-        for (uint32_t fq = 0; fq < n_fields_q && !dead; fq++) {
+        uint64_t known = 0;  // terms found in at least one searched field
+        for (uint32_t fq = 0; fq < n_fields_q; fq++) {
             const uint32_t f = fields[fq];
             if (f >= ix->n_fields) return fail(B200_ERR_INVALID, "field out of range");
             const uint64_t N = stat_total_docs ? stat_total_docs : nd;
@@ -474,10 +539,8 @@ extern "C" int b200_bm25_search_batch(b200_bm25 *ix, const char *const *sentence
             for (int c = 0; c < 256; c++) caches.push_back(kBm25K1 * (1.0f - kBm25B + kBm25B * (float)g_fieldnorm[c] / avgdl));
             for (size_t t = 0; t < terms.size(); t++) {
                 auto it = ix->dict[f].find(terms[t]);
-                if (it == ix->dict[f].end()) {
-                    if (!operator_or) dead = true;
-                    continue;
-                }
+                if (it == ix->dict[f].end()) continue;
+                known |= 1ull << t;
                 const TermList &tl = ix->lists[it->second];
                 const uint64_t n = stat_total_docs ? stat_doc_freq[(size_t)q * n_fields_q * 64 + fq * 64 + t] : tl.docs.size();
                 const float x = ((float)(N - n) + 0.5f) / ((float)n + 0.5f);
@@ -487,11 +550,14 @@ extern "C" int b200_bm25_search_batch(b200_bm25 *ix, const char *const *sentence
                 cl.df = (uint32_t)tl.docs.size();
                 cl.weight = idf * (1.0f + kBm25K1);
                 cl.field = f;
-                cl.cache = cache_idx;
+                cl.cache = cache_idx | ((uint32_t)t << 24);
                 mine.push_back(cl);
             }
         }
-        if (!operator_or && terms.empty()) dead = true;
+        const uint64_t all_terms = terms.size() >= 64 ? ~0ull : ((1ull << terms.size()) - 1);
+        term_masks[q] = all_terms;
+        // AND with a term that no searched field knows matches nothing
+        const bool dead = !operator_or && (terms.empty() || known != all_terms);
         if (!dead) {
             if (mine.size() > (size_t)kMaxClauses) return fail(B200_ERR_UNSUPPORTED, "more than 64 (field, term) clauses in one query");
             clauses.insert(clauses.end(), mine.begin(), mine.end());
@@ -508,6 +574,8 @@ extern "C" int b200_bm25_search_batch(b200_bm25 *ix, const char *const *sentence
     B200_TRY(ix->d_clauses.reserve(clauses.size() * sizeof(Clause)));
     B200_TRY(ix->d_begin.reserve(begin.size() * 4));
     B200_TRY(ix->d_caches.reserve(caches.size() * 4));
+    B200_TRY(ix->d_masks.reserve(term_masks.size() * 8));
+    if (caches.size() / 256 >= (1u << 24)) return fail(B200_ERR_UNSUPPORTED, "too many (query, field) norm tables in one batch");
     B200_TRY(ix->d_pk.reserve((size_t)nq * bx * k * 4));
     B200_TRY(ix->d_pi.reserve((size_t)nq * bx * k * 4));
     B200_TRY(ix->d_odis.reserve((size_t)nq * k * 4));
@@ -518,6 +586,7 @@ extern "C" int b200_bm25_search_batch(b200_bm25 *ix, const char *const *sentence
     B200_CUDA_OK(cudaMemcpyAsync(ix->d_clauses.p, clauses.data(), clauses.size() * sizeof(Clause), cudaMemcpyHostToDevice, s));
     B200_CUDA_OK(cudaMemcpyAsync(ix->d_begin.p, begin.data(), begin.size() * 4, cudaMemcpyHostToDevice, s));
     B200_CUDA_OK(cudaMemcpyAsync(ix->d_caches.p, caches.data(), caches.size() * 4, cudaMemcpyHostToDevice, s));
+    B200_CUDA_OK(cudaMemcpyAsync(ix->d_masks.p, term_masks.data(), term_masks.size() * 8, cudaMemcpyHostToDevice, s));
     const uint8_t *d_alive = nullptr;
     if (use_filter && alive_bits) {
         uint64_t max_row = 0;
@@ -536,6 +605,7 @@ extern "C" int b200_bm25_search_batch(b200_bm25 *ix, const char *const *sentence
     sp.clauses = reinterpret_cast<const Clause *>(ix->d_clauses.p);
     sp.clause_begin = reinterpret_cast<const uint32_t *>(ix->d_begin.p);
     sp.caches = reinterpret_cast<const float *>(ix->d_caches.p);
+    sp.term_mask = reinterpret_cast<const uint64_t *>(ix->d_masks.p);
     sp.part_keys = reinterpret_cast<float *>(ix->d_pk.p);
     sp.part_ids = reinterpret_cast<uint32_t *>(ix->d_pi.p);
     sp.n_docs = (uint32_t)nd;
@@ -581,4 +651,126 @@ extern "C" int b200_bm25_search(b200_bm25 *ix, const char *sentence, const uint3
     const char *one[1] = {sentence};
     return b200_bm25_search_batch(ix, one, 1, fields, n_fields_q, topk, alive_bits, use_filter, operator_or, stat_total_docs,
                                   stat_total_tokens, stat_doc_freq, out_rows, out_scores, out_n);
+}
+
+// ------------------------------------------------------------------------------------
+// persistence: the reference keeps a tantivy directory per part and (re)loads it with ffi_load_index_reader
+// (TantivyIndexStore.cpp:646-686, with retries when the cache directory is damaged).  tantivy's segment files are not
+// reproducible without the crate, so this is our own single file ("B2TX" v1): statistics, dictionary, postings.
+// Loading validates every size before it allocates and uploads to HBM.
+// ------------------------------------------------------------------------------------
+namespace {
+struct TxHeader {
+    char magic[4];
+    uint32_t version, n_fields;
+    uint64_t n_docs, n_lists, n_postings;
+};
+bool fw(FILE *f, const void *p, size_t b) { return b == 0 || fwrite(p, 1, b, f) == b; }
+bool fr(FILE *f, void *p, size_t b) { return b == 0 || fread(p, 1, b, f) == b; }
+}  // namespace
+
+extern "C" int b200_bm25_save(b200_bm25 *ix, const char *path) {
+    if (!ix || !path) return fail(B200_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (!ix->committed) return fail(B200_ERR_INVALID, "commit the index before saving it");
+    B200_CUDA_OK(cudaSetDevice(ix->device));
+    uint64_t total = 0;
+    for (auto &tl : ix->lists) total += tl.docs.size();
+    std::vector<uint32_t> tfs(total ? total : 1);
+    if (total) B200_CUDA_OK(cudaMemcpy(tfs.data(), ix->d_tfs.p, total * 4, cudaMemcpyDeviceToHost));
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(B200_ERR_INVALID, std::string("cannot open ") + path);
+    TxHeader h{};
+    memcpy(h.magic, "B2TX", 4);
+    h.version = 1;
+    h.n_fields = ix->n_fields;
+    h.n_docs = ix->row_ids.size();
+    h.n_lists = ix->lists.size();
+    h.n_postings = total;
+    bool ok = fw(f, &h, sizeof(h)) && fw(f, ix->row_ids.data(), h.n_docs * 8) && fw(f, ix->total_tokens.data(), (size_t)h.n_fields * 8);
+    for (uint32_t fld = 0; ok && fld < ix->n_fields; fld++) ok = fw(f, ix->doc_len[fld].data(), h.n_docs * 4);
+    for (uint32_t fld = 0; ok && fld < ix->n_fields; fld++) {
+        const uint64_t nt = ix->dict[fld].size();
+        ok = fw(f, &nt, 8);
+        for (auto &kv : ix->dict[fld]) {
+            const uint32_t len = (uint32_t)kv.first.size(), li = kv.second;
+            if (!(ok = ok && fw(f, &len, 4) && fw(f, kv.first.data(), len) && fw(f, &li, 4))) break;
+        }
+    }
+    for (auto &tl : ix->lists) {
+        const uint64_t df = tl.docs.size();
+        if (!(ok = ok && fw(f, &df, 8) && fw(f, tl.docs.data(), df * 4) && fw(f, tfs.data() + tl.offset, df * 4))) break;
+    }
+    ok = (fclose(f) == 0) && ok;
+    return ok ? B200_OK : fail(B200_ERR_INVALID, std::string("write failed: ") + path);
+}
+
+extern "C" int b200_bm25_load(const char *path, b200_bm25 **out) {
+    if (!path || !out) return fail(B200_ERR_INVALID, "bad arguments");
+    *out = nullptr;
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(B200_ERR_INVALID, std::string("cannot open ") + path);
+    fseek(f, 0, SEEK_END);
+    const uint64_t file_bytes = (uint64_t)ftell(f);
+    fseek(f, 0, SEEK_SET);
+    TxHeader h{};
+    b200_bm25 *ix = nullptr;
+    auto bail = [&](const std::string &msg) {
+        fclose(f);
+        if (ix) b200_bm25_free(ix);
+        return fail(B200_ERR_INVALID, msg);
+    };
+    if (!fr(f, &h, sizeof(h)) || memcmp(h.magic, "B2TX", 4) != 0 || h.version != 1) return bail("not a B2TX v1 text index file");
+    // nothing below may allocate more than the file can back
+    if (h.n_fields == 0 || h.n_fields > 64 || h.n_docs >= 0xffffffffull || h.n_docs * 8 > file_bytes || h.n_postings * 8 > file_bytes ||
+        h.n_lists > file_bytes / 8 + 1)
+        return bail("corrupt text index header");
+    if (b200_bm25_create(h.n_fields, &ix) != B200_OK) {
+        fclose(f);
+        return B200_ERR_NO_DEVICE;
+    }
+    try {
+        ix->row_ids.resize(h.n_docs);
+        if (!fr(f, ix->row_ids.data(), h.n_docs * 8) || !fr(f, ix->total_tokens.data(), (size_t)h.n_fields * 8)) return bail("truncated text index (rows)");
+        for (uint32_t fld = 0; fld < h.n_fields; fld++) {
+            ix->doc_len[fld].resize(h.n_docs);
+            if (!fr(f, ix->doc_len[fld].data(), h.n_docs * 4)) return bail("truncated text index (field norms)");
+        }
+        ix->lists.resize(h.n_lists);
+        for (uint32_t fld = 0; fld < h.n_fields; fld++) {
+            uint64_t nt = 0;
+            if (!fr(f, &nt, 8) || nt > h.n_lists) return bail("corrupt text index (dictionary)");
+            std::string term;
+            for (uint64_t t = 0; t < nt; t++) {
+                uint32_t len = 0, li = 0;
+                if (!fr(f, &len, 4) || len > 65536) return bail("corrupt text index (term)");
+                term.resize(len);
+                if (!fr(f, &term[0], len) || !fr(f, &li, 4) || li >= h.n_lists) return bail("corrupt text index (term)");
+                ix->dict[fld].emplace(term, li);
+            }
+        }
+        uint64_t total = 0;
+        std::vector<uint32_t> tfs(h.n_postings ? h.n_postings : 1);
+        for (auto &tl : ix->lists) {
+            uint64_t df = 0;
+            if (!fr(f, &df, 8) || total + df > h.n_postings) return bail("corrupt text index (postings)");
+            tl.docs.resize(df);
+            if (!fr(f, tl.docs.data(), df * 4) || !fr(f, tfs.data() + total, df * 4)) return bail("truncated text index (postings)");
+            for (uint64_t i = 0; i < df; i++)
+                if (tl.docs[i] >= h.n_docs || (i && tl.docs[i] <= tl.docs[i - 1])) return bail("corrupt text index (doc ordinals)");
+            tl.tfs.assign(tfs.begin() + total, tfs.begin() + total + df);
+            total += df;
+        }
+        if (total != h.n_postings) return bail("corrupt text index (posting count)");
+    } catch (const std::bad_alloc &) {
+        return bail("out of host memory while loading the text index");
+    }
+    fclose(f);
+    const int rc = b200_bm25_commit(ix);
+    if (rc != B200_OK) {
+        b200_bm25_free(ix);
+        return rc;
+    }
+    *out = ix;
+    return B200_OK;
 }

@@ -101,6 +101,7 @@ struct b200_corpus {
     // workspaces
     DevBuf w_raw, w_q32, w_qbf, w_qlo, w_qnorm, w_pk, w_pi, w_lk, w_li, w_alive, w_odis, w_oids, w_stage, w_prog;
     int sync_slack = 2;
+    int rescore_l2 = 1;      // tensor-core L2: re-score the k winners exactly (B200_GEMM_RESCORE_L2=0 disables, A/B only)
     int gemm_multicast = 1;  // CTA pairs per cluster sharing each corpus tile: 1 auto (4, else 2), 2, 4; B200_GEMM_MULTICAST=0 disables
     int gemm_ts = 0;  // 0 streaming (default: faster at every measured d), 1 TS when d_pad <= 512, 2 TS whenever it fits
     // what the last tensor-core launch really was (tests assert on it): cta_group, pairs per cluster, TS form, grid, kernel id
@@ -236,6 +237,7 @@ extern "C" int b200_corpus_create(int metric, int dtype, int d, int64_t capacity
     cudaGetDevice(&c->device);
     c->sms = num_sms();
     if (const char *ev = getenv("B200_GEMM_SYNC_SLACK")) c->sync_slack = atoi(ev);
+    if (const char *ev = getenv("B200_GEMM_RESCORE_L2")) c->rescore_l2 = atoi(ev);
     if (const char *ev = getenv("B200_GEMM_TS")) c->gemm_ts = atoi(ev);
     if (const char *ev = getenv("B200_GEMM_MULTICAST")) c->gemm_multicast = atoi(ev);
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -674,6 +676,11 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
         mp.out_dis = d_out_dis + qb * k;
         mp.out_ids = d_out_ids + qb * k;
         B200_CUDA_OK(launch_topk_merge(mp, false, s));
+        // L2: the winners' distances from the direct difference form (the expanded form above only RANKS; it cancels for
+        // data far from the origin).  The query operand is what the caller passed (fp32), the rows what is stored.
+        if (c->metric == B200_METRIC_L2 && k <= 1024 && c->rescore_l2)
+            B200_CUDA_OK(launch_rescore_l2(c->data, c->dtype == B200_DTYPE_BF16, c->row_bytes, c->d_pad, q32 + qb * c->d_pad, nq_c, id_offset, k,
+                                           d_out_dis + qb * k, d_out_ids + qb * k, s));
     }
     return B200_OK;
 }

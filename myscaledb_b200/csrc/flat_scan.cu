@@ -435,6 +435,76 @@ __global__ void __launch_bounds__(kScanThreads) topk_merge_ext_kernel(const Merg
 }
 
 // ------------------------------------------------------------------------------------
+// Exact L2 of the winners.  The tensor-core paths rank by ||y||^2 - 2 x.y (+ ||x||^2), faiss' BLAS form
+// (BruteForceSearch.h:77-88 for nx >= 20); for data far from the origin the expansion cancels and the ~1e-5 relative
+// error of the product (3xTF32, bf16 operands) grows to ~2e-4 of the distance (measured: 768-d clusters at |y|^2 = 840,
+// d^2 = 115).  The k winners of every query are therefore re-scored with the direct sum of squared differences in fp32
+// (one warp per winner, the same arithmetic as the scan kernel) and re-ordered by (distance, id).  One CTA per query.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rescore_l2_kernel(const void *corpus, int bf16, int64_t row_bytes, int d_pad, const float *queries,
+                                                         int64_t id_offset, int k, float *dis, int64_t *ids) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *sd = reinterpret_cast<float *>(smem_raw);               // [k]
+    int64_t *si = reinterpret_cast<int64_t *>(sd + ((k + 1) & ~1));  // [k]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t q = blockIdx.x;
+    const float *x = queries + q * d_pad;
+    for (int j = warp; j < k; j += 8) {
+        const int64_t id = ids[q * k + j];
+        float acc = 0.f;
+        if (id >= 0) {
+            const unsigned char *row = reinterpret_cast<const unsigned char *>(corpus) + (size_t)(id - id_offset) * row_bytes;
+            if (bf16) {
+                const uint4 *rp = reinterpret_cast<const uint4 *>(row);
+                for (int c = lane; c < d_pad / 8; c += 32) {
+                    float y[8];
+                    ChunkTraits<true>::unpack(rp[c], y);
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const float t = x[c * 8 + e] - y[e];
+                        acc = fmaf(t, t, acc);
+                    }
+                }
+            } else {
+                const float4 *rp = reinterpret_cast<const float4 *>(row);
+                for (int c = lane; c < d_pad / 4; c += 32) {
+                    const float4 y = rp[c];
+                    float t = x[c * 4] - y.x; acc = fmaf(t, t, acc);
+                    t = x[c * 4 + 1] - y.y; acc = fmaf(t, t, acc);
+                    t = x[c * 4 + 2] - y.z; acc = fmaf(t, t, acc);
+                    t = x[c * 4 + 3] - y.w; acc = fmaf(t, t, acc);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        }
+        if (lane == 0) {
+            sd[j] = id >= 0 ? acc : FLT_MAX;
+            si[j] = id >= 0 ? id : INT64_MAX;
+        }
+    }
+    __syncthreads();
+    // rank sort by (distance, id); unused slots (id = -1) keep the tail
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        const float dj = sd[j];
+        const int64_t ij = si[j];
+        int rank = 0;
+        for (int e = 0; e < k; e++) rank += (sd[e] < dj || (sd[e] == dj && (si[e] < ij || (si[e] == ij && e < j)))) ? 1 : 0;
+        dis[q * k + rank] = ij == INT64_MAX ? FLT_MAX : dj;
+        ids[q * k + rank] = ij == INT64_MAX ? -1 : ij;
+    }
+}
+
+cudaError_t launch_rescore_l2(const void *corpus, int bf16, int64_t row_bytes, int d_pad, const float *queries, int64_t nq, int64_t id_offset,
+                              int k, float *dis, int64_t *ids, cudaStream_t s) {
+    if (nq == 0) return cudaSuccess;
+    const size_t smem = (size_t)((k + 1) & ~1) * 4 + (size_t)k * 8;
+    rescore_l2_kernel<<<(unsigned)nq, 256, smem, s>>>(corpus, bf16, row_bytes, d_pad, queries, id_offset, k, dis, ids);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------
 template <int QT, int U, int CU>

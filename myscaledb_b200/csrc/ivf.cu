@@ -172,6 +172,17 @@ __global__ void residual_sub_kernel(const float *x, int64_t n, int64_t x_stride,
     }
 }
 
+// pairs[2 i] = an empty cluster, pairs[2 i + 1] = a large one: the empty one becomes a nudged copy of the large one
+__global__ void kmeans_split_kernel(float *c, const int *pairs, int d) {
+    const int dst = pairs[2 * blockIdx.x], src = pairs[2 * blockIdx.x + 1];
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+        const float v = c[(size_t)src * d + j];
+        const float eps = (j & 1) ? 1.f / 1024.f : -1.f / 1024.f;
+        c[(size_t)dst * d + j] = v * (1.f + eps) + eps * 1e-3f;
+        c[(size_t)src * d + j] = v * (1.f - eps) - eps * 1e-3f;
+    }
+}
+
 __global__ void iota_kernel(uint32_t *v, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] = (uint32_t)i;
@@ -299,10 +310,15 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const ScatterParams p
         const float *x = p.rows + (int64_t)r * p.stride;
         float acc = 0.f;
         if (p.payload == IVF_PRODUCER_TMA) {
-            __nv_bfloat16 *dst = p.pool + (size_t)slot * p.d_pad64;
+            // k-block-major pages: element (row r of the page, dim j) at ((page * KB + j / 64) * 256 + r) * 64 + j % 64, so
+            // that the 256 x 64 tile of one k-block is 32 KB contiguous in HBM (one DRAM-friendly TMA box per tile)
+            const uint32_t page = slot / kPageRows, r_in = slot % kPageRows;
+            const int kbc = p.d_pad64 / 64;
+            __nv_bfloat16 *pbase = p.pool + (size_t)page * kPageRows * p.d_pad64;
             for (int j = lane; j < p.d_pad64; j += 32) {
                 const __nv_bfloat16 b = __float2bfloat16_rn(j < p.d ? x[j] : 0.f);
-                dst[j] = b;
+                (void)kbc;
+                pbase[((size_t)(j >> 6) * kPageRows + r_in) * 64 + (j & 63)] = b;
                 const float v = __bfloat162float(b);
                 acc = fmaf(v, v, acc);
             }
@@ -949,6 +965,38 @@ static int kmeans_device(const float *x, int64_t n, int64_t stride, int d, int n
         kmeans_accumulate_kernel<<<gridsz(n * d), 256, 0, s>>>(x, n, stride, d, d_idx, d_sums, d_cnt);
         kmeans_update_kernel<<<gridsz((int64_t)nc * d), 256, 0, s>>>(d_c, d_sums, d_cnt, nc, d);
         g_launches += 2;
+        // empty clusters take half of the currently largest ones (both copies nudged apart; the next assignment splits the
+        // members) -- without this a strided initialisation leaves a third of well-separated clusters without a centroid
+        if (it + 1 < iters && nc >= 2) {
+            std::vector<uint32_t> h_cnt(nc);
+            B200_CUDA_OK(cudaMemcpyAsync(h_cnt.data(), d_cnt, (size_t)nc * 4, cudaMemcpyDeviceToHost, s));
+            B200_CUDA_OK(cudaStreamSynchronize(s));
+            std::vector<int> empties, order(nc);
+            for (int i = 0; i < nc; i++) {
+                order[i] = i;
+                if (h_cnt[i] == 0) empties.push_back(i);
+            }
+            if (!empties.empty()) {
+                std::partial_sort(order.begin(), order.begin() + std::min<size_t>(nc, empties.size()), order.end(),
+                                  [&](int a, int b) { return h_cnt[a] > h_cnt[b]; });
+                std::vector<int> pairs;
+                for (size_t e = 0; e < empties.size() && e < (size_t)nc; e++) {
+                    const int src = order[e];
+                    if (h_cnt[src] < 2) break;
+                    pairs.push_back(empties[e]);
+                    pairs.push_back(src);
+                }
+                if (!pairs.empty()) {
+                    int *d_pairs = nullptr;
+                    B200_CUDA_OK(cudaMalloc(&d_pairs, pairs.size() * 4));
+                    B200_CUDA_OK(cudaMemcpyAsync(d_pairs, pairs.data(), pairs.size() * 4, cudaMemcpyHostToDevice, s));
+                    kmeans_split_kernel<<<(unsigned)(pairs.size() / 2), 128, 0, s>>>(d_c, d_pairs, d);
+                    g_launches++;
+                    B200_CUDA_OK(cudaStreamSynchronize(s));
+                    cudaFree(d_pairs);
+                }
+            }
+        }
     }
     if (rc == B200_OK) {
         B200_CUDA_OK(cudaGetLastError());
@@ -1524,6 +1572,7 @@ static int search_device_locked(b200_index *ix, const float *d_queries, int64_t 
             const double split = std::ceil(want_items / std::max(1.0, est_items_unsplit));
             ppc = (uint32_t)std::max(2.0, std::ceil(avg_pages / split));
         }
+        ppc = std::min<uint32_t>(ppc, 16);                                // an item never streams more than 16 pages: no long tail
         ppc = std::max<uint32_t>(ppc, (ix->max_list_pages + 63) / 64);   // at most 64 chunks per list
         ppc = std::max<uint32_t>(ppc, 1);
         if (const int forced = parse_int_param(params, "pages_per_chunk", 0)) ppc = (uint32_t)forced;

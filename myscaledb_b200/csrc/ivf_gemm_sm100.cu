@@ -100,7 +100,8 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                     if (elect_one()) {
                         mbar_arrive_expect_tx(&full_bar[stage], DEC ? A_BYTES : C::TX_BYTES);
                         tma_load_2d(&map_q, &full_bar[stage], sA + stage * A_BYTES, kb * BK, (int)item.q_begin);
-                        if (!DEC) tma_load_2d(&map_c, &full_bar[stage], sB + stage * C::B_BYTES, kb * BK, (int)(page * (uint32_t)BN));
+                        // bf16 pages are stored k-block-major ([page][k-block][256 rows][64]): one B tile = 32 KB CONTIGUOUS in HBM
+                        if (!DEC) tma_load_2d(&map_c, &full_bar[stage], sB + stage * C::B_BYTES, 0, (int)((page * (uint32_t)kb_count + kb) * (uint32_t)BN));
                     }
                     __syncwarp();
                     if (++stage == STAGES) {
@@ -342,20 +343,13 @@ static cudaError_t launch_ivf(const CUtensorMap &map_q, const CUtensorMap &map_c
     constexpr bool DEC = PRODUCER != IVF_PRODUCER_TMA;
     // ring depth: as deep as the per-thread lists (and the PQ codebook) leave room for
     const int extra = PRODUCER == IVF_PRODUCER_PQ ? (int)round_up(p.codebook_bytes, 1024) : 0;
+    // ring depth first (bytes in flight per SM bound the HBM rate of a streaming item): 4 stages whenever they fit; the
+    // per-thread lists move to global scratch (L1 / L2 resident, touched rarely in steady state) when they do not fit too
     int stages = 4;
     auto need = [&](int st, int k_smem) { return Cfg<1>::off_list(st) + k_smem * EPI_THREADS * 8 + extra + SMEM_ALIGN_SLACK; };
-    p.lists_in_smem = 0;
-    for (int st = 4; st >= 2; st--)
-        if (p.k <= kGemmSmemK && need(st, p.k) <= 232448) {
-            stages = st;
-            p.lists_in_smem = 1;
-            break;
-        }
-    if (!p.lists_in_smem) {
-        stages = 4;
-        while (stages > 2 && need(stages, 0) > 232448) stages--;
-        if (need(stages, 0) > 232448) return cudaErrorInvalidValue;
-    }
+    while (stages > 2 && need(stages, 0) > 232448) stages--;
+    if (need(stages, 0) > 232448) return cudaErrorInvalidValue;
+    p.lists_in_smem = (p.k <= kGemmSmemK && need(stages, p.k) <= 232448) ? 1 : 0;
     p.stages = stages;
     const int k_smem = p.lists_in_smem ? p.k : 0;
     p.codebook_smem_off = Cfg<1>::off_list(stages) + k_smem * EPI_THREADS * 8;
@@ -380,7 +374,8 @@ cudaError_t launch_ivf_gemm_topk(const IvfGemmParams &p, const void *queries_bf1
         return cudaErrorInvalidValue;
     }
     if (p.producer == IVF_PRODUCER_TMA) {
-        if (!gemm::encode_rows_map(&map_c, pool_bf16, pool_rows, p.d_pad, gemm::BN)) {
+        // the pool as a [pool_rows * k-blocks][64] matrix: tile (page, kb) = rows [(page * kb_count + kb) * 256, +256)
+        if (!gemm::encode_rows_map(&map_c, pool_bf16, pool_rows * (p.d_pad / gemm::BK), gemm::BK, gemm::BN)) {
             *err_detail = "cuTensorMapEncodeTiled failed (pool)";
             return cudaErrorInvalidValue;
         }

@@ -52,6 +52,9 @@ size_t scan_smem_bytes(int qt, int d_pad, int k);
 cudaError_t launch_flat_scan(const ScanParams &p, int qt, int blocks_x, cudaStream_t s);
 cudaError_t launch_binary_scan(const BinaryScanParams &p, int blocks_x, cudaStream_t s);
 cudaError_t launch_topk_merge(const MergeParams &p, bool external, cudaStream_t s);
+// exact squared-L2 of the k winners of every query (direct differences, fp32) + re-order by (distance, id); k <= 1024
+cudaError_t launch_rescore_l2(const void *corpus, int bf16, int64_t row_bytes, int d_pad, const float *queries, int64_t nq, int64_t id_offset,
+                              int k, float *dis, int64_t *ids, cudaStream_t s);
 
 // ---- tcgen05 bf16 GEMM + fused top-k (ip_gemm_sm100.cu) ---------------------------
 struct GemmTopkParams {

@@ -224,6 +224,17 @@ class BM25Index:
         _check(lib().b200_bm25_commit(self._h))
         return self
 
+    def save(self, path):
+        _check(lib().b200_bm25_save(self._h, str(path).encode()))
+
+    @classmethod
+    def load(cls, path, n_fields=1):
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        self.n_fields = n_fields
+        _check(lib().b200_bm25_load(str(path).encode(), C.byref(self._h)))
+        return self
+
     @property
     def total_docs(self):
         v = C.c_uint64()

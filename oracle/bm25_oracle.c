@@ -15,7 +15,7 @@
  *     norm[c]= k1 * (1 - b + b * fieldnorm(c) / avgdl),  avgdl = total_tokens / total_docs (fp32)
  *     score  = weight * tf / (tf + norm[fieldnorm_id(dl)])
  * with tantivy's 1-byte field-norm code (exact for dl < 40) and the "default"
- * tokenizer (split on non-alphanumeric, drop tokens > 40 bytes, lowercase).
+ * tokenizer (split on non-alphanumeric, drop tokens of 40 bytes or more, lowercase).
  * Multi-term queries are a Boolean OR (operator_or) / AND of term scorers whose
  * scores add; top-k ties go to the smaller doc id (TopDocs).
  * Table-wide statistics override the per-part ones exactly like
@@ -173,21 +173,80 @@ static int64_t intern_term(orc_bm25_index *ix, uint32_t field, const char *s, si
     return ix->n_terms++;
 }
 
-/* tantivy "default" tokenizer: SimpleTokenizer (maximal runs of alphanumeric
- * chars) -> RemoveLongFilter(40) -> LowerCaser.  Bytes >= 0x80 (UTF-8 letters)
- * are kept as token bytes; ASCII is lowercased.  Calls cb(token, len). */
+/* tantivy 0.21 "default" analyzer: SimpleTokenizer (maximal runs of chars with char::is_alphanumeric) ->
+ * RemoveLongFilter::limit(40) (keeps tokens of FEWER than 40 bytes: `token.text.len() < limit`) -> LowerCaser
+ * (Unicode to_lowercase).  Text is UTF-8.  The Unicode classes are restated for the blocks that matter in practice:
+ * Latin-1 / General Punctuation / symbols, arrows, CJK and full-width punctuation are separators; Latin-1, Latin
+ * Extended-A, Greek, Cyrillic and full-width capitals are lowercased; every other non-ASCII code point is a letter
+ * and is kept as is.  (Parity beyond these blocks is unpinned)  Calls cb(token, len). */
 typedef void (*tok_cb)(void *ctx, const char *tok, size_t len);
+static size_t utf8_decode(const unsigned char *s, size_t n, uint32_t *cp) {
+    if (s[0] < 0x80) { *cp = s[0]; return 1; }
+    if ((s[0] & 0xE0) == 0xC0 && n >= 2 && (s[1] & 0xC0) == 0x80) { *cp = ((s[0] & 0x1Fu) << 6) | (s[1] & 0x3Fu); return 2; }
+    if ((s[0] & 0xF0) == 0xE0 && n >= 3 && (s[1] & 0xC0) == 0x80 && (s[2] & 0xC0) == 0x80) {
+        *cp = ((s[0] & 0x0Fu) << 12) | ((s[1] & 0x3Fu) << 6) | (s[2] & 0x3Fu); return 3;
+    }
+    if ((s[0] & 0xF8) == 0xF0 && n >= 4 && (s[1] & 0xC0) == 0x80 && (s[2] & 0xC0) == 0x80 && (s[3] & 0xC0) == 0x80) {
+        *cp = ((s[0] & 0x07u) << 18) | ((s[1] & 0x3Fu) << 12) | ((s[2] & 0x3Fu) << 6) | (s[3] & 0x3Fu); return 4;
+    }
+    *cp = 0xFFFD; /* invalid byte: a letter-like replacement, one byte consumed */
+    return 1;
+}
+static size_t utf8_encode(uint32_t cp, char *out) {
+    if (cp < 0x80) { out[0] = (char)cp; return 1; }
+    if (cp < 0x800) { out[0] = (char)(0xC0 | (cp >> 6)); out[1] = (char)(0x80 | (cp & 0x3F)); return 2; }
+    if (cp < 0x10000) { out[0] = (char)(0xE0 | (cp >> 12)); out[1] = (char)(0x80 | ((cp >> 6) & 0x3F)); out[2] = (char)(0x80 | (cp & 0x3F)); return 3; }
+    out[0] = (char)(0xF0 | (cp >> 18)); out[1] = (char)(0x80 | ((cp >> 12) & 0x3F)); out[2] = (char)(0x80 | ((cp >> 6) & 0x3F));
+    out[3] = (char)(0x80 | (cp & 0x3F)); return 4;
+}
+static int cp_is_alnum(uint32_t c) {
+    if (c < 0x80) return isalnum((int)c) != 0;
+    if (c <= 0xBF) return c == 0xAA || c == 0xB2 || c == 0xB3 || c == 0xB5 || c == 0xB9 || c == 0xBA || c == 0xBC || c == 0xBD || c == 0xBE;
+    if (c == 0xD7 || c == 0xF7) return 0;
+    if (c >= 0x2000 && c <= 0x206F) return 0;
+    if (c >= 0x20A0 && c <= 0x20CF) return 0;
+    if (c >= 0x2190 && c <= 0x245F) return 0;
+    if (c >= 0x2500 && c <= 0x2BFF) return 0;
+    if (c >= 0x2E00 && c <= 0x2E7F) return 0;
+    if ((c >= 0x3000 && c <= 0x3004) || (c >= 0x3008 && c <= 0x3020) || c == 0x3030 || (c >= 0x303D && c <= 0x303F)) return 0;
+    if ((c >= 0xFE10 && c <= 0xFE1F) || (c >= 0xFE30 && c <= 0xFE6F)) return 0;
+    if ((c >= 0xFF00 && c <= 0xFF0F) || (c >= 0xFF1A && c <= 0xFF20) || (c >= 0xFF3B && c <= 0xFF40) || (c >= 0xFF5B && c <= 0xFF65) ||
+        (c >= 0xFFE0 && c <= 0xFFEF))
+        return 0;
+    return 1;
+}
+static uint32_t cp_lower(uint32_t c) {
+    if (c < 0x80) return (uint32_t)tolower((int)c);
+    if (c >= 0xC0 && c <= 0xDE && c != 0xD7) return c + 0x20;
+    if (c >= 0x100 && c <= 0x137) return (c & 1) ? c : c + 1;
+    if (c >= 0x139 && c <= 0x148) return (c & 1) ? c + 1 : c;
+    if (c >= 0x14A && c <= 0x177) return (c & 1) ? c : c + 1;
+    if (c == 0x178) return 0xFF;
+    if (c >= 0x179 && c <= 0x17E) return (c & 1) ? c + 1 : c;
+    if (c >= 0x391 && c <= 0x3A9 && c != 0x3A2) return c + 0x20;
+    if (c >= 0x410 && c <= 0x42F) return c + 0x20;
+    if (c >= 0x400 && c <= 0x40F) return c + 0x50;
+    if (c >= 0xFF21 && c <= 0xFF3A) return c + 0x20;
+    return c;
+}
 static void tokenize(const char *text, tok_cb cb, void *ctx) {
+    const unsigned char *t = (const unsigned char *)text;
     size_t n = strlen(text), i = 0;
-    char buf[64];
+    char buf[192];
     while (i < n) {
-        while (i < n && !(isalnum((unsigned char)text[i]) || (unsigned char)text[i] >= 0x80)) i++;
-        size_t s = i;
-        while (i < n && (isalnum((unsigned char)text[i]) || (unsigned char)text[i] >= 0x80)) i++;
-        size_t len = i - s;
-        if (len == 0 || len > 40) continue;
-        for (size_t j = 0; j < len; j++) buf[j] = (char)tolower((unsigned char)text[s + j]);
-        cb(ctx, buf, len);
+        uint32_t cp;
+        size_t adv = utf8_decode(t + i, n - i, &cp);
+        if (!cp_is_alnum(cp)) { i += adv; continue; }
+        size_t s = i, out = 0;
+        int too_long = 0;
+        while (i < n) {
+            adv = utf8_decode(t + i, n - i, &cp);
+            if (!cp_is_alnum(cp)) break;
+            if (out + 4 < sizeof(buf)) out += utf8_encode(cp_lower(cp), buf + out); else too_long = 1;
+            i += adv;
+        }
+        if (i - s >= 40 || too_long) continue; /* RemoveLongFilter::limit(40): keep len < 40 */
+        cb(ctx, buf, out);
     }
 }
 
@@ -288,8 +347,10 @@ uint32_t orc_bm25_search(const orc_bm25_index *ix, const char *sentence, const u
     tokenize(sentence, q_token, &q);
     if (q.n == 0 || ix->n_docs == 0 || topk == 0) return 0;
     float *score = (float *)calloc(ix->n_docs, sizeof(float));
-    uint32_t *hits = (uint32_t *)calloc(ix->n_docs, sizeof(uint32_t));
-    uint32_t n_clauses = 0;
+    /* tantivy's QueryParser builds AND over TERMS of (OR over the default fields): a document matches when every term
+     * is found in at least one of the searched fields */
+    uint64_t *hits = (uint64_t *)calloc(ix->n_docs, sizeof(uint64_t));
+    const uint64_t all_terms = q.n >= 64 ? ~0ull : ((1ull << q.n) - 1);
     for (uint32_t fq = 0; fq < n_fields_q; fq++) {
         uint32_t f = fields[fq];
         uint64_t N = stat_total_docs ? stat_total_docs : ix->n_docs;
@@ -299,7 +360,6 @@ uint32_t orc_bm25_search(const orc_bm25_index *ix, const char *sentence, const u
         for (int c = 0; c < 256; c++)
             cache[c] = BM25_K1 * (1.0f - BM25_B + BM25_B * (float)g_fieldnorm_table[c] / avgdl);
         for (int t = 0; t < q.n; t++) {
-            n_clauses++;
             int64_t ti = find_term(ix, f, q.toks[t], strlen(q.toks[t]));
             uint64_t n = stat_total_docs ? stat_doc_freq[fq * 64 + t] : (ti < 0 ? 0 : ix->terms[ti].n);
             if (ti < 0) continue;
@@ -312,7 +372,7 @@ uint32_t orc_bm25_search(const orc_bm25_index *ix, const char *sentence, const u
                 float tf = (float)e->p[i].tf;
                 int code = orc_bm25_fieldnorm_to_id(ix->doc_len[(size_t)f * ix->cap_docs + doc]);
                 score[doc] += weight * (tf / (tf + cache[code]));
-                hits[doc]++;
+                hits[doc] |= 1ull << t;
             }
         }
     }
@@ -320,7 +380,7 @@ uint32_t orc_bm25_search(const orc_bm25_index *ix, const char *sentence, const u
     uint32_t cnt = 0;
     for (uint32_t doc = 0; doc < ix->n_docs; doc++) {
         if (!hits[doc]) continue;
-        if (!operator_or && hits[doc] < n_clauses) continue;
+        if (!operator_or && hits[doc] != all_terms) continue;
         uint64_t rid = ix->row_id[doc];
         if (use_filter && alive && !((alive[rid >> 3] >> (rid & 7)) & 1)) continue;
         float s = score[doc];

@@ -107,3 +107,33 @@ def test_large_corpus_property_monotone_and_filter():
         assert (rows % 2 == 1).all()
         keep = [(r, s) for r, s in zip(r0.tolist(), s0.tolist()) if r % 2 == 1]
         assert list(zip(rows.tolist(), sc.tolist()))[:len(keep)] == keep  # filtering == masking the unfiltered ranking
+
+
+def test_tokenizer_unicode_long_tokens_and_multi_field_and_match_the_oracle(tmp_path):
+    """Same documents through the GPU index and the oracle: 40-byte tokens dropped, Unicode punctuation separates, non-ASCII
+    capitals are lowercased, AND over two columns = every term in at least one column; and a save / load round trip."""
+    docs = [["a" * 39 + " " + "b" * 40 + " tail", ""], ["alpha，beta—gamma delta", "ÉCOLE Ünïcode ПРИВЕТ"],
+            ["alpha only here", "beta only there"], ["alpha beta together", ""], ["gamma gamma gamma beta", "alpha"]]
+    g, o = b2.BM25Index(2), orc.BM25Index(2)
+    for i, dd in enumerate(docs):
+        g.add_doc(i, dd); o.add_doc(i, dd)
+    g.commit()
+    for term, f in (("a" * 39, 0), ("b" * 40, 0), ("alpha", 0), ("beta", 1), ("école", 1), ("привет", 1)):
+        assert g.doc_freq(term, f) == o.doc_freq(term, f), term
+    assert b2.BM25Index.query_terms("Alpha，BETA ÉCOLE") == orc.BM25Index.query_terms("Alpha，BETA ÉCOLE") == ["alpha", "beta", "école"]
+    g.save(tmp_path / "t.b2tx")
+    g2 = b2.BM25Index.load(tmp_path / "t.b2tx", 2)
+    for ix in (g, g2):
+        for sentence in ("alpha beta", "gamma alpha", "école alpha", "alpha nosuchterm", "beta"):
+            for fields in ((0, 1), (0,), (1,)):
+                for op_or in (True, False):
+                    rows, sc = ix.search(sentence, 10, fields=fields, operator_or=op_or)
+                    er, es = o.search(sentence, 10, fields=fields, operator_or=op_or)
+                    assert [int(r) for r in rows] == [int(r) for r in er], (sentence, fields, op_or)
+                    assert [float(s) for s in sc] == [float(s) for s in es], (sentence, fields, op_or)
+    with pytest.raises(b2.B200Error):
+        b2.BM25Index.load(tmp_path / "missing.b2tx", 2)
+    raw = (tmp_path / "t.b2tx").read_bytes()
+    (tmp_path / "cut.b2tx").write_bytes(raw[: len(raw) - 20])
+    with pytest.raises(b2.B200Error):
+        b2.BM25Index.load(tmp_path / "cut.b2tx", 2)

@@ -353,3 +353,29 @@ def test_00029_fallback_to_flat_cosine_small_distances(goldens):
     for exp in (g["expect"], g["expect_after_reload"]):
         assert ids[0].tolist() == [e[0] for e in exp]
         np.testing.assert_allclose(dis[0], [e[1] for e in exp], rtol=0, atol=2.4e-7)
+
+
+def test_bm25_tokenizer_and_multi_field_and_semantics():
+    """ADVICE r1: (1) RemoveLongFilter::limit(40) keeps tokens of fewer than 40 bytes; (2) SimpleTokenizer splits on every
+    non-alphanumeric CHAR, so Unicode punctuation / spaces separate tokens and LowerCaser lowercases non-ASCII letters;
+    (3) AND over several columns = every term found in at least one column (tantivy QueryParser), not every (column, term)."""
+    ix = orc.BM25Index(2)
+    ix.add_doc(0, ["a" * 39 + " " + "b" * 40 + " tail", ""])
+    ix.add_doc(1, ["alpha，beta—gamma delta", "ÉCOLE Ünïcode ПРИВЕТ"])
+    ix.add_doc(2, ["alpha only here", "beta only there"])
+    ix.add_doc(3, ["alpha beta together", ""])
+    assert ix.doc_freq("a" * 39, 0) == 1 and ix.doc_freq("b" * 40, 0) == 0 and ix.doc_len(0, 0) == 2
+    for t in ("alpha", "beta", "gamma", "delta"):
+        assert ix.doc_freq(t, 0) >= 1, t
+    assert ix.doc_len(1, 0) == 4
+    for t in ("école", "ünïcode", "привет"):
+        assert ix.doc_freq(t, 1) == 1, t
+    assert orc.BM25Index.query_terms("Alpha，BETA") == ["alpha", "beta"]
+    rows, _ = ix.search("alpha beta", 10, fields=(0, 1), operator_or=False)
+    assert sorted(int(r) for r in rows) == [1, 2, 3]      # doc 2 has alpha in column 0 and beta in column 1
+    rows, _ = ix.search("alpha beta", 10, fields=(0,), operator_or=False)
+    assert sorted(int(r) for r in rows) == [1, 3]
+    rows, _ = ix.search("alpha nosuchterm", 10, fields=(0, 1), operator_or=False)
+    assert len(rows) == 0
+    rows, _ = ix.search("alpha nosuchterm", 10, fields=(0, 1), operator_or=True)
+    assert sorted(int(r) for r in rows) == [1, 2, 3]

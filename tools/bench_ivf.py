@@ -103,6 +103,7 @@ def main():
     for i, off in enumerate(range(0, a.rows, CH)):
         m = min(CH, a.rows - off)
         x = chunk(i, m).contiguous()
+        torch.cuda.synchronize()   # adopt_device reads the rows on the corpus' own stream: they must be complete
         c = b2.Corpus(metric, a.dim)
         c.adopt_device(x.data_ptr(), m)
         c.search_device(q.data_ptr(), nt, a.k, od.data_ptr(), oi.data_ptr(), id_offset=off, stream=torch.cuda.current_stream().cuda_stream)
@@ -119,6 +120,16 @@ def main():
     truth_i = torch.gather(truth_i, 1, o).cpu().numpy()
     t_truth = time.perf_counter() - t0
 
+    sz = ix.list_sizes() if info["uses_ivf"] else np.zeros(1)
+    chk = {"phase": "check", "list_rows_min": int(sz.min()), "list_rows_max": int(sz.max()), "list_rows_mean": float(sz.mean()),
+           "empty_lists": int((sz == 0).sum())}
+    if a.keep_raw != 0:  # the truth must equal an exact pass over the index's own fp32 rows
+        ed = torch.empty((nt, a.k), dtype=torch.float32, device=dev); ei = torch.empty((nt, a.k), dtype=torch.int64, device=dev)
+        ix.search_device(q.data_ptr(), nt, a.k, ed.data_ptr(), ei.data_ptr(), "exact_batch=1", stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        ei = ei.cpu().numpy()
+        chk["truth_vs_index_rows_exact_pass"] = float(np.mean([len(set(ei[j].tolist()) & set(truth_i[j].tolist())) / a.k for j in range(nt)]))
+    print(json.dumps(chk), flush=True)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
