@@ -210,6 +210,7 @@ int b200_index_search_device(b200_index *ix, const float *d_queries, int64_t nq,
                              void *stream);
 /* roofline inputs of the list scan: CUDA-event time of the grouped scan kernel since the last reset, bytes per list row,
  * and an upper bound of the work items of the last search */
+int b200_index_phase_ms(b200_index *ix, double out_ms[5]);   /* last search: coarse | pairs+plan+gather | scan | merge | refine */
 int b200_index_list_sizes(const b200_index *ix, uint32_t *out_sizes /*[nlist]*/, int capacity);
 int b200_index_enable_timing(b200_index *ix, int on);
 int b200_index_last_scan(b200_index *ix, int64_t *rows_streamed, int64_t *payload_row_bytes, int64_t *work_items,

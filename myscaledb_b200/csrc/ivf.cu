@@ -818,9 +818,13 @@ struct b200_index {
     int64_t last_scan_rows = 0, last_items = 0;
     bool timing = false, timed_pending = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_ph[6] = {};      // phase boundaries of the last search: start | coarse | pairs+plan+gather | scan | merge | refine
+    double phase_ms[5] = {0, 0, 0, 0, 0};
     double timed_ms = 0;
     int64_t timed_launches = 0;
 };
+
+static void timing_collect(b200_index *ix);
 
 // internal hooks into capi.cu
 extern "C" int b200_corpus_search_device(b200_corpus *c, const float *d_queries, int64_t nq, int k, const uint8_t *d_alive_bits,
@@ -911,6 +915,8 @@ extern "C" int b200_index_free(b200_index *ix) {
         a->release();
     if (ix->ev0) cudaEventDestroy(ix->ev0);
     if (ix->ev1) cudaEventDestroy(ix->ev1);
+    for (auto &e : ix->ev_ph)
+        if (e) cudaEventDestroy(e);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
     return B200_OK;
@@ -1416,8 +1422,6 @@ extern "C" int b200_index_info(const b200_index *ix, int64_t *n, int *nlist, int
     return B200_OK;
 }
 
-static void timing_collect(b200_index *ix);
-
 extern "C" int b200_index_last_scan(b200_index *ix, int64_t *rows_streamed, int64_t *payload_row_bytes_out, int64_t *work_items,
                                     double *kernel_ms_total, int64_t *kernel_launches, int reset) {
     if (!ix) return fail(B200_ERR_INVALID, "null index");
@@ -1440,6 +1444,17 @@ extern "C" int b200_index_last_scan(b200_index *ix, int64_t *rows_streamed, int6
     return B200_OK;
 }
 
+// milliseconds of the phases of the LAST list search (timing enabled): coarse probe | pair sort + plan + query gather |
+// grouped scan | per-query merge | exact second stage
+extern "C" int b200_index_phase_ms(b200_index *ix, double out_ms[5]) {
+    if (!ix || !out_ms) return fail(B200_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    cudaSetDevice(ix->device);
+    timing_collect(ix);
+    for (int i = 0; i < 5; i++) out_ms[i] = ix->phase_ms[i];
+    return B200_OK;
+}
+
 // rows per inverted list (diagnostics: balance of the coarse quantiser); out_sizes[nlist]
 extern "C" int b200_index_list_sizes(const b200_index *ix, uint32_t *out_sizes, int capacity) {
     if (!ix || !out_sizes) return fail(B200_ERR_INVALID, "bad arguments");
@@ -1456,6 +1471,7 @@ extern "C" int b200_index_enable_timing(b200_index *ix, int on) {
     if (on && !ix->ev0) {
         cudaEventCreate(&ix->ev0);
         cudaEventCreate(&ix->ev1);
+        for (auto &e : ix->ev_ph) cudaEventCreate(&e);
     }
     return B200_OK;
 }
@@ -1532,6 +1548,7 @@ static int search_device_locked(b200_index *ix, const float *d_queries, int64_t 
     const int64_t n_pairs = nq * nprobe;
     if (n_pairs >= (int64_t)1 << 31) return fail(B200_ERR_UNSUPPORTED, "nq * nprobe must stay below 2^31");
 
+    if (ix->timing) cudaEventRecord(ix->ev_ph[0], s);
     // ---- coarse probe: nprobe nearest centroids per query (exact FLAT search of the centroid table)
     B200_TRY(ix->w_qraw.reserve((size_t)nq * ix->d * 4));
     B200_TRY(ix->w_probe.reserve((size_t)n_pairs * 8));
@@ -1540,6 +1557,7 @@ static int search_device_locked(b200_index *ix, const float *d_queries, int64_t 
     else B200_CUDA_OK(cudaMemcpy2DAsync(ix->w_qraw.p, (size_t)ix->d * 4, d_q, (size_t)ix->d_pad * 4, (size_t)ix->d * 4, nq, cudaMemcpyDeviceToDevice, s));
     B200_TRY(b200_corpus_search_device(ix->coarse, ix->w_qraw.as<float>(), nq, nprobe, nullptr, 0, ix->w_pd.as<float>(), ix->w_probe.as<int64_t>(), s));
 
+    if (ix->timing) cudaEventRecord(ix->ev_ph[1], s);
     // ---- pairs sorted by list
     B200_TRY(ix->w_u32a.reserve((size_t)n_pairs * 4));
     B200_TRY(ix->w_u32b.reserve((size_t)n_pairs * 4));
@@ -1665,10 +1683,14 @@ static int search_device_locked(b200_index *ix, const float *d_queries, int64_t 
         gp.list_ids_gmem = ix->w_li.as<uint32_t>();
     }
     const char *detail = nullptr;
-    if (ix->timing) cudaEventRecord(ix->ev0, s);
+    if (ix->timing) {
+        cudaEventRecord(ix->ev_ph[2], s);
+        cudaEventRecord(ix->ev0, s);
+    }
     cudaError_t e = launch_ivf_gemm_topk(gp, ix->w_qbuf.p, n_pairs + 128, ix->d_pool, (int64_t)ix->pool_pages * kPageRows, grid, s, &detail);
     if (ix->timing) {
         cudaEventRecord(ix->ev1, s);
+        cudaEventRecord(ix->ev_ph[3], s);
         ix->timed_pending = true;
     }
     if (e != cudaSuccess) return fail(B200_ERR_CUDA, std::string("ivf_gemm_topk launch: ") + (detail ? detail : cudaGetErrorString(e)));
@@ -1707,7 +1729,9 @@ static int search_device_locked(b200_index *ix, const float *d_queries, int64_t 
         g_launches++;
         B200_CUDA_OK(cudaGetLastError());
     }
+    if (ix->timing) cudaEventRecord(ix->ev_ph[4], s);
     if (two_stage) B200_TRY(refine_device(ix, d_q, nq, m_ids, k1, k, id_offset, d_out_dis, d_out_ids, s));
+    if (ix->timing) cudaEventRecord(ix->ev_ph[5], s);
     return B200_OK;
 }
 
@@ -1718,6 +1742,11 @@ static void timing_collect(b200_index *ix) {
         ix->timed_ms += ms;
         ix->timed_launches++;
     }
+    if (cudaEventSynchronize(ix->ev_ph[5]) == cudaSuccess)
+        for (int i = 0; i < 5; i++) {
+            float pm = 0;
+            if (cudaEventElapsedTime(&pm, ix->ev_ph[i], ix->ev_ph[i + 1]) == cudaSuccess) ix->phase_ms[i] = pm;
+        }
     ix->timed_pending = false;
 }
 

@@ -38,7 +38,7 @@ struct IvfGemmParams {
     const void *codebook_bf16;        // PQ: [m][256][dsub] bf16
     int code_bytes, m, dsub, codebook_bytes;
     // filled in by the launcher
-    int stages, lists_in_smem, codebook_smem_off;
+    int stages, lists_in_smem, codebook_smem_off, coop_smem_off, coop_enabled;
 };
 
 // queries_bf16: gathered query rows [n_query_rows][d_pad] (bf16); pool_bf16: page pool [pool_rows][d_pad] (bf16 payload only)

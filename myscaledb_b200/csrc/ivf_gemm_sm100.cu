@@ -32,6 +32,72 @@ constexpr int IVF_THREADS_TMA = 192;       // producer, issuer, 4 epilogue warps
 constexpr int IVF_DEC_WARPS = 4;           // extra decoder warps of the code payloads
 constexpr int IVF_THREADS_DEC = IVF_THREADS_TMA + IVF_DEC_WARPS * 32;
 
+// Items with only a few queries (the usual case for small batches: every probed list is visited by one or two queries)
+// would leave all the top-k work to one or two lanes of the per-thread scheme, and every item starts with an empty list
+// ("insert storm": ~k ln(rows / k) inserts per item, each a rescan of the lane's k slots).  For q_count <= kCoopMax the
+// WARP keeps one sorted list per query slot in shared memory instead and inserts cooperatively (WarpTopKT: rank by
+// ballot / popc, shift by 32 lanes at a time): measured 190 us -> ~10 us per item at k = 40.
+constexpr int kCoopMax = 8;
+
+struct CoopState {   // one per query slot, in shared memory
+    float thr_key;
+    uint32_t thr_id;
+    int n;
+    int pad;
+};
+
+// One 32-column chunk in cooperative mode.  `thr` is this lane's own slot threshold (-FLT_MAX for lanes without a query).
+__device__ __forceinline__ void epilogue_chunk_coop(float &thr, float (&v)[32], const float *scale, const float *bias, uint32_t id0,
+                                                    float *scratch_warp /* lane 0's scratch column */, int lane, int q_count,
+                                                    float *coop_keys, uint32_t *coop_ids, CoopState *coop_state, int k) {
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = fmaf(v[j], scale[j], bias[j]);
+    float m0 = fminf(v[0], v[1]), m1 = fminf(v[2], v[3]), m2 = fminf(v[4], v[5]), m3 = fminf(v[6], v[7]);
+#pragma unroll
+    for (int j = 8; j < 32; j += 8) {
+        m0 = fminf(m0, fminf(v[j], v[j + 1]));
+        m1 = fminf(m1, fminf(v[j + 2], v[j + 3]));
+        m2 = fminf(m2, fminf(v[j + 4], v[j + 5]));
+        m3 = fminf(m3, fminf(v[j + 6], v[j + 7]));
+    }
+    const bool mine = fminf(fminf(m0, m1), fminf(m2, m3)) <= thr;
+    unsigned pending = __ballot_sync(0xffffffffu, mine);
+    if (!pending) return;
+    // lanes with a candidate park their 32 keys in their scratch column
+    if (mine) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) scratch_warp[j * EPI_THREADS + lane] = v[j];
+    }
+    __syncwarp();
+    while (pending) {
+        const int s = __ffs(pending) - 1;   // query slot = lane s of this warp
+        pending &= pending - 1;
+        if (s >= q_count) continue;
+        WarpTopK L;
+        L.keys = coop_keys + (size_t)s * k;
+        L.ids = coop_ids + (size_t)s * k;
+        L.k = k;
+        L.n = coop_state[s].n;
+        L.thr_key = coop_state[s].thr_key;
+        L.thr_id = coop_state[s].thr_id;
+        const float key = scratch_warp[lane * EPI_THREADS + s];   // column (row of the page) `lane` of slot s
+        const uint32_t id = id0 + (uint32_t)lane;
+        unsigned m = __ballot_sync(0xffffffffu, L.passes(key, id));
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            L.insert(__shfl_sync(0xffffffffu, key, src), __shfl_sync(0xffffffffu, id, src));
+        }
+        if (lane == 0) {
+            coop_state[s].n = L.n;
+            coop_state[s].thr_key = L.thr_key;
+            coop_state[s].thr_id = L.thr_id;
+        }
+        if (lane == s) thr = L.thr_key;
+        __syncwarp();
+    }
+}
+
 // smem (PRODUCER_TMA): the Cfg<1> layout of ip_gemm_sm100.cu.  Code payloads add a codebook region behind the lists.
 template <int PRODUCER, int DSUB>
 __global__ void __launch_bounds__(PRODUCER == IVF_PRODUCER_TMA ? IVF_THREADS_TMA : IVF_THREADS_DEC, 1)
@@ -163,14 +229,29 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             list.keys = p.list_keys_gmem + (size_t)blockIdx.x * p.k * EPI_THREADS + row;
             list.ids = p.list_ids_gmem + (size_t)blockIdx.x * p.k * EPI_THREADS + row;
         }
+        // cooperative lists (items with <= kCoopMax queries): [kCoopMax][k] keys + ids + state, owned by the warp of TMEM lanes 0..31
+        float *coop_keys = reinterpret_cast<float *>(smem + p.coop_smem_off);
+        uint32_t *coop_ids = reinterpret_cast<uint32_t *>(coop_keys + (size_t)kCoopMax * p.k);
+        CoopState *coop_state = reinterpret_cast<CoopState *>(coop_ids + (size_t)kCoopMax * p.k);
+        float *scratch_warp = scratch - lane;
         int as = 0;
         uint32_t aphase = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
             const IvfGemmItem item = p.items[it];
+            const bool coop = p.coop_enabled && item.q_count <= (uint32_t)kCoopMax;
             list.n = 0;
             list.worst = 0;
             list.thr_key = ((uint32_t)row < item.q_count) ? FLT_MAX : -FLT_MAX;   // padding slots never enter the slow path
             list.thr_id = 0;
+            float coop_thr = list.thr_key;
+            if (coop && quarter == 0) {
+                if (lane < kCoopMax) {
+                    coop_state[lane].n = 0;
+                    coop_state[lane].thr_key = FLT_MAX;
+                    coop_state[lane].thr_id = 0;
+                }
+                __syncwarp();
+            }
             for (uint32_t j = 0; j < item.page_count; j++) {
                 const uint32_t page = p.list_pages[item.page_begin + j];
                 const uint32_t row0 = page * (uint32_t)BN;
@@ -197,12 +278,16 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 for (int chunk = 0; chunk < BN / 32; chunk += 2) {
                     __syncwarp();
                     tmem_ld32_issue(taddr + (chunk + 1) * 32, vb);
-                    epilogue_chunk(list, va, true, side_scale + chunk * 32, side_bias + chunk * 32, row0 + chunk * 32, false, 0, scratch);
+                    if (coop) epilogue_chunk_coop(coop_thr, va, side_scale + chunk * 32, side_bias + chunk * 32, row0 + chunk * 32, scratch_warp, lane,
+                                                  quarter == 0 ? (int)item.q_count : 0, coop_keys, coop_ids, coop_state, p.k);
+                    else epilogue_chunk(list, va, true, side_scale + chunk * 32, side_bias + chunk * 32, row0 + chunk * 32, false, 0, scratch);
                     tmem_ld_wait();
                     __syncwarp();
                     if (chunk + 2 < BN / 32) tmem_ld32_issue(taddr + (chunk + 2) * 32, va);
-                    epilogue_chunk(list, vb, true, side_scale + (chunk + 1) * 32, side_bias + (chunk + 1) * 32,
-                                   row0 + (chunk + 1) * 32, false, 0, scratch);
+                    if (coop) epilogue_chunk_coop(coop_thr, vb, side_scale + (chunk + 1) * 32, side_bias + (chunk + 1) * 32, row0 + (chunk + 1) * 32,
+                                                  scratch_warp, lane, quarter == 0 ? (int)item.q_count : 0, coop_keys, coop_ids, coop_state, p.k);
+                    else epilogue_chunk(list, vb, true, side_scale + (chunk + 1) * 32, side_bias + (chunk + 1) * 32,
+                                        row0 + (chunk + 1) * 32, false, 0, scratch);
                     tmem_ld_wait();
                 }
                 tc_fence_before();
@@ -213,8 +298,23 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                     aphase ^= 1;
                 }
             }
-            // publish this (item, query slot)'s partial list: unsorted, pool rows mapped to row ids, worst kept key aside
-            if ((uint32_t)row < item.q_count) {
+            // publish this (item, query slot)'s partial list: pool rows mapped to row ids, worst kept key aside
+            if (coop) {
+                if (quarter == 0) {
+                    __syncwarp();
+                    for (uint32_t sl = 0; sl < item.q_count; sl++) {
+                        const size_t part = (size_t)p.pair_part_base[item.q_begin + sl] + item.chunk;
+                        const int n = coop_state[sl].n;
+                        for (int e = lane; e < p.k; e += 32) {
+                            const bool have = e < n;
+                            p.part_keys[part * p.k + e] = have ? coop_keys[(size_t)sl * p.k + e] : FLT_MAX;
+                            p.part_ids[part * p.k + e] = have ? p.row_ids[coop_ids[(size_t)sl * p.k + e]] : kNoId;
+                        }
+                        if (lane == 0) p.part_worst[part] = n == p.k ? coop_state[sl].thr_key : FLT_MAX;
+                    }
+                    __syncwarp();
+                }
+            } else if ((uint32_t)row < item.q_count) {
                 const size_t part = (size_t)p.pair_part_base[item.q_begin + row] + item.chunk;
                 float *ok = p.part_keys + part * p.k;
                 uint32_t *oi = p.part_ids + part * p.k;
@@ -349,12 +449,18 @@ static cudaError_t launch_ivf(const CUtensorMap &map_q, const CUtensorMap &map_c
     auto need = [&](int st, int k_smem) { return Cfg<1>::off_list(st) + k_smem * EPI_THREADS * 8 + extra + SMEM_ALIGN_SLACK; };
     while (stages > 2 && need(stages, 0) > 232448) stages--;
     if (need(stages, 0) > 232448) return cudaErrorInvalidValue;
-    p.lists_in_smem = (p.k <= kGemmSmemK && need(stages, p.k) <= 232448) ? 1 : 0;
+    // cooperative lists: kCoopMax x k x 8 bytes + state, always in shared memory (k <= 512); they come first, the per-thread
+    // lists (for items with many queries) use what is left or global scratch
+    const int coop_bytes = p.k <= 512 ? (int)round_up((size_t)kCoopMax * p.k * 8 + kCoopMax * sizeof(CoopState), 16) : 0;
+    p.coop_enabled = coop_bytes > 0 && need(2, 0) + coop_bytes <= 232448 ? 1 : 0;
+    const int coop_used = p.coop_enabled ? coop_bytes : 0;
+    while (stages > 2 && need(stages, 0) + coop_used > 232448) stages--;
+    p.lists_in_smem = (p.k <= kGemmSmemK && need(stages, p.k) + coop_used <= 232448) ? 1 : 0;
     p.stages = stages;
     const int k_smem = p.lists_in_smem ? p.k : 0;
-    p.codebook_smem_off = Cfg<1>::off_list(stages) + k_smem * EPI_THREADS * 8;
-    p.codebook_smem_off = (int)round_up(p.codebook_smem_off, 16);
-    const size_t smem = (size_t)need(stages, k_smem) + 16;
+    p.coop_smem_off = (int)round_up(Cfg<1>::off_list(stages) + k_smem * EPI_THREADS * 8, 16);
+    p.codebook_smem_off = (int)round_up(p.coop_smem_off + coop_used, 16);
+    const size_t smem = (size_t)need(stages, k_smem) + coop_used + 48;
     auto kern = ivf_gemm_topk_kernel<PRODUCER, DSUB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -388,6 +388,11 @@ class VectorIndex:
                                           C.c_int(1 if reset else 0)))
         return dict(rows_streamed=rows.value, payload_row_bytes=rb.value, work_items=items.value, kernel_ms=ms.value, launches=nl.value)
 
+    def phase_ms(self):
+        a = (C.c_double * 5)()
+        _check(lib().b200_index_phase_ms(self._h, a))
+        return dict(zip(("coarse", "plan", "scan", "merge", "refine"), [round(v, 4) for v in a]))
+
     def list_sizes(self):
         nl = self.info()["nlist"]
         out = np.zeros(nl, np.uint32)

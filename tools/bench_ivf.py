@@ -161,7 +161,7 @@ def main():
                           "qps": round(a.nq / ms * 1e3), "recall": round(rec, 4), "scan_kernel_ms": round(kms, 3),
                           "scan_GB": round(gb, 3), "scan_GB_per_s": round(gb / kms * 1e3) if kms else None,
                           "frac_hbm": round(gb / kms * 1e3 / hbm, 3) if kms else None, "bytes_per_query": round(gb * 1e9 / a.nq),
-                          "work_items_bound": sc["work_items"]}), flush=True)
+                          "work_items_bound": sc["work_items"], "phase_ms": ix.phase_ms()}), flush=True)
     print(json.dumps({"phase": "truth", "seconds": round(t_truth, 1), "queries": nt}))
 
 
