@@ -53,11 +53,12 @@ def test_compute_fails_loudly_without_gpu():
         b2.Corpus(b2.IP, 64)
 
 
-def test_cpp_shim_compiles_and_links_against_the_c_abi():
-    """shim/b200_search_shim.hpp presents Search:: / faiss:: / TANTIVY:: and forwards to the C ABI."""
-    exe = os.path.join(ROOT, "tests", "cpp", "shim_smoke")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
-                           "-I" + os.path.join(ROOT, "shim"), os.path.join(ROOT, "tests", "cpp", "shim_smoke.cpp"), "-o", exe,
+def test_reference_call_sites_compile_against_the_shim():
+    """tests/cpp/callsite_compile.cpp pastes the call expressions of VIWithDataPart.cpp / BruteForceSearch.h /
+    TantivyIndexStore.cpp; it must compile with -Werror against shim/b200_search_shim.hpp and link against the C ABI."""
+    exe = os.path.join(ROOT, "tests", "cpp", "callsite_compile")
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           "-I" + os.path.join(ROOT, "shim"), os.path.join(ROOT, "tests", "cpp", "callsite_compile.cpp"), "-o", exe,
                            "-L" + os.path.join(ROOT, "myscaledb_b200"), "-lb200search",
                            "-Wl,-rpath,$ORIGIN/../../myscaledb_b200"])
     assert os.path.exists(exe)

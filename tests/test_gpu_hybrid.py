@@ -89,13 +89,14 @@ def test_random_lists_match_oracle_bitexact(ft, direction):
         assert [(a, b, c, float(F32(d))) for a, b, c, d in got[q]] == [(a, b, c, float(F32(d))) for a, b, c, d in exp], q
 
 
-def test_cpp_shim_runs_on_gpu():
-    """The reference-side C++ binding (Search::VectorIndex, faiss::knn_L2sqr, TANTIVY::ffi_*) end to end."""
+def test_reference_call_sites_run_on_gpu():
+    """The reference's own call expressions (createVectorIndex, reader-driven build, search with a filter, serialize / load
+    through the stream classes, computeTopDistanceSubset, faiss::knn_*, TANTIVY::ffi_*) end to end on the GPU."""
     import os
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    exe = os.path.join(root, "tests", "cpp", "shim_smoke")
+    exe = os.path.join(root, "tests", "cpp", "callsite_compile")
     if not os.path.exists(exe):
-        pytest.skip("shim_smoke not built (run __graft_entry__.build())")
+        pytest.skip("callsite_compile not built (run __graft_entry__.build())")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
-    assert r.returncode == 0 and "SHIM OK" in r.stdout, r.stdout + r.stderr
+    assert r.returncode == 0 and "CALLSITES OK" in r.stdout, r.stdout + r.stderr
