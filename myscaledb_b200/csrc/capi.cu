@@ -101,6 +101,12 @@ struct b200_corpus {
     // workspaces
     DevBuf w_raw, w_q32, w_qbf, w_qlo, w_qnorm, w_pk, w_pi, w_lk, w_li, w_alive, w_odis, w_oids, w_stage, w_prog;
     int sync_slack = 2;
+    // fused single-launch path of the host entry point (small batches, scan kernel): mapped pinned staging + counters
+    void *h_pin = nullptr;         // [queries 8 * d fp32 | dis 8 * k | ids 8 * k | flag]
+    size_t h_pin_bytes = 0;
+    unsigned int *d_tickets = nullptr;   // [8] + tiles_done
+    unsigned int fused_seq = 0;
+    int fused_enabled = 1;         // B200_FUSED_SCAN=0 disables (A/B)
     int rescore_l2 = 1;      // tensor-core L2: re-score the k winners exactly (B200_GEMM_RESCORE_L2=0 disables, A/B only)
     int gemm_multicast = 1;  // CTA pairs per cluster sharing each corpus tile: 1 auto (4, else 2), 2, 4; B200_GEMM_MULTICAST=0 disables
     int gemm_ts = 0;  // 0 streaming (default: faster at every measured d), 1 TS when d_pad <= 512, 2 TS whenever it fits
@@ -238,6 +244,7 @@ extern "C" int b200_corpus_create(int metric, int dtype, int d, int64_t capacity
     c->sms = num_sms();
     if (const char *ev = getenv("B200_GEMM_SYNC_SLACK")) c->sync_slack = atoi(ev);
     if (const char *ev = getenv("B200_GEMM_RESCORE_L2")) c->rescore_l2 = atoi(ev);
+    if (const char *ev = getenv("B200_FUSED_SCAN")) c->fused_enabled = atoi(ev);
     if (const char *ev = getenv("B200_GEMM_TS")) c->gemm_ts = atoi(ev);
     if (const char *ev = getenv("B200_GEMM_MULTICAST")) c->gemm_multicast = atoi(ev);
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -420,6 +427,8 @@ extern "C" int b200_corpus_free(b200_corpus *c) {
     if (c->data && c->owns) cudaFree(c->data);
     if (c->row_scale) cudaFree(c->row_scale);
     if (c->row_bias) cudaFree(c->row_bias);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->d_tickets) cudaFree(c->d_tickets);
     for (DevBuf *b : {&c->w_raw, &c->w_q32, &c->w_qbf, &c->w_qlo, &c->w_qnorm, &c->w_pk, &c->w_pi, &c->w_lk, &c->w_li, &c->w_alive,
                       &c->w_odis, &c->w_oids, &c->w_stage, &c->w_prog})
         b->release();
@@ -698,6 +707,121 @@ extern "C" int b200_corpus_search_device(b200_corpus *c, const float *d_queries,
     return B200_OK;
 }
 
+// One launch per call for small batches that go to the scan kernel (the reference's usual shape: one query x many parts from a
+// ThreadPool, MergeTreeSelectWithHybridSearchProcessor.cpp:1212-1241).  The query is written to mapped pinned memory and
+// read by the kernel directly, the last block to finish merges the partial lists and writes the result to mapped pinned
+// memory, the host waits on a flag in that memory: no pad / merge launches, no H2D / D2H copies, no stream synchronise
+// (round 1: 103 us per resident call against a 16 us kernel).
+static int search_host_fused(b200_corpus *c, const float *queries, int64_t nq, int k, const uint8_t *alive_bits, int ip_min_quirk,
+                             float *out_dis, int64_t *out_ids, bool *done) {
+    *done = false;
+    if (!c->fused_enabled || c->dtype == B200_DTYPE_BIN || nq > 8 || k > 1024 || c->n == 0) return B200_OK;
+    int path = c->path;
+    if (path == 0) {
+        const int64_t min_nq = c->metric == B200_METRIC_L2 ? 20 : (c->dtype == B200_DTYPE_BF16 ? 2 : 5);
+        path = (nq >= min_nq) ? 2 : 1;
+    }
+    if (path != 1) return B200_OK;
+    int qt = nq == 1 ? 1 : nq <= 4 ? 4 : 8;
+    while (qt > 1 && scan_smem_bytes(qt, c->d_pad, k) > 100 * 1024) qt = qt == 8 ? 4 : 1;
+    if (scan_smem_bytes(qt, c->d_pad, k) > 200 * 1024) return B200_OK;   // the staged path reports the error
+    cudaStream_t s = c->stream;
+    const size_t need = (size_t)8 * c->d * 4 + (size_t)8 * k * 12 + 64;
+    if (need > c->h_pin_bytes) {
+        if (c->h_pin) cudaFreeHost(c->h_pin);
+        c->h_pin = nullptr;
+        c->h_pin_bytes = 0;
+        if (cudaHostAlloc(&c->h_pin, need, cudaHostAllocMapped) != cudaSuccess) {
+            cudaGetLastError();
+            return B200_OK;   // no pinned memory: the staged path still works
+        }
+        c->h_pin_bytes = need;
+    }
+    if (!c->d_tickets) {
+        B200_CUDA_OK(cudaMalloc(&c->d_tickets, 16 * 4));
+        B200_CUDA_OK(cudaMemsetAsync(c->d_tickets, 0, 16 * 4, s));
+    }
+    char *hp = reinterpret_cast<char *>(c->h_pin);
+    float *h_q = reinterpret_cast<float *>(hp);
+    float *h_dis = reinterpret_cast<float *>(hp + (size_t)8 * c->d * 4);
+    int64_t *h_ids = reinterpret_cast<int64_t *>(hp + (size_t)8 * c->d * 4 + (size_t)round_up(8 * k * 4, 8));
+    volatile unsigned int *h_flag = reinterpret_cast<volatile unsigned int *>(hp + need - 16);
+    void *dp = nullptr;
+    B200_CUDA_OK(cudaHostGetDevicePointer(&dp, c->h_pin, 0));
+    char *dpc = reinterpret_cast<char *>(dp);
+    memcpy(h_q, queries, (size_t)nq * c->d * 4);
+    const uint8_t *d_alive = nullptr;
+    if (alive_bits) {
+        const size_t ab = (size_t)ceil_div(c->n, 8);
+        B200_TRY(c->w_alive.reserve(ab + 16));
+        B200_CUDA_OK(cudaMemcpyAsync(c->w_alive.p, alive_bits, ab, cudaMemcpyHostToDevice, s));
+        d_alive = c->w_alive.as<uint8_t>();
+    }
+    const int elems = c->dtype == B200_DTYPE_BF16 ? 8 : 4;
+    const int chunks = c->d_pad / elems;
+    int group = 1;
+    while (group < 32 && group < chunks) group <<= 1;
+    const int64_t y_tiles = ceil_div(nq, qt);
+    const int64_t rows_per_block_step = 8 * (32 / group);
+    int64_t bx = std::max<int64_t>(1, (2 * c->sms) / std::min<int64_t>(y_tiles, 2 * c->sms));
+    bx = std::min<int64_t>(bx, std::max<int64_t>(1, ceil_div(c->n, rows_per_block_step * 4)));
+    const int blocks_x = (int)bx;
+    B200_TRY(c->w_pk.reserve((size_t)nq * blocks_x * k * 4));
+    B200_TRY(c->w_pi.reserve((size_t)nq * blocks_x * k * 4));
+    ScanParams sp{};
+    sp.corpus = c->data;
+    sp.queries = reinterpret_cast<const float *>(dpc);
+    sp.row_scale = c->metric == B200_METRIC_COSINE ? c->row_scale : nullptr;
+    sp.alive = d_alive;
+    sp.part_keys = c->w_pk.as<float>();
+    sp.part_ids = c->w_pi.as<uint32_t>();
+    sp.n = c->n;
+    sp.nq = nq;
+    sp.row_bytes = c->row_bytes;
+    sp.d_pad = c->d_pad;
+    sp.k = k;
+    sp.group = group;
+    sp.l2 = c->metric == B200_METRIC_L2;
+    sp.bf16 = c->dtype == B200_DTYPE_BF16;
+    sp.fused = 1;
+    sp.q_dim = c->d;
+    sp.cosine = c->metric == B200_METRIC_COSINE;
+    sp.out_mode = c->metric == B200_METRIC_L2 ? kOutKey : c->metric == B200_METRIC_IP ? kOutNeg : kOutOnePlus;
+    sp.ip_min_quirk = ip_min_quirk && c->metric == B200_METRIC_IP;
+    sp.id_offset = 0;
+    sp.tickets = c->d_tickets;
+    sp.tiles_done = c->d_tickets + 8;
+    sp.out_dis = reinterpret_cast<float *>(dpc + (reinterpret_cast<char *>(h_dis) - hp));
+    sp.out_ids = reinterpret_cast<int64_t *>(dpc + (reinterpret_cast<char *>(h_ids) - hp));
+    sp.done_flag = reinterpret_cast<volatile unsigned int *>(dpc + need - 16);
+    sp.done_value = ++c->fused_seq ? c->fused_seq : ++c->fused_seq;   // never 0
+    *h_flag = 0;
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    timing_begin(c, s, ev);
+    B200_CUDA_OK(launch_flat_scan(sp, qt, blocks_x, s));
+    timing_end(c, s, ev);
+    c->last_kernel = B200_KERNEL_SCAN; c->last_cg = 0; c->last_mc = 0; c->last_grid = blocks_x;
+    // wait for the flag; look at the stream now and then so that a failed launch cannot hang the caller
+    for (uint64_t spin = 1;; spin++) {
+        if (*h_flag == sp.done_value) break;
+        if ((spin & 0x3fff) == 0) {
+            const cudaError_t qe = cudaStreamQuery(s);
+            if (qe == cudaSuccess) {
+                if (*h_flag == sp.done_value) break;
+                return fail(B200_ERR_CUDA, "fused scan finished without publishing its result");
+            }
+            if (qe != cudaErrorNotReady) return fail(B200_ERR_CUDA, std::string("fused scan: ") + cudaGetErrorString(qe));
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    memcpy(out_dis, h_dis, (size_t)nq * k * 4);
+    memcpy(out_ids, h_ids, (size_t)nq * k * 8);
+    *done = true;
+    return B200_OK;
+}
+
 static int search_host(b200_corpus *c, const void *queries, int64_t nq, int k, const uint8_t *alive_bits, int ip_min_quirk,
                        float *out_dis, int64_t *out_ids) {
     if (!c || (!queries && nq > 0) || !out_dis || !out_ids || nq < 0 || k <= 0)
@@ -705,6 +829,11 @@ static int search_host(b200_corpus *c, const void *queries, int64_t nq, int k, c
     if (nq == 0) return B200_OK;
     std::lock_guard<std::mutex> lk(c->mu);
     B200_CUDA_OK(cudaSetDevice(c->device));
+    {
+        bool done = false;
+        B200_TRY(search_host_fused(c, reinterpret_cast<const float *>(queries), nq, k, alive_bits, ip_min_quirk, out_dis, out_ids, &done));
+        if (done) return B200_OK;
+    }
     cudaStream_t s = c->stream;
     const size_t q_bytes = c->dtype == B200_DTYPE_BIN ? (size_t)nq * c->d_pad : (size_t)nq * c->d * 4;
     B200_TRY(c->w_stage.reserve(q_bytes));

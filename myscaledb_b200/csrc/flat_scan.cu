@@ -10,6 +10,8 @@
 // K7     topk_merge_kernel : merges P sorted lists per query; replaces the running merge
 //        in searchWrapper (MergeTreeVSManager.cpp:1652-1678) and the multimap merge in
 //        getTotalTopSearchResultImpl (MergeTreeBaseSearchManager.cpp:207-299).
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanPa
     // 16-byte words (a single 32-byte-strided array costs a 2-way bank conflict on every LDS.128).
     for (int i = threadIdx.x; i < QT * p.d_pad; i += kScanThreads) {
         const int q = i / p.d_pad, j = i - q * p.d_pad;
-        const float v = (q < nq_here) ? p.queries[(q0 + q) * p.d_pad + j] : 0.f;
+        const float v = (q < nq_here) ? (p.fused ? (j < p.q_dim ? p.queries[(q0 + q) * p.q_dim + j] : 0.f) : p.queries[(q0 + q) * p.d_pad + j]) : 0.f;
         if (E == 8) {
             const int c = j >> 3, e = j & 7;
             qs[q * p.d_pad + (e >> 2) * (p.d_pad >> 1) + c * 4 + (e & 3)] = v;
@@ -84,6 +86,20 @@ __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanPa
         for (int j = lane; j < p.k; j += 32) lists[q].keys[j] = FLT_MAX;  // sentinel for the block merge
     }
     __syncthreads();
+    if (p.fused && p.cosine) {
+        // VectorDataset::normalize on the staged queries (VectorDataset.h:99-117): one warp per query
+        for (int q = warp; q < nq_here; q += kScanWarps) {
+            float ss = 0.f;
+            for (int j = lane; j < p.d_pad; j += 32) ss = fmaf(qs[q * p.d_pad + j], qs[q * p.d_pad + j], ss);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            if (!(ss < FLT_EPSILON)) {
+                const float nrm = sqrtf(ss);
+                for (int j = lane; j < p.d_pad; j += 32) qs[q * p.d_pad + j] = qs[q * p.d_pad + j] / nrm;
+            }
+        }
+        __syncthreads();
+    }
 
     const int G = p.group;           // lanes per row (power of two)
     const int R = 32 / G;            // rows per warp step
@@ -185,6 +201,82 @@ __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanPa
         block_rank_merge(lk + (size_t)q * p.k, li + (size_t)q * p.k, kScanWarps, QT * p.k, p.k,
                          p.part_keys + ((q0 + q) * (int64_t)gridDim.x + blockIdx.x) * p.k,
                          p.part_ids + ((q0 + q) * (int64_t)gridDim.x + blockIdx.x) * p.k);
+    if (!p.fused) return;
+    // ---- fused form: the last block of this query tile merges the gridDim.x partial lists of each of its queries
+    __shared__ unsigned int s_ticket;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&p.tickets[blockIdx.y], 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    __threadfence();
+    // the staging area is free now: [warps][k] keys + ids, merged list behind it (launch reserves (warps + 1) * k * 8 bytes)
+    float *mk = reinterpret_cast<float *>(smem_raw);
+    uint32_t *mi = reinterpret_cast<uint32_t *>(mk + (size_t)kScanWarps * p.k);
+    float *fk = reinterpret_cast<float *>(mi + (size_t)kScanWarps * p.k);
+    uint32_t *fi = reinterpret_cast<uint32_t *>(fk + p.k);
+    for (int q = 0; q < nq_here; q++) {
+        __syncthreads();
+        WarpTopK list;
+        list.init(mk + (size_t)warp * p.k, mi + (size_t)warp * p.k, p.k);
+        for (int j = lane; j < p.k; j += 32) list.keys[j] = FLT_MAX;
+        __syncwarp();
+        const float *pkeys = p.part_keys + (q0 + q) * (int64_t)gridDim.x * p.k;
+        const uint32_t *pids = p.part_ids + (q0 + q) * (int64_t)gridDim.x * p.k;
+        const int64_t ncand = (int64_t)gridDim.x * p.k;
+        for (int64_t c0 = (int64_t)warp * 32; c0 < ncand; c0 += kScanThreads) {
+            const int64_t c = c0 + lane;
+            float key = FLT_MAX;
+            uint32_t id = kNoId;
+            bool cand = false;
+            if (c < ncand) {
+                key = __ldcg(pkeys + c);
+                id = __ldcg(pids + c);
+                cand = id != kNoId && list.passes(key, id);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, cand);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                list.insert(__shfl_sync(0xffffffffu, key, src), __shfl_sync(0xffffffffu, id, src));
+            }
+        }
+        __syncthreads();
+        block_rank_merge(mk, mi, kScanWarps, p.k, p.k, fk, fi);
+        __syncthreads();
+        for (int j = threadIdx.x; j < p.k; j += kScanThreads) {
+            float dis;
+            int64_t id;
+            if (fi[j] != kNoId) {
+                const float key = fk[j];
+                id = (int64_t)fi[j] + p.id_offset;
+                dis = p.out_mode == kOutKey ? key : p.out_mode == kOutNeg ? -key : 1.f + key;
+                if (p.ip_min_quirk && !(dis > FLT_MIN)) {
+                    id = -1;
+                    dis = FLT_MIN;
+                }
+            } else {
+                id = -1;
+                dis = (p.out_mode == kOutNeg) ? -FLT_MAX : FLT_MAX;
+                if (p.ip_min_quirk) dis = FLT_MIN;
+            }
+            p.out_dis[(q0 + q) * p.k + j] = dis;
+            p.out_ids[(q0 + q) * p.k + j] = id;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        p.tickets[blockIdx.y] = 0;            // ready for the next call
+        __threadfence_system();               // results (mapped host memory) before the flag
+        const unsigned int t = atomicAdd(p.tiles_done, 1u);
+        if (t == gridDim.y - 1) {
+            *p.tiles_done = 0;
+            if (p.done_flag) {
+                __threadfence_system();
+                *p.done_flag = p.done_value;
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -521,7 +613,8 @@ static cudaError_t launch_scan_qt(const ScanParams &p, dim3 grid, size_t smem, c
 }
 
 size_t scan_smem_bytes(int qt, int d_pad, int k) {
-    return (size_t)qt * d_pad * 4 + (size_t)kScanWarps * qt * k * 8;
+    // + one merged list for the fused form's last-block merge (which reuses the front of the buffer)
+    return std::max((size_t)qt * d_pad * 4 + (size_t)kScanWarps * qt * k * 8, (size_t)(kScanWarps + 1) * k * 8);
 }
 
 cudaError_t launch_flat_scan(const ScanParams &p, int qt, int blocks_x, cudaStream_t s) {

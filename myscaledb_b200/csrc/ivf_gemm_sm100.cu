@@ -33,23 +33,53 @@ constexpr int IVF_DEC_WARPS = 4;           // extra decoder warps of the code pa
 constexpr int IVF_THREADS_DEC = IVF_THREADS_TMA + IVF_DEC_WARPS * 32;
 
 // Items with only a few queries (the usual case for small batches: every probed list is visited by one or two queries)
-// would leave all the top-k work to one or two lanes of the per-thread scheme, and every item starts with an empty list
-// ("insert storm": ~k ln(rows / k) inserts per item, each a rescan of the lane's k slots).  For q_count <= kCoopMax the
-// WARP keeps one sorted list per query slot in shared memory instead and inserts cooperatively (WarpTopKT: rank by
-// ballot / popc, shift by 32 lanes at a time): measured 190 us -> ~10 us per item at k = 40.
-constexpr int kCoopMax = 8;
+// would leave all the top-k work to one or two lanes of the per-thread scheme, and every item starts with an empty list:
+// ~k ln(rows / k) + k inserts per item, each a latency-bound ~1 us chain (ncu, profiles/r02_ivf_scan_v1: 100 us per page,
+// 52 % of the stall samples on the epilogue barrier behind the one busy warp).  For q_count <= kCoopMax the warp of TMEM
+// lanes 0..31 therefore works TILE-wise and in bulk: lanes whose chunk minimum beats their threshold park the chunk's keys
+// in a per-slot tile buffer; after the tile (TMEM already released to the MMA warp) the warp compacts each slot's
+// candidates, sorts them with a bitonic network in shared memory and rank-merges them with the slot's sorted k-list
+// (binary searches, all lanes busy): ~2 us for a full tile of candidates instead of 256 dependent inserts.
+constexpr int kCoopMax = 16;
+constexpr int kTileBufStride = BN;       // [16][256] floats = exactly the 16 KB slow-path scratch of the per-thread mode, which
+                                         // it aliases (an item is either cooperative or per-thread); columns are XOR-swizzled
+                                         // with the slot so that lanes parking the same column hit different banks
 
 struct CoopState {   // one per query slot, in shared memory
     float thr_key;
     uint32_t thr_id;
     int n;
-    int pad;
+    int buf;         // which of the slot's two list buffers is current
 };
 
-// One 32-column chunk in cooperative mode.  `thr` is this lane's own slot threshold (-FLT_MAX for lanes without a query).
-__device__ __forceinline__ void epilogue_chunk_coop(float &thr, float (&v)[32], const float *scale, const float *bias, uint32_t id0,
-                                                    float *scratch_warp /* lane 0's scratch column */, int lane, int q_count,
-                                                    float *coop_keys, uint32_t *coop_ids, CoopState *coop_state, int k) {
+struct CoopSmem {
+    float *keys[2];          // [kCoopMax][k] x 2 (double buffer for the rank merge)
+    uint32_t *ids[2];
+    CoopState *state;        // [kCoopMax]
+    float *tilebuf;          // [kCoopMax][kTileBufStride]
+    float *cand_keys;        // [BN]
+    uint32_t *cand_ids;      // [BN]
+};
+__host__ __device__ inline size_t coop_smem_bytes(int k) {
+    return (size_t)kCoopMax * k * 8 * 2 + kCoopMax * sizeof(CoopState) + (size_t)BN * 8 + 64;
+}
+static_assert(kCoopMax * kTileBufStride * 4 <= SCRATCH_BYTES, "the tile buffer aliases the epilogue scratch");
+__device__ __forceinline__ CoopSmem coop_smem_carve(unsigned char *base, unsigned char *scratch_base, int k) {
+    CoopSmem c;
+    c.keys[0] = reinterpret_cast<float *>(base);
+    c.keys[1] = c.keys[0] + (size_t)kCoopMax * k;
+    c.ids[0] = reinterpret_cast<uint32_t *>(c.keys[1] + (size_t)kCoopMax * k);
+    c.ids[1] = c.ids[0] + (size_t)kCoopMax * k;
+    c.state = reinterpret_cast<CoopState *>(c.ids[1] + (size_t)kCoopMax * k);
+    c.tilebuf = reinterpret_cast<float *>(scratch_base);
+    c.cand_keys = reinterpret_cast<float *>(c.state + kCoopMax);
+    c.cand_ids = reinterpret_cast<uint32_t *>(c.cand_keys + BN);
+    return c;
+}
+
+// One 32-column chunk in cooperative mode: transform, and park the keys if this lane's slot can use any of them.
+__device__ __forceinline__ void coop_stage_chunk(float thr, float (&v)[32], const float *scale, const float *bias, float *tile_row /* this lane's slot */,
+                                                 int chunk, uint32_t &chunk_mask, int swz /* slot & 31 */) {
 #pragma unroll
     for (int j = 0; j < 32; j++) v[j] = fmaf(v[j], scale[j], bias[j]);
     float m0 = fminf(v[0], v[1]), m1 = fminf(v[2], v[3]), m2 = fminf(v[4], v[5]), m3 = fminf(v[6], v[7]);
@@ -60,40 +90,96 @@ __device__ __forceinline__ void epilogue_chunk_coop(float &thr, float (&v)[32], 
         m2 = fminf(m2, fminf(v[j + 4], v[j + 5]));
         m3 = fminf(m3, fminf(v[j + 6], v[j + 7]));
     }
-    const bool mine = fminf(fminf(m0, m1), fminf(m2, m3)) <= thr;
-    unsigned pending = __ballot_sync(0xffffffffu, mine);
-    if (!pending) return;
-    // lanes with a candidate park their 32 keys in their scratch column
-    if (mine) {
+    if (fminf(fminf(m0, m1), fminf(m2, m3)) <= thr) {
 #pragma unroll
-        for (int j = 0; j < 32; j++) scratch_warp[j * EPI_THREADS + lane] = v[j];
+        for (int j = 0; j < 32; j++) tile_row[chunk * 32 + (j ^ swz)] = v[j];
+        chunk_mask |= 1u << chunk;
     }
-    __syncwarp();
-    while (pending) {
-        const int s = __ffs(pending) - 1;   // query slot = lane s of this warp
-        pending &= pending - 1;
-        if (s >= q_count) continue;
-        WarpTopK L;
-        L.keys = coop_keys + (size_t)s * k;
-        L.ids = coop_ids + (size_t)s * k;
-        L.k = k;
-        L.n = coop_state[s].n;
-        L.thr_key = coop_state[s].thr_key;
-        L.thr_id = coop_state[s].thr_id;
-        const float key = scratch_warp[lane * EPI_THREADS + s];   // column (row of the page) `lane` of slot s
-        const uint32_t id = id0 + (uint32_t)lane;
-        unsigned m = __ballot_sync(0xffffffffu, L.passes(key, id));
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            L.insert(__shfl_sync(0xffffffffu, key, src), __shfl_sync(0xffffffffu, id, src));
+}
+
+// After a tile: the warp folds the parked keys of every slot into that slot's sorted list.  Returns (to lane s) the new
+// threshold of slot s through `thr`.
+__device__ __forceinline__ void coop_merge_tile(const CoopSmem &cs, int k, int q_count, uint32_t chunk_mask, uint32_t row0, int lane, float &thr) {
+    for (int s = 0; s < q_count; s++) {
+        const uint32_t cm = __shfl_sync(0xffffffffu, chunk_mask, s);
+        if (!cm) continue;
+        CoopState st = cs.state[s];
+        const float *tb = cs.tilebuf + (size_t)s * kTileBufStride;
+        // ---- compaction of the candidates that beat the current threshold
+        int c = 0;
+        for (uint32_t m = cm; m; m &= m - 1) {
+            const int ch = __ffs(m) - 1;
+            const float key = tb[ch * 32 + (lane ^ s)];
+            const uint32_t id = row0 + (uint32_t)(ch * 32 + lane);
+            const bool pass = better(key, id, st.thr_key, st.thr_id);
+            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            if (pass) {
+                const int pos = c + __popc(bal & ((1u << lane) - 1u));
+                cs.cand_keys[pos] = key;
+                cs.cand_ids[pos] = id;
+            }
+            c += __popc(bal);
         }
-        if (lane == 0) {
-            coop_state[s].n = L.n;
-            coop_state[s].thr_key = L.thr_key;
-            coop_state[s].thr_id = L.thr_id;
+        if (c == 0) continue;
+        int n2 = 32;
+        while (n2 < c) n2 <<= 1;
+        for (int i = c + lane; i < n2; i += 32) {
+            cs.cand_keys[i] = FLT_MAX;
+            cs.cand_ids[i] = kNoId;
         }
-        if (lane == s) thr = L.thr_key;
+        __syncwarp();
+        // ---- bitonic sort of cand[0, n2) by (key, id)
+        for (int size = 2; size <= n2; size <<= 1)
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = lane; t < (n2 >> 1); t += 32) {
+                    const int i = ((t / stride) * 2 * stride) + (t % stride), j = i + stride;
+                    const float ki = cs.cand_keys[i], kj = cs.cand_keys[j];
+                    const uint32_t ii = cs.cand_ids[i], ij = cs.cand_ids[j];
+                    const bool up = (i & size) == 0;
+                    if (better(kj, ij, ki, ii) == up) {
+                        cs.cand_keys[i] = kj; cs.cand_ids[i] = ij;
+                        cs.cand_keys[j] = ki; cs.cand_ids[j] = ii;
+                    }
+                }
+                __syncwarp();
+            }
+        // ---- rank merge of list[0, n) and cand[0, m): element -> its position in the union, kept if < k
+        const int m_c = c < k ? c : k;
+        const float *lk = cs.keys[st.buf] + (size_t)s * k;
+        const uint32_t *li = cs.ids[st.buf] + (size_t)s * k;
+        float *ok = cs.keys[st.buf ^ 1] + (size_t)s * k;
+        uint32_t *oi = cs.ids[st.buf ^ 1] + (size_t)s * k;
+        for (int a = lane; a < st.n; a += 32) {
+            const float key = lk[a];
+            const uint32_t id = li[a];
+            int lo = 0, hi = m_c;   // candidates strictly better than this list element
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (better(cs.cand_keys[mid], cs.cand_ids[mid], key, id)) lo = mid + 1; else hi = mid;
+            }
+            const int rank = a + lo;
+            if (rank < k) { ok[rank] = key; oi[rank] = id; }
+        }
+        for (int b = lane; b < m_c; b += 32) {
+            const float key = cs.cand_keys[b];
+            const uint32_t id = cs.cand_ids[b];
+            int lo = 0, hi = st.n;  // list elements better than this candidate (ids are unique: no ties between the two sets)
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (better(lk[mid], li[mid], key, id)) lo = mid + 1; else hi = mid;
+            }
+            const int rank = b + lo;
+            if (rank < k) { ok[rank] = key; oi[rank] = id; }
+        }
+        __syncwarp();
+        st.n = st.n + m_c < k ? st.n + m_c : k;
+        st.buf ^= 1;
+        if (st.n == k) {
+            st.thr_key = ok[k - 1];
+            st.thr_id = oi[k - 1];
+        }
+        if (lane == 0) cs.state[s] = st;
+        if (lane == s) thr = st.thr_key;
         __syncwarp();
     }
 }
@@ -229,11 +315,9 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             list.keys = p.list_keys_gmem + (size_t)blockIdx.x * p.k * EPI_THREADS + row;
             list.ids = p.list_ids_gmem + (size_t)blockIdx.x * p.k * EPI_THREADS + row;
         }
-        // cooperative lists (items with <= kCoopMax queries): [kCoopMax][k] keys + ids + state, owned by the warp of TMEM lanes 0..31
-        float *coop_keys = reinterpret_cast<float *>(smem + p.coop_smem_off);
-        uint32_t *coop_ids = reinterpret_cast<uint32_t *>(coop_keys + (size_t)kCoopMax * p.k);
-        CoopState *coop_state = reinterpret_cast<CoopState *>(coop_ids + (size_t)kCoopMax * p.k);
-        float *scratch_warp = scratch - lane;
+        // cooperative lists (items with <= kCoopMax queries), owned by the warp of TMEM lanes 0..31
+        const CoopSmem cs = coop_smem_carve(smem + p.coop_smem_off, smem + C::off_scratch(STAGES), p.k);
+        float *tile_row = cs.tilebuf + (size_t)(lane < kCoopMax ? lane : 0) * kTileBufStride;
         int as = 0;
         uint32_t aphase = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
@@ -246,12 +330,13 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             float coop_thr = list.thr_key;
             if (coop && quarter == 0) {
                 if (lane < kCoopMax) {
-                    coop_state[lane].n = 0;
-                    coop_state[lane].thr_key = FLT_MAX;
-                    coop_state[lane].thr_id = 0;
+                    CoopState st;
+                    st.n = 0; st.thr_key = FLT_MAX; st.thr_id = 0; st.buf = 0;
+                    cs.state[lane] = st;
                 }
                 __syncwarp();
             }
+            if (coop && quarter != 0) coop_thr = -FLT_MAX;   // only TMEM lanes 0 .. q_count - 1 carry queries (q_count <= 16)
             for (uint32_t j = 0; j < item.page_count; j++) {
                 const uint32_t page = p.list_pages[item.page_begin + j];
                 const uint32_t row0 = page * (uint32_t)BN;
@@ -271,6 +356,7 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
                 float va[32], vb[32];
+                uint32_t chunk_mask = 0;
                 __syncwarp();
                 tmem_ld32_issue(taddr, va);
                 tmem_ld_wait();
@@ -278,21 +364,20 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 for (int chunk = 0; chunk < BN / 32; chunk += 2) {
                     __syncwarp();
                     tmem_ld32_issue(taddr + (chunk + 1) * 32, vb);
-                    if (coop) epilogue_chunk_coop(coop_thr, va, side_scale + chunk * 32, side_bias + chunk * 32, row0 + chunk * 32, scratch_warp, lane,
-                                                  quarter == 0 ? (int)item.q_count : 0, coop_keys, coop_ids, coop_state, p.k);
+                    if (coop) coop_stage_chunk(coop_thr, va, side_scale + chunk * 32, side_bias + chunk * 32, tile_row, chunk, chunk_mask, lane);
                     else epilogue_chunk(list, va, true, side_scale + chunk * 32, side_bias + chunk * 32, row0 + chunk * 32, false, 0, scratch);
                     tmem_ld_wait();
                     __syncwarp();
                     if (chunk + 2 < BN / 32) tmem_ld32_issue(taddr + (chunk + 2) * 32, va);
-                    if (coop) epilogue_chunk_coop(coop_thr, vb, side_scale + (chunk + 1) * 32, side_bias + (chunk + 1) * 32, row0 + (chunk + 1) * 32,
-                                                  scratch_warp, lane, quarter == 0 ? (int)item.q_count : 0, coop_keys, coop_ids, coop_state, p.k);
+                    if (coop) coop_stage_chunk(coop_thr, vb, side_scale + (chunk + 1) * 32, side_bias + (chunk + 1) * 32, tile_row, chunk + 1, chunk_mask, lane);
                     else epilogue_chunk(list, vb, true, side_scale + (chunk + 1) * 32, side_bias + (chunk + 1) * 32,
                                         row0 + (chunk + 1) * 32, false, 0, scratch);
                     tmem_ld_wait();
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);   // the accumulator is free: the merge below runs beside the next tile's MMAs
+                if (coop && quarter == 0) coop_merge_tile(cs, p.k, (int)item.q_count, chunk_mask, row0, lane, coop_thr);
                 if (++as == ACC_STAGES) {
                     as = 0;
                     aphase ^= 1;
@@ -304,13 +389,15 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                     __syncwarp();
                     for (uint32_t sl = 0; sl < item.q_count; sl++) {
                         const size_t part = (size_t)p.pair_part_base[item.q_begin + sl] + item.chunk;
-                        const int n = coop_state[sl].n;
+                        const CoopState st = cs.state[sl];
+                        const float *lkeys = cs.keys[st.buf] + (size_t)sl * p.k;
+                        const uint32_t *lids = cs.ids[st.buf] + (size_t)sl * p.k;
                         for (int e = lane; e < p.k; e += 32) {
-                            const bool have = e < n;
-                            p.part_keys[part * p.k + e] = have ? coop_keys[(size_t)sl * p.k + e] : FLT_MAX;
-                            p.part_ids[part * p.k + e] = have ? p.row_ids[coop_ids[(size_t)sl * p.k + e]] : kNoId;
+                            const bool have = e < st.n;
+                            p.part_keys[part * p.k + e] = have ? lkeys[e] : FLT_MAX;
+                            p.part_ids[part * p.k + e] = have ? p.row_ids[lids[e]] : kNoId;
                         }
-                        if (lane == 0) p.part_worst[part] = n == p.k ? coop_state[sl].thr_key : FLT_MAX;
+                        if (lane == 0) p.part_worst[part] = st.n == p.k ? st.thr_key : FLT_MAX;
                     }
                     __syncwarp();
                 }
@@ -451,7 +538,7 @@ static cudaError_t launch_ivf(const CUtensorMap &map_q, const CUtensorMap &map_c
     if (need(stages, 0) > 232448) return cudaErrorInvalidValue;
     // cooperative lists: kCoopMax x k x 8 bytes + state, always in shared memory (k <= 512); they come first, the per-thread
     // lists (for items with many queries) use what is left or global scratch
-    const int coop_bytes = p.k <= 512 ? (int)round_up((size_t)kCoopMax * p.k * 8 + kCoopMax * sizeof(CoopState), 16) : 0;
+    const int coop_bytes = p.k <= 256 ? (int)round_up(coop_smem_bytes(p.k), 16) : 0;
     p.coop_enabled = coop_bytes > 0 && need(2, 0) + coop_bytes <= 232448 ? 1 : 0;
     const int coop_used = p.coop_enabled ? coop_bytes : 0;
     while (stages > 2 && need(stages, 0) + coop_used > 232448) stages--;

@@ -16,6 +16,20 @@ struct ScanParams {
     int64_t row_bytes;
     int d_pad, k, group;
     int l2, bf16;
+    // fused single-launch form (small batches on a resident corpus: the call is latency-bound): raw queries [nq][q_dim]
+    // are padded (and for cosine normalised) while they are staged, the LAST block of a query tile to finish merges every
+    // block's partial list and writes the final result (mapped pinned host memory) -- one launch, no pad / merge kernels
+    int fused;               // 0 = plain scan (queries pre-padded, partial lists only)
+    int q_dim;               // fused: row length of `queries`
+    int cosine;              // fused: normalise the staged queries (skip sum sq < FLT_EPSILON), output 1 + key
+    int out_mode, ip_min_quirk;
+    int64_t id_offset;
+    unsigned int *tickets;   // fused: [gridDim.y] zeroed counters (the last block resets its own)
+    float *out_dis;          // fused: [nq][k]
+    int64_t *out_ids;
+    volatile unsigned int *done_flag;  // fused, nullable: set to done_value once every query tile has been written
+    unsigned int done_value;
+    unsigned int *tiles_done;          // fused: one zeroed counter (reset by the last tile)
 };
 
 struct BinaryScanParams {

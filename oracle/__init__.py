@@ -176,6 +176,18 @@ def knn_flat_parts(metric, x, y, k, n_parts):
     return dis, ids
 
 
+def knn_flat_simd(metric, x, y, k):
+    """Small-batch CPU arm: faiss' nx < 20 form (exact differences, SIMD, one thread), cpu_baseline.c."""
+    x, y = _f32(x), _f32(y)
+    nx, d = x.shape
+    ny = y.shape[0]
+    dis = np.empty((nx, k), np.float32)
+    ids = np.empty((nx, k), np.int64)
+    lib().orc_knn_flat_simd(C.c_int(metric), _p(x, C.c_float), C.c_int64(nx), _p(y, C.c_float), C.c_int64(ny), C.c_int(d), C.c_int(k),
+                            _p(dis, C.c_float), _p(ids, C.c_int64))
+    return dis, ids
+
+
 def blas_path():
     """OpenBLAS shipped inside numpy's wheel (numpy.libs/libscipy_openblas64_*.so), or None."""
     import glob

@@ -363,3 +363,60 @@ int orc_knn_flat_parts_blas(int metric, const float *x, int64_t nx, const float 
     free(th);
     return 0;
 }
+
+
+/* ------------------------------------------------------------------------- */
+/* Small-batch CPU arm (BASELINE configs[0]: FLAT L2 distance(), 10k x 128, one query): faiss' nx < 20 path computes     */
+/* exact squared differences row by row with SIMD (fvec_L2sqr_ny) and keeps a heap -- single-threaded inside a part        */
+/* (omp_set_num_threads(1), VIWithDataPart.h:350).  16-lane accumulators; target_clones picks AVX-512 / AVX2 at run time.  */
+/* Results are verified against vs_oracle.c in tests/test_oracle_golden.py.                                               */
+/* ------------------------------------------------------------------------- */
+__attribute__((target_clones("avx512f", "avx2,fma", "default"))) static float orc_l2_simd(const float *x, const float *y, int d) {
+    float acc[16] = {0};
+    int j = 0;
+    for (; j + 16 <= d; j += 16) {
+#pragma GCC unroll 16
+        for (int l = 0; l < 16; l++) {
+            const float t = x[j + l] - y[j + l];
+            acc[l] += t * t;
+        }
+    }
+    float s = 0;
+    for (int l = 0; l < 16; l++) s += acc[l];
+    for (; j < d; j++) {
+        const float t = x[j] - y[j];
+        s += t * t;
+    }
+    return s;
+}
+__attribute__((target_clones("avx512f", "avx2,fma", "default"))) static float orc_ip_simd(const float *x, const float *y, int d) {
+    float acc[16] = {0};
+    int j = 0;
+    for (; j + 16 <= d; j += 16) {
+#pragma GCC unroll 16
+        for (int l = 0; l < 16; l++) acc[l] += x[j + l] * y[j + l];
+    }
+    float s = 0;
+    for (int l = 0; l < 16; l++) s += acc[l];
+    for (; j < d; j++) s += x[j] * y[j];
+    return s;
+}
+
+void orc_knn_flat_simd(int metric, const float *x, int64_t nx, const float *y, int64_t ny, int d, int k, float *dis, int64_t *ids) {
+    for (int64_t q = 0; q < nx; q++) {
+        orc_topk t = {k, 0, dis + q * k, ids + q * k};
+        for (int64_t i = 0; i < ny; i++) {
+            const float key = metric == ORC_L2 ? orc_l2_simd(x + q * d, y + i * d, d) : -orc_ip_simd(x + q * d, y + i * d, d);
+            if (t.n == k && !(key < t.key[k - 1])) continue;
+            orc_topk_push(&t, key, i);
+        }
+        for (int j = 0; j < k; j++) {
+            if (j < t.n) {
+                if (metric != ORC_L2) dis[q * k + j] = -dis[q * k + j];
+            } else {
+                dis[q * k + j] = metric == ORC_L2 ? FLT_MAX : -FLT_MAX;
+                ids[q * k + j] = -1;
+            }
+        }
+    }
+}

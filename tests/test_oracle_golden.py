@@ -379,3 +379,15 @@ def test_bm25_tokenizer_and_multi_field_and_semantics():
     assert len(rows) == 0
     rows, _ = ix.search("alpha nosuchterm", 10, fields=(0, 1), operator_or=True)
     assert sorted(int(r) for r in rows) == [1, 2, 3]
+
+
+def test_simd_small_batch_cpu_arm_agrees_with_the_checker():
+    """cpu_baseline.c::orc_knn_flat_simd (the timed cfg-1 CPU arm) returns what vs_oracle.c returns."""
+    rng = np.random.default_rng(8)
+    y = rng.standard_normal((10000, 128)).astype(np.float32)
+    x = rng.standard_normal((3, 128)).astype(np.float32)
+    for metric in (orc.L2, orc.IP):
+        d0, i0 = orc.knn_flat(metric, x, y, 10)
+        d1, i1 = orc.knn_flat_simd(metric, x, y, 10)
+        assert (i0 == i1).all()
+        np.testing.assert_allclose(d1, d0, rtol=2e-6, atol=1e-5)
