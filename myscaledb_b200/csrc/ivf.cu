@@ -829,6 +829,7 @@ static void timing_collect(b200_index *ix);
 // internal hooks into capi.cu
 extern "C" int b200_corpus_search_device(b200_corpus *c, const float *d_queries, int64_t nq, int k, const uint8_t *d_alive_bits,
                                          int64_t id_offset, float *d_out_dis, int64_t *d_out_ids, void *stream);
+extern "C" int b200_corpus_set_path(b200_corpus *c, int path);
 namespace b200 {
 const void *corpus_device_rows(const b200_corpus *c);
 int corpus_normalize_rows(b200_corpus *c);
@@ -1555,7 +1556,19 @@ static int search_device_locked(b200_index *ix, const float *d_queries, int64_t 
     B200_TRY(ix->w_pd.reserve((size_t)n_pairs * 4));
     if (ix->d == ix->d_pad) B200_CUDA_OK(cudaMemcpyAsync(ix->w_qraw.p, d_q, (size_t)nq * ix->d * 4, cudaMemcpyDeviceToDevice, s));
     else B200_CUDA_OK(cudaMemcpy2DAsync(ix->w_qraw.p, (size_t)ix->d * 4, d_q, (size_t)ix->d_pad * 4, (size_t)ix->d * 4, nq, cudaMemcpyDeviceToDevice, s));
-    B200_TRY(b200_corpus_search_device(ix->coarse, ix->w_qraw.as<float>(), nq, nprobe, nullptr, 0, ix->w_pd.as<float>(), ix->w_probe.as<int64_t>(), s));
+    {
+        // The centroid table is small and nprobe is a large k for it: the tensor-core path keeps one k-list per query lane
+        // and never gets a selective threshold when k / nlist is a few percent (measured 9 ms for 10 000 x 4096 x 96, k = 32).
+        // The scan kernel's warp lists cost O(k / 32) per insert: use it when its estimated time (FMA-bound at ~1.4 TB/s of
+        // table bytes per 8-query pass) undercuts ~1 us per (query, 32 probes) of the tensor-core path.
+        const double t_scan = (double)ceil_div(nq, 8) * nl * ix->d_pad * 4.0 / 1.4e12;
+        const double t_gemm = 1e-6 * (double)nq * std::max(1.0, nprobe / 32.0) + 30e-6;
+        const bool use_scan = nprobe > 8 && t_scan < t_gemm;
+        b200_corpus_set_path(ix->coarse, use_scan ? 1 : 0);
+        const int rc = b200_corpus_search_device(ix->coarse, ix->w_qraw.as<float>(), nq, nprobe, nullptr, 0, ix->w_pd.as<float>(), ix->w_probe.as<int64_t>(), s);
+        b200_corpus_set_path(ix->coarse, 0);
+        B200_TRY(rc);
+    }
 
     if (ix->timing) cudaEventRecord(ix->ev_ph[1], s);
     // ---- pairs sorted by list
@@ -1622,6 +1635,8 @@ static int search_device_locked(b200_index *ix, const float *d_queries, int64_t 
     g_launches++;
     // ---- gather queries, per-pair bookkeeping
     B200_TRY(ix->w_qbuf.reserve(((size_t)n_pairs + 128) * ix->d_pad64 * 2));
+    // the 128 rows behind the last pair are read by the last items' A tiles (TMEM lanes without a query): keep them finite
+    B200_CUDA_OK(cudaMemsetAsync(ix->w_qbuf.as<char>() + (size_t)n_pairs * ix->d_pad64 * 2, 0, (size_t)128 * ix->d_pad64 * 2, s));
     B200_TRY(ix->w_inv.reserve((size_t)n_pairs * 4));
     B200_TRY(ix->w_ppb.reserve((size_t)n_pairs * 4));
     B200_TRY(ix->w_pconst.reserve((size_t)n_pairs * 4));

@@ -304,7 +304,7 @@ int main() {
             std::vector<uint8_t> u8_alived_bitmap;
             TANTIVY::FFIVecRowIdWithScoreResult result = TANTIVY::ffi_bm25_search(                                // :908-917
                 index_files_cache_path, sentence, column_names, static_cast<uint32_t>(topk), u8_alived_bitmap, false, enable_nlq, operator_or, statistics);
-            REQUIRE(!result.error.is_error && result.result.size() == 2 && result.result[0].row_id == 0);
+            REQUIRE(!result.error.is_error && result.result.size() == 2 && result.result[0].row_id == 2 && result.result[1].row_id == 0);   // the shorter document scores higher
             u8_alived_bitmap = {0x06};   // row 0 deleted
             result = TANTIVY::ffi_bm25_search(index_files_cache_path, sentence, column_names, static_cast<uint32_t>(topk), u8_alived_bitmap, true,   // :939-948
                                               enable_nlq, operator_or, statistics);

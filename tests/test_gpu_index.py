@@ -248,3 +248,15 @@ def test_serialize_load_roundtrip_and_golden_00001_after_reload(goldens, tmp_pat
         b2.VectorIndex.load(tmp_path / "bad.b2ix", 64)
     with pytest.raises(b2.B200Error):
         b2.VectorIndex.load(tmp_path / "missing.b2ix", 64)
+
+
+def test_cooperative_tile_merge_unit():
+    """tests/cuda/coop_merge_test.cu drives csrc/ivf_coop.cuh (compaction + bitonic sort + rank merge of the grouped IVF scan)
+    with synthetic tiles: 240 (k, slots, tiles, distribution) cases against std::sort, ties included."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "cuda", "coop_merge_test")
+    if not os.path.exists(exe):
+        pytest.skip("coop_merge_test not built (run __graft_entry__.build())")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "COOP MERGE OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
