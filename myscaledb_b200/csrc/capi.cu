@@ -104,8 +104,9 @@ struct b200_corpus {
     // fused single-launch path of the host entry point (small batches, scan kernel): mapped pinned staging + counters
     void *h_pin = nullptr;         // [queries 8 * d fp32 | dis 8 * k | ids 8 * k | flag]
     size_t h_pin_bytes = 0;
-    unsigned int *d_tickets = nullptr;   // [8] + tiles_done
+    unsigned int *d_tickets = nullptr;   // [8] + tiles_done, then (at +64 bytes) the device copy of the staged queries
     unsigned int fused_seq = 0;
+    int d_tickets_d = 0;           // row length the query staging behind d_tickets was sized for
     int fused_enabled = 1;         // B200_FUSED_SCAN=0 disables (A/B)
     int rescore_l2 = 1;      // tensor-core L2: re-score the k winners exactly (B200_GEMM_RESCORE_L2=0 disables, A/B only)
     int gemm_multicast = 1;  // CTA pairs per cluster sharing each corpus tile: 1 auto (4, else 2), 2, 4; B200_GEMM_MULTICAST=0 disables
@@ -737,10 +738,14 @@ static int search_host_fused(b200_corpus *c, const float *queries, int64_t nq, i
         }
         c->h_pin_bytes = need;
     }
-    if (!c->d_tickets) {
-        B200_CUDA_OK(cudaMalloc(&c->d_tickets, 16 * 4));
-        B200_CUDA_OK(cudaMemsetAsync(c->d_tickets, 0, 16 * 4, s));
+    if (!c->d_tickets || c->d_tickets_d != c->d) {
+        if (c->d_tickets) cudaFree(c->d_tickets);
+        c->d_tickets = nullptr;
+        B200_CUDA_OK(cudaMalloc(&c->d_tickets, 64 + (size_t)8 * c->d * 4));
+        B200_CUDA_OK(cudaMemsetAsync(c->d_tickets, 0, 64, s));
+        c->d_tickets_d = c->d;
     }
+    float *d_q = reinterpret_cast<float *>(reinterpret_cast<char *>(c->d_tickets) + 64);
     char *hp = reinterpret_cast<char *>(c->h_pin);
     float *h_q = reinterpret_cast<float *>(hp);
     float *h_dis = reinterpret_cast<float *>(hp + (size_t)8 * c->d * 4);
@@ -749,7 +754,10 @@ static int search_host_fused(b200_corpus *c, const float *queries, int64_t nq, i
     void *dp = nullptr;
     B200_CUDA_OK(cudaHostGetDevicePointer(&dp, c->h_pin, 0));
     char *dpc = reinterpret_cast<char *>(dp);
+    // the query goes pinned -> device with one small async copy (reading it from the kernel over PCIe, 4 bytes per thread and
+    // block, cost 45 us of a 60 us kernel at 296 blocks); the RESULT is written to mapped host memory by one block
     memcpy(h_q, queries, (size_t)nq * c->d * 4);
+    B200_CUDA_OK(cudaMemcpyAsync(d_q, h_q, (size_t)nq * c->d * 4, cudaMemcpyHostToDevice, s));
     const uint8_t *d_alive = nullptr;
     if (alive_bits) {
         const size_t ab = (size_t)ceil_div(c->n, 8);
@@ -764,13 +772,15 @@ static int search_host_fused(b200_corpus *c, const float *queries, int64_t nq, i
     const int64_t y_tiles = ceil_div(nq, qt);
     const int64_t rows_per_block_step = 8 * (32 / group);
     int64_t bx = std::max<int64_t>(1, (2 * c->sms) / std::min<int64_t>(y_tiles, 2 * c->sms));
-    bx = std::min<int64_t>(bx, std::max<int64_t>(1, ceil_div(c->n, rows_per_block_step * 4)));
+    // small parts: every block should stream >= 64 KB (fewer partial lists for the last block to merge)
+    bx = std::min<int64_t>(bx, std::max<int64_t>(1, ceil_div(c->n * c->row_bytes, 64 * 1024)));
+    bx = std::min<int64_t>(bx, std::max<int64_t>(1, ceil_div(c->n, rows_per_block_step)));
     const int blocks_x = (int)bx;
     B200_TRY(c->w_pk.reserve((size_t)nq * blocks_x * k * 4));
     B200_TRY(c->w_pi.reserve((size_t)nq * blocks_x * k * 4));
     ScanParams sp{};
     sp.corpus = c->data;
-    sp.queries = reinterpret_cast<const float *>(dpc);
+    sp.queries = d_q;
     sp.row_scale = c->metric == B200_METRIC_COSINE ? c->row_scale : nullptr;
     sp.alive = d_alive;
     sp.part_keys = c->w_pk.as<float>();

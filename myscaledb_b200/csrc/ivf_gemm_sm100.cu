@@ -383,20 +383,28 @@ static cudaError_t launch_ivf(const CUtensorMap &map_q, const CUtensorMap &map_c
     constexpr bool DEC = PRODUCER != IVF_PRODUCER_TMA;
     // ring depth: as deep as the per-thread lists (and the PQ codebook) leave room for
     const int extra = PRODUCER == IVF_PRODUCER_PQ ? (int)round_up(p.codebook_bytes, 1024) : 0;
-    // ring depth first (bytes in flight per SM bound the HBM rate of a streaming item): 4 stages whenever they fit; the
-    // per-thread lists move to global scratch (L1 / L2 resident, touched rarely in steady state) when they do not fit too
-    int stages = 4;
+    // Shared-memory budget: operand ring (48 KB per stage) + cooperative lists + per-thread lists.  Items with many queries
+    // insert into per-thread lists ~k ln(rows / k) times per lane: in global scratch that is ~1 us per insert (measured: 0.8 ms
+    // per 3-page item at k = 40), in shared memory ~0.1 us -- so the per-thread lists get shared memory even at the price of
+    // a 3-stage ring; only when they do not fit beside 3 stages do they move to global scratch (and the ring gets 4 stages).
     auto need = [&](int st, int k_smem) { return Cfg<1>::off_list(st) + k_smem * EPI_THREADS * 8 + extra + SMEM_ALIGN_SLACK; };
-    while (stages > 2 && need(stages, 0) > 232448) stages--;
-    if (need(stages, 0) > 232448) return cudaErrorInvalidValue;
-    // cooperative lists: kCoopMax x k x 8 bytes + state, always in shared memory (k <= 512); they come first, the per-thread
-    // lists (for items with many queries) use what is left or global scratch
     const int coop_bytes = p.k <= 256 ? (int)round_up(coop_smem_bytes(p.k), 16) : 0;
     p.coop_enabled = coop_bytes > 0 && need(2, 0) + coop_bytes <= 232448 ? kCoopMax : 0;
     if (const char *ev = getenv("B200_IVF_COOP")) p.coop_enabled = std::min(p.coop_enabled, atoi(ev));   // A/B and debugging
     const int coop_used = p.coop_enabled ? coop_bytes : 0;
-    while (stages > 2 && need(stages, 0) + coop_used > 232448) stages--;
-    p.lists_in_smem = (p.k <= kGemmSmemK && need(stages, p.k) + coop_used <= 232448) ? 1 : 0;
+    int stages = 4;
+    p.lists_in_smem = 0;
+    if (p.k <= kGemmSmemK)
+        for (int st = 4; st >= 3; st--)
+            if (need(st, p.k) + coop_used <= 232448) {
+                stages = st;
+                p.lists_in_smem = 1;
+                break;
+            }
+    if (!p.lists_in_smem) {
+        while (stages > 2 && need(stages, 0) + coop_used > 232448) stages--;
+        if (need(stages, 0) + coop_used > 232448) return cudaErrorInvalidValue;
+    }
     p.stages = stages;
     const int k_smem = p.lists_in_smem ? p.k : 0;
     p.coop_smem_off = (int)round_up(Cfg<1>::off_list(stages) + k_smem * EPI_THREADS * 8, 16);
