@@ -394,7 +394,13 @@ def index_extra(a, dev, N, rank, comm):
     ix.reserve(shard)
     n_chunks = shard // CH
     per = -(-min(shard, 64 * nlist) // n_chunks)
-    sample = torch.cat([chunk((r0 // CH) + i, CH, 100)[:: max(1, CH // per)][:per] for i in range(n_chunks)]).contiguous()
+    parts = []
+    for i in range(n_chunks):   # a strided slice is a VIEW of its 1.4 GB chunk: copy it out, drop the chunk
+        x = chunk((r0 // CH) + i, CH, 100)
+        parts.append(x[:: max(1, CH // per)][:per].clone())
+        del x
+    sample = torch.cat(parts).contiguous()
+    del parts
     torch.cuda.synchronize()
     ix.train_device(sample.data_ptr(), sample.shape[0])
     del sample

@@ -756,8 +756,11 @@ static int search_host_fused(b200_corpus *c, const float *queries, int64_t nq, i
     char *dpc = reinterpret_cast<char *>(dp);
     // the query goes pinned -> device with one small async copy (reading it from the kernel over PCIe, 4 bytes per thread and
     // block, cost 45 us of a 60 us kernel at 296 blocks); the RESULT is written to mapped host memory by one block
-    memcpy(h_q, queries, (size_t)nq * c->d * 4);
-    B200_CUDA_OK(cudaMemcpyAsync(d_q, h_q, (size_t)nq * c->d * 4, cudaMemcpyHostToDevice, s));
+    const bool q_inline = nq * c->d <= 256;   // small queries ride in the kernel parameters: no copy at all
+    if (!q_inline) {
+        memcpy(h_q, queries, (size_t)nq * c->d * 4);
+        B200_CUDA_OK(cudaMemcpyAsync(d_q, h_q, (size_t)nq * c->d * 4, cudaMemcpyHostToDevice, s));
+    }
     const uint8_t *d_alive = nullptr;
     if (alive_bits) {
         const size_t ab = (size_t)ceil_div(c->n, 8);
@@ -772,8 +775,6 @@ static int search_host_fused(b200_corpus *c, const float *queries, int64_t nq, i
     const int64_t y_tiles = ceil_div(nq, qt);
     const int64_t rows_per_block_step = 8 * (32 / group);
     int64_t bx = std::max<int64_t>(1, (2 * c->sms) / std::min<int64_t>(y_tiles, 2 * c->sms));
-    // small parts: every block should stream >= 64 KB (fewer partial lists for the last block to merge)
-    bx = std::min<int64_t>(bx, std::max<int64_t>(1, ceil_div(c->n * c->row_bytes, 64 * 1024)));
     bx = std::min<int64_t>(bx, std::max<int64_t>(1, ceil_div(c->n, rows_per_block_step)));
     const int blocks_x = (int)bx;
     B200_TRY(c->w_pk.reserve((size_t)nq * blocks_x * k * 4));
@@ -805,6 +806,8 @@ static int search_host_fused(b200_corpus *c, const float *queries, int64_t nq, i
     sp.out_ids = reinterpret_cast<int64_t *>(dpc + (reinterpret_cast<char *>(h_ids) - hp));
     sp.done_flag = reinterpret_cast<volatile unsigned int *>(dpc + need - 16);
     sp.done_value = ++c->fused_seq ? c->fused_seq : ++c->fused_seq;   // never 0
+    sp.q_inline = q_inline ? 1 : 0;
+    if (q_inline) memcpy(sp.qinline, queries, (size_t)nq * c->d * 4);
     *h_flag = 0;
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     timing_begin(c, s, ev);

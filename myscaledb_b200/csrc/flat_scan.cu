@@ -70,7 +70,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanPa
     // 16-byte words (a single 32-byte-strided array costs a 2-way bank conflict on every LDS.128).
     for (int i = threadIdx.x; i < QT * p.d_pad; i += kScanThreads) {
         const int q = i / p.d_pad, j = i - q * p.d_pad;
-        const float v = (q < nq_here) ? (p.fused ? (j < p.q_dim ? p.queries[(q0 + q) * p.q_dim + j] : 0.f) : p.queries[(q0 + q) * p.d_pad + j]) : 0.f;
+        const float v = (q < nq_here) ? (p.fused ? (j < p.q_dim ? (p.q_inline ? p.qinline[(q0 + q) * p.q_dim + j] : p.queries[(q0 + q) * p.q_dim + j]) : 0.f)
+                                                  : p.queries[(q0 + q) * p.d_pad + j])
+                                      : 0.f;
         if (E == 8) {
             const int c = j >> 3, e = j & 7;
             qs[q * p.d_pad + (e >> 2) * (p.d_pad >> 1) + c * 4 + (e & 3)] = v;
@@ -224,6 +226,24 @@ __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanPa
         const float *pkeys = p.part_keys + (q0 + q) * (int64_t)gridDim.x * p.k;
         const uint32_t *pids = p.part_ids + (q0 + q) * (int64_t)gridDim.x * p.k;
         const int64_t ncand = (int64_t)gridDim.x * p.k;
+        {   // every block's list is sorted and complete: the smallest k-th key over the blocks bounds the global k-th key
+            __shared__ float bound_s[kScanWarps];
+            float b = FLT_MAX;
+            for (int l = threadIdx.x; l < (int)gridDim.x; l += kScanThreads)
+                if (__ldcg(pids + (int64_t)l * p.k + (p.k - 1)) != kNoId) b = fminf(b, __ldcg(pkeys + (int64_t)l * p.k + (p.k - 1)));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) b = fminf(b, __shfl_xor_sync(0xffffffffu, b, o));
+            if (lane == 0) bound_s[warp] = b;
+            __syncthreads();
+            b = bound_s[0];
+#pragma unroll
+            for (int w = 1; w < kScanWarps; w++) b = fminf(b, bound_s[w]);
+            if (b < FLT_MAX) {
+                list.thr_key = b;
+                list.thr_id = kNoId;
+            }
+            __syncthreads();
+        }
         for (int64_t c0 = (int64_t)warp * 32; c0 < ncand; c0 += kScanThreads) {
             const int64_t c = c0 + lane;
             float key = FLT_MAX;

@@ -30,6 +30,8 @@ struct ScanParams {
     volatile unsigned int *done_flag;  // fused, nullable: set to done_value once every query tile has been written
     unsigned int done_value;
     unsigned int *tiles_done;          // fused: one zeroed counter (reset by the last tile)
+    int q_inline;                      // fused: the queries travel in the kernel parameters (nq * q_dim <= 256 floats)
+    float qinline[256];
 };
 
 struct BinaryScanParams {

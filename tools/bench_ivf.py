@@ -73,7 +73,7 @@ def main():
     parts = []
     for i, off in enumerate(range(0, a.rows, CH)):
         m = min(CH, a.rows - off)
-        parts.append(chunk(i, m)[:: max(1, m // per)][:per])
+        parts.append(chunk(i, m)[:: max(1, m // per)][:per].clone())
     sample = torch.cat(parts).contiguous()
     del parts
     torch.cuda.synchronize()

@@ -2,12 +2,12 @@
 cd "$(dirname "$0")/../.." || exit 1
 mkdir -p gpurun_out
 exec > >(tee gpurun_out/r02_gpu14.log) 2>&1
-echo "== index + flat tests"
-timeout 900 python -m pytest tests/test_gpu_index.py tests/test_gpu_flat.py tests/test_gpu_edges.py -m gpu -q --timeout 600 2>&1 | tail -4
+echo "== flat tests"
+timeout 900 python -m pytest tests/test_gpu_flat.py tests/test_gpu_edges.py tests/test_gpu_properties.py -m gpu -q --timeout 600 2>&1 | tail -4
 echo "== latency"
 timeout 300 python tools/bench_latency.py 2>&1 | tail -2
 echo "== bench N=1 (headline + extras incl. 100M index)"
-/usr/bin/time -v timeout 1500 python bench.py --steps 50 --warmup 3 > gpurun_out/r02_bench_line_b.json 2> gpurun_out/r02_bench_b.err; tail -3 gpurun_out/r02_bench_b.err | head -2; grep -E "Elapsed|Maximum resident" gpurun_out/r02_bench_b.err
+timeout 1500 python bench.py --steps 50 --warmup 3 > gpurun_out/r02_bench_line_b.json 2> gpurun_out/r02_bench_b.err; tail -3 gpurun_out/r02_bench_b.err
 python - <<'PY'
 import json
 d=json.loads([l for l in open('gpurun_out/r02_bench_line_b.json') if l.startswith('{')][-1])
