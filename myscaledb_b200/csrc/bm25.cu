@@ -294,6 +294,172 @@ __global__ void __launch_bounds__(256) bm25_score_kernel(const Bm25ScoreParams p
                      p.part_ids + ((size_t)q * gridDim.x + blockIdx.x) * p.k);
 }
 
+// ------------------------------------------------------------------------------------
+// Round 2: document-at-a-time inside doc RANGES.  The kernel above scores posting by posting and searches every other
+// clause's list for each group of 32 postings (33 GB/s of posting bytes: 0.5 % of HBM).  Here a warp owns a CONTIGUOUS run of
+// doc ranges of one query; for a range [r W, (r + 1) W) it
+//   1. advances one cursor per clause (lanes = clauses) to the range end by a galloping + binary search from the previous
+//      cursor (lists are sorted by doc: the cursors only move forward, every posting is read exactly once, coalesced),
+//   2. accumulates the postings of the range clause after clause into a per-warp open-addressing table in shared memory keyed
+//      by doc (score added with explicit rn ops in clause order -> bit-identical to the term-at-a-time sums; a bit per matched
+//      query term for AND),
+//   3. sweeps the table: AND mask, alive bitmap, warp-cooperative top-k.
+// W is chosen per query on the host so that a range holds ~384 postings of its clauses together; a range that turns out
+// denser than the table can hold is halved on the fly.
+// ------------------------------------------------------------------------------------
+constexpr int kDaatSlots = 1024;          // per warp: doc u32 + score f32 + mask u64 = 16 KB
+constexpr int kDaatFill = 704;            // postings a table takes in one go (load factor ~0.69)
+constexpr uint32_t kDaatEmpty = 0xffffffffu;
+
+struct Bm25DaatParams {
+    Bm25ScoreParams base;
+    const uint32_t *range_log2;   // [nq] log2 of the range width W of each query
+};
+
+// first index i in docs[from, n) with docs[i] >= key (galloping from `from`, then binary search)
+__device__ __forceinline__ uint32_t gallop_lower_bound(const uint32_t *docs, uint32_t from, uint32_t n, uint64_t key) {
+    uint32_t lo = from, step = 32;
+    if (lo >= n || docs[lo] >= key) return lo;
+    uint32_t hi = lo + step;
+    while (hi < n && docs[hi] < key) {   // docs[lo] < key always holds
+        lo = hi;
+        step <<= 1;
+        hi = lo + step;
+    }
+    if (hi > n) hi = n;
+    lo++;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (docs[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) bm25_daat_kernel(const Bm25DaatParams dp) {
+    const Bm25ScoreParams &p = dp.base;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *lk = reinterpret_cast<float *>(smem_raw);                       // [8][k]
+    uint32_t *li = reinterpret_cast<uint32_t *>(lk + 8 * p.k);             // [8][k]
+    unsigned char *tables = reinterpret_cast<unsigned char *>(li + 8 * p.k);
+    tables = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tables) + 15) & ~(uintptr_t)15);
+    __shared__ Clause cl[kMaxClauses];
+    __shared__ uint32_t cur_s[8][kMaxClauses], end_s[8][kMaxClauses];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *t_doc = reinterpret_cast<uint32_t *>(tables + (size_t)warp * kDaatSlots * 16);
+    float *t_score = reinterpret_cast<float *>(t_doc + kDaatSlots);
+    unsigned long long *t_mask = reinterpret_cast<unsigned long long *>(t_score + kDaatSlots);
+    const uint32_t q = blockIdx.y;
+    const uint32_t c0 = p.clause_begin[q], nc = p.clause_begin[q + 1] - c0;
+    for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) cl[i] = p.clauses[c0 + i];
+    WarpTopK list;
+    list.init(lk + (size_t)warp * p.k, li + (size_t)warp * p.k, p.k);
+    for (int j = lane; j < p.k; j += 32) list.keys[j] = FLT_MAX;
+    __syncthreads();
+    if (nc) {
+        const uint32_t lg = dp.range_log2[q];
+        const uint64_t W = 1ull << lg;
+        const uint64_t n_ranges = ((uint64_t)p.n_docs + W - 1) >> lg;
+        // this warp's contiguous run of ranges
+        const uint64_t warps_total = (uint64_t)gridDim.x * 8, wid = (uint64_t)blockIdx.x * 8 + warp;
+        const uint64_t per = (n_ranges + warps_total - 1) / warps_total;
+        const uint64_t r_begin = wid * per, r_end = r_begin + per < n_ranges ? r_begin + per : n_ranges;
+        const unsigned long long full_mask = p.term_mask[q];
+        if (r_begin < r_end) {
+            // cursors at the start of the first range
+            for (uint32_t c = lane; c < nc; c += 32)
+                cur_s[warp][c] = gallop_lower_bound(p.post_docs + cl[c].offset, 0, cl[c].df, r_begin << lg);
+            __syncwarp();
+            uint64_t d_lo = r_begin << lg;
+            const uint64_t d_stop = (r_end << lg) < (uint64_t)p.n_docs ? (r_end << lg) : (uint64_t)p.n_docs;
+            uint64_t width = W;
+            while (d_lo < d_stop) {
+                uint64_t d_hi = d_lo + width < d_stop ? d_lo + width : d_stop;
+                // ---- 1. range ends per clause; shrink the range until its postings fit the table
+                uint32_t total;
+                for (;;) {
+                    uint32_t mine = 0;
+                    for (uint32_t c = lane; c < nc; c += 32) {
+                        const uint32_t e = gallop_lower_bound(p.post_docs + cl[c].offset, cur_s[warp][c], cl[c].df, d_hi);
+                        end_s[warp][c] = e;
+                        mine += e - cur_s[warp][c];
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+                    total = mine;
+                    if (total <= (uint32_t)kDaatFill || d_hi - d_lo <= 1) break;
+                    width = (d_hi - d_lo + 1) >> 1;   // halve and retry (a single doc always fits: <= 64 clauses)
+                    d_hi = d_lo + width;
+                }
+                __syncwarp();
+                if (total) {
+                    // ---- 2. accumulate clause after clause
+                    for (int i = lane; i < kDaatSlots; i += 32) t_doc[i] = kDaatEmpty;
+                    __syncwarp();
+                    for (uint32_t c = 0; c < nc; c++) {
+                        const uint32_t b = cur_s[warp][c], e = end_s[warp][c];
+                        const uint32_t *docs = p.post_docs + cl[c].offset;
+                        const uint32_t *tfs = p.post_tfs + cl[c].offset;
+                        const unsigned long long bit = 1ull << clause_term(cl[c]);
+                        for (uint32_t i0 = b; i0 < e; i0 += 32) {
+                            const uint32_t i = i0 + lane;
+                            if (i < e) {
+                                const uint32_t doc = docs[i];
+                                const float tf = (float)tfs[i];
+                                const float norm = p.caches[(size_t)clause_cache(cl[c]) * 256 + p.fieldnorm[(size_t)cl[c].field * p.n_docs + doc]];
+                                const float contrib = __fmul_rn(cl[c].weight, __fdiv_rn(tf, __fadd_rn(tf, norm)));
+                                uint32_t slot = (doc * 2654435761u) >> 22;   // 10 bits
+                                for (;;) {
+                                    const uint32_t prev = atomicCAS(&t_doc[slot], kDaatEmpty, doc);
+                                    if (prev == kDaatEmpty) {   // first clause that contains this doc
+                                        t_score[slot] = contrib;
+                                        t_mask[slot] = bit;
+                                        break;
+                                    }
+                                    if (prev == doc) {          // an earlier clause owns the slot: add in clause order
+                                        t_score[slot] = __fadd_rn(t_score[slot], contrib);
+                                        t_mask[slot] |= bit;
+                                        break;
+                                    }
+                                    slot = (slot + 1) & (kDaatSlots - 1);
+                                }
+                            }
+                        }
+                        __syncwarp();   // clause c is complete (and visible) before clause c + 1 touches the same docs
+                    }
+                    // ---- 3. sweep
+                    for (int i0 = 0; i0 < kDaatSlots; i0 += 32) {
+                        const int i = i0 + lane;
+                        const uint32_t doc = t_doc[i];
+                        bool cand = doc != kDaatEmpty;
+                        float key = FLT_MAX;
+                        if (cand && !p.operator_or && t_mask[i] != full_mask) cand = false;
+                        if (cand) {
+                            const uint32_t rid = p.row_id[doc];
+                            cand = !p.alive || ((p.alive[rid >> 3] >> (rid & 7)) & 1);
+                            key = -t_score[i];
+                            cand = cand && list.passes(key, doc);
+                        }
+                        unsigned m = __ballot_sync(0xffffffffu, cand);
+                        while (m) {
+                            const int src = __ffs(m) - 1;
+                            m &= m - 1;
+                            list.insert(__shfl_sync(0xffffffffu, key, src), __shfl_sync(0xffffffffu, doc, src));
+                        }
+                    }
+                    __syncwarp();
+                }
+                for (uint32_t c = lane; c < nc; c += 32) cur_s[warp][c] = end_s[warp][c];
+                __syncwarp();
+                d_lo = d_hi;
+                if (width < W && total <= (uint32_t)kDaatFill / 4) width <<= 1;   // dense spot passed: widen again
+            }
+        }
+    }
+    __syncthreads();
+    block_rank_merge(lk, li, 8, p.k, p.k, p.part_keys + ((size_t)q * gridDim.x + blockIdx.x) * p.k,
+                     p.part_ids + ((size_t)q * gridDim.x + blockIdx.x) * p.k);
+}
+
 // doc ordinal -> row id on the merged result
 __global__ void bm25_finish_kernel(const float *dis, const int64_t *docs, const uint32_t *row_id, int64_t n, float *out_score,
                                    uint64_t *out_row, uint32_t *out_count, int k) {
@@ -342,7 +508,7 @@ struct b200_bm25 {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::mutex mu;
-    DevVec d_docs, d_tfs, d_fn, d_rows, d_clauses, d_begin, d_caches, d_pk, d_pi, d_alive, d_odis, d_oids, d_score, d_row64, d_cnt, d_masks;
+    DevVec d_docs, d_tfs, d_fn, d_rows, d_clauses, d_begin, d_caches, d_pk, d_pi, d_alive, d_odis, d_oids, d_score, d_row64, d_cnt, d_masks, d_ranges;
 };
 
 static int bm25_device_ok() {
@@ -377,7 +543,7 @@ extern "C" int b200_bm25_free(b200_bm25 *ix) {
     if (!ix) return B200_OK;
     cudaSetDevice(ix->device);
     for (DevVec *v : {&ix->d_docs, &ix->d_tfs, &ix->d_fn, &ix->d_rows, &ix->d_clauses, &ix->d_begin, &ix->d_caches, &ix->d_pk,
-                      &ix->d_pi, &ix->d_alive, &ix->d_odis, &ix->d_oids, &ix->d_score, &ix->d_row64, &ix->d_cnt, &ix->d_masks})
+                      &ix->d_pi, &ix->d_alive, &ix->d_odis, &ix->d_oids, &ix->d_score, &ix->d_row64, &ix->d_cnt, &ix->d_masks, &ix->d_ranges})
         v->release();
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
@@ -611,9 +777,31 @@ extern "C" int b200_bm25_search_batch(b200_bm25 *ix, const char *const *sentence
     sp.n_docs = (uint32_t)nd;
     sp.k = k;
     sp.operator_or = operator_or;
-    const size_t smem = (size_t)8 * k * 8;
-    B200_CUDA_OK(cudaFuncSetAttribute(bm25_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bm25_score_kernel<<<dim3(bx, (unsigned)nq), 256, smem, s>>>(sp);
+    static const int use_taat = getenv("B200_BM25_TAAT") ? atoi(getenv("B200_BM25_TAAT")) : 0;   // A/B: the round-1 kernel
+    if (use_taat) {
+        const size_t smem = (size_t)8 * k * 8;
+        B200_CUDA_OK(cudaFuncSetAttribute(bm25_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bm25_score_kernel<<<dim3(bx, (unsigned)nq), 256, smem, s>>>(sp);
+    } else {
+        // range width per query: ~384 postings of all its clauses per range
+        std::vector<uint32_t> range_log2(nq, 8);
+        for (int64_t q = 0; q < nq; q++) {
+            uint64_t m_q = 0;
+            for (uint32_t c = begin[q]; c < begin[q + 1]; c++) m_q += clauses[c].df;
+            const double w = m_q ? 384.0 * (double)nd / (double)m_q : (double)nd;
+            uint32_t lg = 8;
+            while (lg < 31 && (double)(1ull << (lg + 1)) <= w) lg++;
+            range_log2[q] = lg;
+        }
+        B200_TRY(ix->d_ranges.reserve((size_t)nq * 4));
+        B200_CUDA_OK(cudaMemcpyAsync(ix->d_ranges.p, range_log2.data(), (size_t)nq * 4, cudaMemcpyHostToDevice, s));
+        Bm25DaatParams dpp{};
+        dpp.base = sp;
+        dpp.range_log2 = reinterpret_cast<const uint32_t *>(ix->d_ranges.p);
+        const size_t smem = (size_t)8 * k * 8 + 16 + (size_t)8 * kDaatSlots * 16;
+        B200_CUDA_OK(cudaFuncSetAttribute(bm25_daat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bm25_daat_kernel<<<dim3(bx, (unsigned)nq), 256, smem, s>>>(dpp);
+    }
     g_launches++;
     B200_CUDA_OK(cudaGetLastError());
     MergeParams mp{};

@@ -1594,16 +1594,18 @@ static int search_device_locked(b200_index *ix, const float *d_queries, int64_t 
     }
     // ---- work items.  Long lists are cut into chunks of pages so that even a single query fills the SMs; the cut is
     //      chosen from host-side knowledge only (no device -> host round trip on the query path).
+    // Lists are cut into chunks of `ppc` pages so that the persistent grid gets ~16 items per SM (static round-robin over items
+    // sorted by list length: finer items = better balance; measured at 100 M x 768, nprobe 2: 13-page items left 0.43 of the HBM
+    // peak, see profiles/).  Each item pays one cold start of its top-k lists, so >= 2 pages; <= 16 pages bounds the tail.  The
+    // estimate uses host-side knowledge only (no device -> host round trip on the query path): probed lists <= min(pairs, nlist),
+    // their length size-biased (a query lands in a list with probability proportional to its size).
     const double avg_pages = std::max(1.0, (double)ix->pages_used / std::max(1, nl));
-    const double est_items_unsplit = std::min<double>((double)n_pairs, (double)nl);   // distinct probed lists, at most
-    uint32_t ppc = ix->max_list_pages ? ix->max_list_pages : 1;
+    const double est_lists = std::min<double>((double)n_pairs, (double)nl);
+    const double est_pages = est_lists * std::min<double>(ix->max_list_pages ? ix->max_list_pages : 1, 1.5 * avg_pages);
+    uint32_t ppc;
     {
-        const double want_items = 4.0 * ix->sms;
-        if (est_items_unsplit < want_items) {
-            const double split = std::ceil(want_items / std::max(1.0, est_items_unsplit));
-            ppc = (uint32_t)std::max(2.0, std::ceil(avg_pages / split));
-        }
-        ppc = std::min<uint32_t>(ppc, 16);                                // an item never streams more than 16 pages: no long tail
+        const double want_items = 16.0 * ix->sms;
+        ppc = (uint32_t)std::min(16.0, std::max(2.0, std::ceil(est_pages / want_items)));
         ppc = std::max<uint32_t>(ppc, (ix->max_list_pages + 63) / 64);   // at most 64 chunks per list
         ppc = std::max<uint32_t>(ppc, 1);
         if (const int forced = parse_int_param(params, "pages_per_chunk", 0)) ppc = (uint32_t)forced;

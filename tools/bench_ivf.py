@@ -123,7 +123,7 @@ def main():
     sz = ix.list_sizes() if info["uses_ivf"] else np.zeros(1)
     chk = {"phase": "check", "list_rows_min": int(sz.min()), "list_rows_max": int(sz.max()), "list_rows_mean": float(sz.mean()),
            "empty_lists": int((sz == 0).sum())}
-    if a.keep_raw != 0:  # the truth must equal an exact pass over the index's own fp32 rows
+    if a.keep_raw != 0 and not (a.keep_raw < 0 and a.rows * a.dim * 4 > 60e9):  # the truth must equal an exact pass over the index's own fp32 rows
         ed = torch.empty((nt, a.k), dtype=torch.float32, device=dev); ei = torch.empty((nt, a.k), dtype=torch.int64, device=dev)
         ix.search_device(q.data_ptr(), nt, a.k, ed.data_ptr(), ei.data_ptr(), "exact_batch=1", stream=torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
@@ -139,8 +139,8 @@ def main():
     ix.enable_timing(True)
     res_d = torch.empty((a.nq, a.k), dtype=torch.float32, device=dev); res_i = torch.empty((a.nq, a.k), dtype=torch.int64, device=dev)
     s = torch.cuda.current_stream().cuda_stream
-    for nprobe in [int(v) for v in a.nprobe.split(",")]:
-        par = f"nprobe={nprobe}" + (", " + a.extra if a.extra else "")
+    for nprobe, extra in [(int(v), e) for e in a.extra.split(";") for v in a.nprobe.split(",")]:
+        par = f"nprobe={nprobe}" + (", " + extra if extra else "")
         for _ in range(2):
             ix.search_device(q.data_ptr(), a.nq, a.k, res_d.data_ptr(), res_i.data_ptr(), par, stream=s)
         torch.cuda.synchronize()
@@ -157,7 +157,7 @@ def main():
         rec = float(np.mean([len(set(ids[j].tolist()) & set(truth_i[j].tolist())) / a.k for j in range(nt)]))
         kms = sc["kernel_ms"] / max(1, sc["launches"])
         gb = sc["rows_streamed"] * sc["payload_row_bytes"] / 1e9
-        print(json.dumps({"phase": "search", "type": a.type, "nprobe": nprobe, "nq": a.nq, "k": a.k, "ms_per_batch": round(ms, 3),
+        print(json.dumps({"phase": "search", "type": a.type, "params": par, "nprobe": nprobe, "nq": a.nq, "k": a.k, "ms_per_batch": round(ms, 3),
                           "qps": round(a.nq / ms * 1e3), "recall": round(rec, 4), "scan_kernel_ms": round(kms, 3),
                           "scan_GB": round(gb, 3), "scan_GB_per_s": round(gb / kms * 1e3) if kms else None,
                           "frac_hbm": round(gb / kms * 1e3 / hbm, 3) if kms else None, "bytes_per_query": round(gb * 1e9 / a.nq),
