@@ -301,6 +301,13 @@ int b200_index_memory_bytes(const b200_index *ix, uint64_t *out_bytes);
  * Filter bitmaps and decoupled-part row-id maps (VIWithMeta::{row_ids_map, inverted_row_ids_map,
  * inverted_row_sources_map}, VectorIndex/Cache/VICacheObject.h:40-117).
  * ---------------------------------------------------------------------------------- */
+/* Device-resident filters (the filtered-search fast path): build the DenseBitmap in HBM from the surviving _part_offset values
+ * of the PREWHERE pipeline (getFilterFromPipeline, ...SelectWithHybridSearchProcessor.cpp:906-934) or from the _row_exists
+ * bytes of a lightweight delete (MergeTreeVSManager.cpp:1435-1460), intersect there, and pass the result as d_alive_bits to the
+ * *_search_device / b200_sharded_* calls.  Buffers: (nbits + 7) / 8 bytes rounded up to a multiple of 4, 4-byte aligned. */
+int b200_bitmap_from_offsets_device(const uint64_t *d_offsets, int64_t n, int64_t nbits, uint8_t *d_out_bits, void *stream);
+int b200_bitmap_from_row_exists_device(const uint8_t *d_row_exists, int64_t n, uint8_t *d_out_bits, void *stream);
+int b200_bitmap_and_device(const uint8_t *d_a, const uint8_t *d_b, int64_t nbits, uint8_t *d_out, void *stream);
 /* Search::intersectDenseBitmaps (VIWithDataPart.cpp:908): out = a & b */
 int b200_bitmap_and(const uint8_t *a, const uint8_t *b, int64_t nbits, uint8_t *out);
 /* getRealBitmap (VectorIndex/Utils/VIUtils.cpp:479-497): filter over the merged part -> bitmap over this old part */
@@ -344,6 +351,8 @@ int b200_bm25_search(b200_bm25 *ix, const char *sentence, const uint32_t *fields
                      const uint8_t *alive_bits /*over row ids*/, int use_filter, int operator_or, uint64_t stat_total_docs,
                      const uint64_t *stat_total_tokens, const uint64_t *stat_doc_freq, uint64_t *out_rows,
                      float *out_scores, uint32_t *out_n);
+/* roofline inputs of the last batch on this index: scoring-kernel ms (CUDA events), wall ms inside the C call, postings walked */
+int b200_bm25_last_timing(b200_bm25 *ix, double *kernel_ms, double *call_ms, uint64_t *postings);
 int b200_bm25_search_batch(b200_bm25 *ix, const char *const *sentences, int64_t nq, const uint32_t *fields,
                            uint32_t n_fields_q, uint32_t topk, const uint8_t *alive_bits, int use_filter, int operator_or,
                            uint64_t stat_total_docs, const uint64_t *stat_total_tokens, const uint64_t *stat_doc_freq,

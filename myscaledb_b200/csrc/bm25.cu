@@ -22,6 +22,7 @@
 // warp-cooperative top-k as the vector scan (key = -score, tie -> smaller doc).
 // HBM-bound: sum over clauses of df * (8 B posting + 1 B field norm).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -505,6 +506,9 @@ struct b200_bm25 {
     std::vector<uint64_t> row_ids;
     std::vector<uint64_t> total_tokens;
     bool committed = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // around the scoring kernel of the last batch
+    double last_call_ms = 0;                     // wall time of the last b200_bm25_search_batch inside the library
+    uint64_t last_postings = 0;                  // postings the scoring kernel walked (sum of df over the batch's clauses)
     int device = 0;
     cudaStream_t stream = nullptr;
     std::mutex mu;
@@ -545,8 +549,25 @@ extern "C" int b200_bm25_free(b200_bm25 *ix) {
     for (DevVec *v : {&ix->d_docs, &ix->d_tfs, &ix->d_fn, &ix->d_rows, &ix->d_clauses, &ix->d_begin, &ix->d_caches, &ix->d_pk,
                       &ix->d_pi, &ix->d_alive, &ix->d_odis, &ix->d_oids, &ix->d_score, &ix->d_row64, &ix->d_cnt, &ix->d_masks, &ix->d_ranges})
         v->release();
+    if (ix->ev0) cudaEventDestroy(ix->ev0);
+    if (ix->ev1) cudaEventDestroy(ix->ev1);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
+    return B200_OK;
+}
+
+// roofline inputs of the last batch: scoring-kernel milliseconds (CUDA events), wall milliseconds of the whole C call, postings walked
+extern "C" int b200_bm25_last_timing(b200_bm25 *ix, double *kernel_ms, double *call_ms, uint64_t *postings) {
+    if (!ix) return fail(B200_ERR_INVALID, "null index");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    float ms = 0;
+    if (ix->ev0 && cudaEventElapsedTime(&ms, ix->ev0, ix->ev1) != cudaSuccess) {
+        cudaGetLastError();
+        ms = 0;
+    }
+    if (kernel_ms) *kernel_ms = ms;
+    if (call_ms) *call_ms = ix->last_call_ms;
+    if (postings) *postings = ix->last_postings;
     return B200_OK;
 }
 
@@ -676,6 +697,7 @@ extern "C" int b200_bm25_search_batch(b200_bm25 *ix, const char *const *sentence
     std::lock_guard<std::mutex> lk(ix->mu);
     if (!ix->committed) return fail(B200_ERR_INVALID, "commit the index before searching");
     if (nq == 0) return B200_OK;
+    const auto t_call0 = std::chrono::steady_clock::now();
     B200_CUDA_OK(cudaSetDevice(ix->device));
     cudaStream_t s = ix->stream;
     const size_t nd = ix->row_ids.size();
@@ -777,6 +799,13 @@ extern "C" int b200_bm25_search_batch(b200_bm25 *ix, const char *const *sentence
     sp.n_docs = (uint32_t)nd;
     sp.k = k;
     sp.operator_or = operator_or;
+    if (!ix->ev0) {
+        cudaEventCreate(&ix->ev0);
+        cudaEventCreate(&ix->ev1);
+    }
+    ix->last_postings = 0;
+    for (auto &c : clauses) ix->last_postings += c.df;
+    cudaEventRecord(ix->ev0, s);
     static const int use_taat = getenv("B200_BM25_TAAT") ? atoi(getenv("B200_BM25_TAAT")) : 0;   // A/B: the round-1 kernel
     if (use_taat) {
         const size_t smem = (size_t)8 * k * 8;
@@ -802,6 +831,7 @@ extern "C" int b200_bm25_search_batch(b200_bm25 *ix, const char *const *sentence
         B200_CUDA_OK(cudaFuncSetAttribute(bm25_daat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         bm25_daat_kernel<<<dim3(bx, (unsigned)nq), 256, smem, s>>>(dpp);
     }
+    cudaEventRecord(ix->ev1, s);
     g_launches++;
     B200_CUDA_OK(cudaGetLastError());
     MergeParams mp{};
@@ -829,6 +859,7 @@ extern "C" int b200_bm25_search_batch(b200_bm25 *ix, const char *const *sentence
     B200_CUDA_OK(cudaMemcpyAsync(out_rows, ix->d_row64.p, (size_t)tot * 8, cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaMemcpyAsync(out_counts, ix->d_cnt.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaStreamSynchronize(s));
+    ix->last_call_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call0).count();
     return B200_OK;
 }
 

@@ -340,7 +340,11 @@ template <int CG, int MC>
 static cudaError_t launch_cg(const CUtensorMap &map_q, const CUtensorMap &map_c, const GemmTopkParams &p_in, int grid,
                              cudaStream_t s) {
     GemmTopkParams p = p_in;
-    p.lists_in_smem = Cfg<CG>::lists_fit(p.k) ? 1 : 0;
+    // Per-thread lists live in shared memory only while they leave a deep operand ring: at k = 100 they squeezed the ring to 2
+    // stages and the launch took 33 ms instead of 11.7 (the inserts are rare after the first tiles; a starved TMA -> MMA pipeline
+    // is paid on every tile).  Below `min_stages` the lists move to global scratch and the ring keeps its full depth.
+    static const int min_stages = getenv("B200_GEMM_LIST_SMEM_MIN_STAGES") ? atoi(getenv("B200_GEMM_LIST_SMEM_MIN_STAGES")) : (CG == 2 ? 5 : 3);
+    p.lists_in_smem = (Cfg<CG>::lists_fit(p.k) && Cfg<CG>::stages_for(p.k) >= min_stages) ? 1 : 0;
     const int k_smem = p.lists_in_smem ? p.k : 0;
     p.stages = Cfg<CG>::stages_for(k_smem);
     {
@@ -371,7 +375,8 @@ static cudaError_t launch_cg(const CUtensorMap &map_q, const CUtensorMap &map_c,
 // how many clusters of CG * MC CTAs of this kernel can be co-resident (persistent grid upper bound)
 template <int CG, int MC>
 static int max_clusters(int k) {
-    const int k_smem = Cfg<CG>::lists_fit(k) ? k : 0;
+    static const int min_stages = getenv("B200_GEMM_LIST_SMEM_MIN_STAGES") ? atoi(getenv("B200_GEMM_LIST_SMEM_MIN_STAGES")) : (CG == 2 ? 5 : 3);
+    const int k_smem = (Cfg<CG>::lists_fit(k) && Cfg<CG>::stages_for(k) >= min_stages) ? k : 0;
     const int stages = Cfg<CG>::stages_for(k_smem);
     const size_t smem = (size_t)Cfg<CG>::off_list(stages) + (size_t)k_smem * EPI_THREADS * 8 + SMEM_ALIGN_SLACK;
     auto kern = gemm_topk_kernel<CG, MC>;

@@ -1594,18 +1594,19 @@ static int search_device_locked(b200_index *ix, const float *d_queries, int64_t 
     }
     // ---- work items.  Long lists are cut into chunks of pages so that even a single query fills the SMs; the cut is
     //      chosen from host-side knowledge only (no device -> host round trip on the query path).
-    // Lists are cut into chunks of `ppc` pages so that the persistent grid gets ~16 items per SM (static round-robin over items
-    // sorted by list length: finer items = better balance; measured at 100 M x 768, nprobe 2: 13-page items left 0.43 of the HBM
-    // peak, see profiles/).  Each item pays one cold start of its top-k lists, so >= 2 pages; <= 16 pages bounds the tail.  The
-    // estimate uses host-side knowledge only (no device -> host round trip on the query path): probed lists <= min(pairs, nlist),
-    // their length size-biased (a query lands in a list with probability proportional to its size).
+    // Lists are cut into chunks of `ppc` pages: an item never streams more than 16 pages (bounds the tail of the static
+    // round-robin schedule), and small batches are split further so that every SM gets ~4 items.  Finer is NOT better: every item
+    // pays one cold start of its top-k lists (sweep at 100 M x 768, nprobe 1: 4-page items 0.64 of the HBM peak, 8 to 16-page
+    // items 0.77-0.78; nprobe 4: 0.33 vs 0.45; profiles/r02_gpu17_*).  The estimate uses host-side knowledge only (no device ->
+    // host round trip on the query path): probed lists <= min(pairs, nlist), their length size-biased.
     const double avg_pages = std::max(1.0, (double)ix->pages_used / std::max(1, nl));
     const double est_lists = std::min<double>((double)n_pairs, (double)nl);
     const double est_pages = est_lists * std::min<double>(ix->max_list_pages ? ix->max_list_pages : 1, 1.5 * avg_pages);
     uint32_t ppc;
     {
-        const double want_items = 16.0 * ix->sms;
-        ppc = (uint32_t)std::min(16.0, std::max(2.0, std::ceil(est_pages / want_items)));
+        const double want_items = 4.0 * ix->sms;
+        ppc = (uint32_t)std::min(16.0, std::max(8.0, std::ceil(est_pages / want_items)));
+        if (est_lists * 2 < want_items) ppc = (uint32_t)std::max(2.0, std::min<double>(ppc, std::ceil(1.5 * avg_pages * est_lists / want_items)));   // a handful of queries
         ppc = std::max<uint32_t>(ppc, (ix->max_list_pages + 63) / 64);   // at most 64 chunks per list
         ppc = std::max<uint32_t>(ppc, 1);
         if (const int forced = parse_int_param(params, "pages_per_chunk", 0)) ppc = (uint32_t)forced;

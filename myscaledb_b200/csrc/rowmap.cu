@@ -5,6 +5,7 @@
 // (src/VectorIndex/Common/VIWithDataPart.cpp:56-68) and TransferToOldRowIds (:69-126).
 // All are byte/integer gathers over at most N bits or k labels; bit-exact by construction.
 // HBM-bound: n/8 bytes per bitmap, 8-9 bytes per mapped row.
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -35,9 +36,64 @@ __global__ void remap_labels_kernel(const uint64_t *map, int64_t map_len, int64_
     }
 }
 
+// filter->set(offset) for every surviving _part_offset of the PREWHERE pipeline (getFilterFromPipeline,
+// src/VectorIndex/Storages/MergeTreeSelectWithHybridSearchProcessor.cpp:906-934), built where the searches consume it
+__global__ void bitmap_from_offsets_kernel(const uint64_t *offsets, int64_t n, int64_t nbits, uint32_t *out_words) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t o = offsets[i];
+        if ((int64_t)o < nbits) atomicOr(&out_words[o >> 5], 1u << (o & 31));
+    }
+}
+// lightweight delete: bit = _row_exists[i] != 0 (MergeTreeVSManager.cpp:1435-1460)
+__global__ void bitmap_from_bytes_kernel(const uint8_t *row_exists, int64_t n, uint8_t *out_bits) {
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < (n + 7) / 8; b += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t v = 0;
+        for (int j = 0; j < 8; j++)
+            if (b * 8 + j < n && row_exists[b * 8 + j]) v |= 1u << j;
+        out_bits[b] = (uint8_t)v;
+    }
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+// Device-resident filter bitmaps: the bitmap is BUILT in HBM from what the PREWHERE pipeline produces and handed
+// to b200_corpus_search_device / b200_index_search_device / b200_sharded_*_search as d_alive_bits -- no n/8-byte upload per call.
+// d_out_bits: device buffer of (nbits + 7) / 8 bytes rounded up to a multiple of 4, zeroed by the call.  Asynchronous on `stream`.
+extern "C" int b200_bitmap_from_offsets_device(const uint64_t *d_offsets, int64_t n, int64_t nbits, uint8_t *d_out_bits, void *stream) {
+    if ((!d_offsets && n > 0) || !d_out_bits || n < 0 || nbits < 0) return fail(B200_ERR_INVALID, "bad arguments");
+    if ((reinterpret_cast<uintptr_t>(d_out_bits) & 3) != 0) return fail(B200_ERR_INVALID, "the bitmap buffer must be 4-byte aligned");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    B200_CUDA_OK(cudaMemsetAsync(d_out_bits, 0, (size_t)round_up(ceil_div(nbits, 8), 4), s));
+    if (n) {
+        bitmap_from_offsets_kernel<<<(int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256), 148 * 16)), 256, 0, s>>>(
+            d_offsets, n, nbits, reinterpret_cast<uint32_t *>(d_out_bits));
+        g_launches++;
+        B200_CUDA_OK(cudaGetLastError());
+    }
+    return B200_OK;
+}
+extern "C" int b200_bitmap_from_row_exists_device(const uint8_t *d_row_exists, int64_t n, uint8_t *d_out_bits, void *stream) {
+    if ((!d_row_exists && n > 0) || !d_out_bits || n < 0) return fail(B200_ERR_INVALID, "bad arguments");
+    if (n == 0) return B200_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    bitmap_from_bytes_kernel<<<(int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(ceil_div(n, 8), 256), 148 * 16)), 256, 0, s>>>(d_row_exists, n, d_out_bits);
+    g_launches++;
+    B200_CUDA_OK(cudaGetLastError());
+    return B200_OK;
+}
+// out = a & b, all three device resident ((nbits + 7) / 8 bytes rounded up to a multiple of 4)
+extern "C" int b200_bitmap_and_device(const uint8_t *d_a, const uint8_t *d_b, int64_t nbits, uint8_t *d_out, void *stream) {
+    if (!d_a || !d_b || !d_out || nbits < 0) return fail(B200_ERR_INVALID, "bad arguments");
+    if (nbits == 0) return B200_OK;
+    const int64_t nwords = ceil_div(nbits, 32);
+    bitmap_and_kernel<<<(int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(nwords, 256), 148 * 16)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const uint32_t *>(d_a), reinterpret_cast<const uint32_t *>(d_b), nwords, reinterpret_cast<uint32_t *>(d_out));
+    g_launches++;
+    B200_CUDA_OK(cudaGetLastError());
+    return B200_OK;
+}
 
 namespace {
 struct Scratch {

@@ -284,6 +284,11 @@ class BM25Index:
                                             _p(counts, C.c_uint32)))
         return [(rows[q, :counts[q]].copy(), scores[q, :counts[q]].copy()) for q in range(nq)]
 
+    def last_timing(self):
+        km, cm, po = C.c_double(), C.c_double(), C.c_uint64()
+        _check(lib().b200_bm25_last_timing(self._h, C.byref(km), C.byref(cm), C.byref(po)))
+        return dict(kernel_ms=km.value, call_ms=cm.value, postings=po.value)
+
     def search(self, sentence, topk, **kw):
         return self.search_batch([sentence], topk, **kw)[0]
 

@@ -109,6 +109,7 @@ def bench_bm25():
     t_build = time.perf_counter() - t0
     queries = [" ".join(words[100 + rng.choice(vocab - 100, size=3, p=pz[100:] / pz[100:].sum())]) for _ in range(nq)]
     t, res = timed(lambda: g.search_batch(queries, 30))
+    tm = g.last_timing()
     post = sum(g.doc_freq(t_) for qs in queries for t_ in set(qs.split()))
     t0 = time.perf_counter()
     for qs in queries[:64]:
@@ -117,7 +118,8 @@ def bench_bm25():
     print(json.dumps({"workload": f"BM25 top-30 (num_candidates = 3 x LIMIT 10), {n_docs} docs, Zipf(1.1) vocab {vocab}, "
                                   f"len ~ Poisson(64), batch {nq} x 3 terms (config 5 text side, 1 GPU)",
                       "build_s_host_tokenise_and_upload": t_build, "qps": nq / t, "postings_scored_per_batch": post,
-                      "posting_GB_per_s": post * 9 / t / 1e9,
+                      "posting_GB_per_s": post * 9 / t / 1e9, "python_call_ms": t * 1e3, "c_call_ms": tm["call_ms"],
+                      "score_kernel_ms": tm["kernel_ms"], "score_kernel_posting_GB_per_s": tm["postings"] * 9 / (tm["kernel_ms"] * 1e-3) / 1e9 if tm["kernel_ms"] else None,
                       "cpu_oracle_qps_1_thread_scaled": 1.0 / t_cpu}))
 
 
