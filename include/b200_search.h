@@ -246,6 +246,10 @@ int b200_comm_free(b200_comm *c);
 /* building blocks: device buffers a shard search writes its [nq][k] result to, then all-gather + merge on `stream` */
 int b200_comm_local_buffers(b200_comm *c, int64_t nq, int k, float **d_dis, int64_t **d_ids);
 int b200_comm_gather_merge(b200_comm *c, int64_t nq, int k, int descending, float *d_out_dis, int64_t *d_out_ids, void *stream);
+/* the same for lists produced on the host (per-shard BM25 top-k: scores descending, unused slots score -inf / id -1);
+ * uploads, all-gathers, merges and returns the table-wide top-k to the host; synchronous */
+int b200_comm_gather_merge_host(b200_comm *c, const float *h_dis, const int64_t *h_ids, int64_t nq, int k, int descending,
+                                float *h_out_dis, int64_t *h_out_ids);
 /* in-place sum over the ranks of n host-resident uint64 counters (total_docs, total_tokens[field], doc_freq[...]) */
 int b200_comm_allreduce_sum_u64(b200_comm *c, uint64_t *host_counters, int64_t n);
 /* whole steps.  Every rank passes its own shard and the same queries; every rank receives the global top-k.

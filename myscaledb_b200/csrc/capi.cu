@@ -635,8 +635,8 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
         gp.part_keys = c->w_pk.as<float>();
         gp.part_ids = c->w_pi.as<uint32_t>();
         {  // global scratch for the per-thread lists, used when they do not fit in shared memory (large k)
-            B200_TRY(c->w_lk.reserve((size_t)grid * 128 * k * 4));
-            B200_TRY(c->w_li.reserve((size_t)grid * 128 * k * 4));
+            B200_TRY(c->w_lk.reserve((size_t)grid * 128 * list_cap_append(k) * 4));
+            B200_TRY(c->w_li.reserve((size_t)grid * 128 * list_cap_append(k) * 4));
             gp.list_keys_gmem = c->w_lk.as<float>();
             gp.list_ids_gmem = c->w_li.as<uint32_t>();
         }

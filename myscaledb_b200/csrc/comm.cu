@@ -82,6 +82,8 @@ struct b200_comm {
     size_t send_cap = 0, recv_cap = 0;
     uint64_t *d_counters = nullptr;          // all-reduce scratch
     size_t counters_cap = 0;
+    void *d_host_out = nullptr;              // merged result of the host-buffer gather
+    size_t host_out_cap = 0;
     std::mutex mu;
     // CUDA graphs of whole sharded search steps, keyed by everything that is baked into the nodes
     std::map<std::tuple<const void *, const void *, int64_t, int, const void *, int64_t, void *, void *, void *>, cudaGraphExec_t> graphs;
@@ -135,7 +137,7 @@ extern "C" int b200_comm_free(b200_comm *c) {
     cudaDeviceSynchronize();
     for (auto &kv : c->graphs) cudaGraphExecDestroy(kv.second);
     if (c->comm) c->api->CommDestroy(c->comm);
-    for (void *p : {c->send, c->recv, (void *)c->d_counters, c->host_stage})
+    for (void *p : {c->send, c->recv, (void *)c->d_counters, c->host_stage, c->d_host_out})
         if (p) cudaFree(p);
     delete c;
     return B200_OK;
@@ -200,6 +202,41 @@ extern "C" int b200_comm_gather_merge(b200_comm *c, int64_t nq, int k, int desce
                                      reinterpret_cast<const int64_t *>(reinterpret_cast<const char *>(c->recv) + (size_t)nq * k * 4), c->world,
                                      (int64_t)(rec / 4), (int64_t)(rec / 8), nq, k, k, descending, 0, d_out_dis, d_out_ids, nullptr,
                                      stream ? stream : nullptr);
+}
+
+// Host-buffer form for lists that are produced on the host (the per-shard BM25 top-k of b200_bm25_search_batch): uploads
+// this rank's [nq][k] scores / ids (unused slots: score -inf (descending) or +inf, id -1), all-gathers + merges, and
+// returns the table-wide top-k to the host.  Synchronous.
+extern "C" int b200_comm_gather_merge_host(b200_comm *c, const float *h_dis, const int64_t *h_ids, int64_t nq, int k, int descending,
+                                           float *h_out_dis, int64_t *h_out_ids) {
+    if (!c || !h_dis || !h_ids || !h_out_dis || !h_out_ids || nq < 0 || k <= 0) return fail(B200_ERR_INVALID, "bad arguments");
+    if (nq == 0) return B200_OK;
+    if (c->world == 1) {
+        if (h_out_dis != h_dis) memcpy(h_out_dis, h_dis, (size_t)nq * k * 4);
+        if (h_out_ids != h_ids) memcpy(h_out_ids, h_ids, (size_t)nq * k * 8);
+        return B200_OK;
+    }
+    float *d_dis = nullptr;
+    int64_t *d_ids = nullptr;
+    B200_TRY(b200_comm_local_buffers(c, nq, k, &d_dis, &d_ids));
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t nd = (size_t)nq * k * 4, ni = (size_t)nq * k * 8;
+    if (nd + ni > c->host_out_cap) {
+        if (c->d_host_out) cudaFree(c->d_host_out);
+        c->d_host_out = nullptr;
+        c->host_out_cap = 0;
+        B200_CUDA_OK(cudaMalloc(&c->d_host_out, nd + ni + 256));
+        c->host_out_cap = nd + ni + 256;
+    }
+    float *o_dis = reinterpret_cast<float *>(c->d_host_out);
+    int64_t *o_ids = reinterpret_cast<int64_t *>(reinterpret_cast<char *>(c->d_host_out) + ((nd + 7) & ~(size_t)7));
+    B200_CUDA_OK(cudaMemcpyAsync(d_dis, h_dis, nd, cudaMemcpyHostToDevice, nullptr));
+    B200_CUDA_OK(cudaMemcpyAsync(d_ids, h_ids, ni, cudaMemcpyHostToDevice, nullptr));
+    B200_TRY(b200_comm_gather_merge(c, nq, k, descending, o_dis, o_ids, nullptr));
+    B200_CUDA_OK(cudaMemcpyAsync(h_out_dis, o_dis, nd, cudaMemcpyDeviceToHost, nullptr));
+    B200_CUDA_OK(cudaMemcpyAsync(h_out_ids, o_ids, ni, cudaMemcpyDeviceToHost, nullptr));
+    B200_CUDA_OK(cudaStreamSynchronize(nullptr));
+    return B200_OK;
 }
 
 // table-wide statistics: in-place sum over the ranks of n uint64 counters held on the host

@@ -244,21 +244,58 @@ __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanPa
             }
             __syncthreads();
         }
-        for (int64_t c0 = (int64_t)warp * 32; c0 < ncand; c0 += kScanThreads) {
-            const int64_t c = c0 + lane;
-            float key = FLT_MAX;
-            uint32_t id = kNoId;
-            bool cand = false;
-            if (c < ncand) {
-                key = __ldcg(pkeys + c);
-                id = __ldcg(pids + c);
-                cand = id != kNoId && list.passes(key, id);
+        // Survivors of the bound are few (~k): every thread first sweeps its share of the candidates with independent loads
+        // (no vote between them, so the L2 latencies overlap) and appends survivors to a compact shared array; only those go
+        // through the warp lists.  (The first version voted after every load: 12 dependent L2 round trips, ~12 us of a 45 us call.)
+        __shared__ float cand_k[1024];
+        __shared__ uint32_t cand_i[1024];
+        __shared__ int cand_n;
+        if (threadIdx.x == 0) cand_n = 0;
+        __syncthreads();
+        const float bound_key = list.thr_key;
+        for (int64_t c = threadIdx.x; c < ncand; c += kScanThreads) {
+            const uint32_t id = __ldcg(pids + c);
+            const float key = __ldcg(pkeys + c);
+            if (id != kNoId && key <= bound_key) {
+                const int pos = atomicAdd(&cand_n, 1);
+                if (pos < 1024) {
+                    cand_k[pos] = key;
+                    cand_i[pos] = id;
+                }
             }
-            unsigned m = __ballot_sync(0xffffffffu, cand);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                list.insert(__shfl_sync(0xffffffffu, key, src), __shfl_sync(0xffffffffu, id, src));
+        }
+        __syncthreads();
+        const int n_surv = cand_n;
+        if (n_surv <= 1024) {
+            for (int c0 = warp * 32; c0 < n_surv; c0 += kScanThreads) {
+                const int c = c0 + lane;
+                const float key = c < n_surv ? cand_k[c] : FLT_MAX;
+                const uint32_t id = c < n_surv ? cand_i[c] : kNoId;
+                unsigned m = __ballot_sync(0xffffffffu, c < n_surv && list.passes(key, id));
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    list.insert(__shfl_sync(0xffffffffu, key, src), __shfl_sync(0xffffffffu, id, src));
+                }
+            }
+        } else {
+            // more survivors than the compact array holds (huge k or many ties): the plain sweep
+            for (int64_t c0 = (int64_t)warp * 32; c0 < ncand; c0 += kScanThreads) {
+                const int64_t c = c0 + lane;
+                float key = FLT_MAX;
+                uint32_t id = kNoId;
+                bool cand = false;
+                if (c < ncand) {
+                    key = __ldcg(pkeys + c);
+                    id = __ldcg(pids + c);
+                    cand = id != kNoId && list.passes(key, id);
+                }
+                unsigned m = __ballot_sync(0xffffffffu, cand);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    list.insert(__shfl_sync(0xffffffffu, key, src), __shfl_sync(0xffffffffu, id, src));
+                }
             }
         }
         __syncthreads();

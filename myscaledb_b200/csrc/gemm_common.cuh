@@ -46,7 +46,7 @@ struct Cfg {
         return st;
     }
     __host__ __device__ static bool lists_fit(int k) {
-        return k <= kGemmSmemK && off_list(2) + k * EPI_THREADS * 8 + SMEM_ALIGN_SLACK <= 232448;
+        return off_list(2) + k * EPI_THREADS * 8 + SMEM_ALIGN_SLACK <= 232448;   // k: slots per list
     }
 };
 
@@ -225,12 +225,109 @@ struct ThreadTopK {
     float *keys;
     uint32_t *ids;
     int k, n, worst;
+    int cap;           // slots of the buffer: == k -> "rescan" mode, > k (>= k + 32) -> "append" mode, see below
     float thr_key;     // key of the current worst kept element (FLT_MAX while n < k)
     uint32_t thr_id;
 };
 
+// Two ways to keep the k best:
+//  * rescan (cap == k): an accepted candidate overwrites the worst entry and the list is rescanned for the new worst --
+//    O(k) dependent-free loads per insert.  Right for small k (the k = 10 headline): the threshold is always exact.
+//  * append (cap > k): an accepted candidate is stored behind the others (two stores, nothing to wait for); when some lane
+//    of the warp is within 32 slots of the end, EVERY lane of the warp compacts its own buffer in lock-step (quickselect
+//    for the k-th entry, then one partition pass) and tightens its threshold.  An insert no longer costs the other 31
+//    lanes a k-entry rescan: at k = 100 the rescans were 2/3 of the launch (36 ms against 12 ms at k = 10; 125 ms with
+//    the lists in global scratch), and in the IVF scan, where every work item starts with empty lists, they were most of
+//    the kernel.  Between compactions the threshold is stale (it is the k-th key of the previous compaction), which only
+//    lets a few more candidates through.
+// (slot counts: list_cap_for / list_cap_append in kernels.h)
+
+struct ListThr {
+    float key;
+    uint32_t id;
+};
+
+// Keep the k best of this thread's n (> k) entries in slots [0, k) and return the k-th (the new threshold).  Entries are
+// distinct (unique ids), so (key, id) is a strict total order and exactly one entry has rank k.  Quickselect without
+// moving data: the pivot's rank is counted in one pass, which also picks the next pivot on either side pseudo-randomly
+// (smallest multiplicative hash of the slot), so sorted input does not degrade it.  All lanes of a warp run this together.
+static __device__ __noinline__ ListThr list_compact(float *keys, uint32_t *ids, int k, int n) {
+    float lo_k = 0.f, hi_k = 0.f;          // open interval (lo, hi) that still contains the rank-k entry
+    uint32_t lo_i = 0, hi_i = 0;
+    bool have_lo = false, have_hi = false;
+    float pk = keys[(n - 1) * EPI_THREADS];
+    uint32_t pi = ids[(n - 1) * EPI_THREADS];
+    uint32_t salt = 0x9E3779B1u;
+    for (;;) {
+        int rank = 0;
+        float ck_lo = 0.f, ck_hi = 0.f;
+        uint32_t ci_lo = 0, ci_hi = 0, h_lo = 0xffffffffu, h_hi = 0xffffffffu;
+        for (int j = 0; j < n; j++) {
+            const float kj = keys[j * EPI_THREADS];
+            const uint32_t ij = ids[j * EPI_THREADS];
+            const uint32_t h = ((uint32_t)j + 1u) * salt;
+            if (better(kj, ij, pk, pi)) {
+                rank++;
+                if ((!have_lo || better(lo_k, lo_i, kj, ij)) && h <= h_lo) {
+                    h_lo = h;
+                    ck_lo = kj;
+                    ci_lo = ij;
+                }
+            } else if (better(pk, pi, kj, ij)) {
+                if ((!have_hi || better(kj, ij, hi_k, hi_i)) && h <= h_hi) {
+                    h_hi = h;
+                    ck_hi = kj;
+                    ci_hi = ij;
+                }
+            }
+        }
+        rank++;  // the pivot itself
+        if (rank == k) break;
+        if (rank < k) {          // the answer is worse than the pivot
+            lo_k = pk; lo_i = pi; have_lo = true;
+            pk = ck_hi; pi = ci_hi;
+        } else {
+            hi_k = pk; hi_i = pi; have_hi = true;
+            pk = ck_lo; pi = ci_lo;
+        }
+        salt = salt * 0x85EBCA6Bu + 0xC2B2AE35u;
+        salt |= 1u;
+    }
+    // partition: kept entries found behind slot k fill the slots of dropped entries in front of it
+    int dst = 0;
+    for (int j = k; j < n; j++) {
+        const float kj = keys[j * EPI_THREADS];
+        const uint32_t ij = ids[j * EPI_THREADS];
+        if (!better(pk, pi, kj, ij)) {   // kj <= pivot: kept
+            while (!better(pk, pi, keys[dst * EPI_THREADS], ids[dst * EPI_THREADS])) dst++;   // skip kept entries
+            keys[dst * EPI_THREADS] = kj;
+            ids[dst * EPI_THREADS] = ij;
+            dst++;
+        }
+    }
+    ListThr r;
+    r.key = pk;
+    r.id = pi;
+    return r;
+}
+
+__device__ __forceinline__ void list_compact_if_over(ThreadTopK &t) {
+    if (t.n > t.k) {
+        const ListThr r = list_compact(t.keys, t.ids, t.k, t.n);
+        t.n = t.k;
+        t.thr_key = r.key;
+        t.thr_id = r.id;
+    }
+}
+
 __device__ __forceinline__ void list_insert(ThreadTopK &t, float key, uint32_t id) {
     if (!better(key, id, t.thr_key, t.thr_id)) return;
+    if (t.cap > t.k) {   // append mode: the caller keeps n + 32 <= cap before every chunk (epilogue_chunk)
+        t.keys[t.n * EPI_THREADS] = key;
+        t.ids[t.n * EPI_THREADS] = id;
+        t.n++;
+        return;
+    }
     if (t.n < t.k) {
         t.keys[t.n * EPI_THREADS] = key;
         t.ids[t.n * EPI_THREADS] = id;
@@ -260,6 +357,7 @@ __device__ __forceinline__ void list_insert(ThreadTopK &t, float key, uint32_t i
 
 // sort the n kept entries best-first (insertion sort, once per kernel) and publish them
 static __device__ __noinline__ void list_publish(ThreadTopK &t, float *out_keys, uint32_t *out_ids) {
+    list_compact_if_over(t);
     for (int i = 1; i < t.n; i++) {
         const float ki = t.keys[i * EPI_THREADS];
         const uint32_t ii = t.ids[i * EPI_THREADS];
@@ -288,7 +386,7 @@ static __device__ __noinline__ void list_publish(ThreadTopK &t, float *out_keys,
 // scratch: this thread's column of a [32][EPI_THREADS] float array.
 __device__ __forceinline__ void epilogue_chunk(ThreadTopK &list, float (&v)[32], bool use_side, const float *scale,
                                                const float *bias, uint32_t id0, bool tail, int64_t n, float *scratch) {
-    const float thr = list.thr_key;
+    float thr = list.thr_key;
     bool mine;
     if (use_side) {
 #pragma unroll
@@ -315,6 +413,10 @@ __device__ __forceinline__ void epilogue_chunk(ThreadTopK &list, float (&v)[32],
         mine = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) >= -thr;
     }
     if (__any_sync(0xffffffffu, mine)) {
+        if (list.cap > list.k && __any_sync(0xffffffffu, list.n + 32 > list.cap)) {
+            list_compact_if_over(list);   // every lane, in lock-step: room for this chunk and a fresh threshold
+            thr = list.thr_key;
+        }
         uint32_t mask = 0;
 #pragma unroll
         for (int j = 0; j < 32; j++) {

@@ -234,6 +234,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         float *scratch = reinterpret_cast<float *>(smem + C::off_scratch(STAGES)) + et;
         ThreadTopK list;
         list.k = p.k;
+        list.cap = p.list_cap;
         list.n = 0;
         list.worst = 0;
         // rows past the batch (zero padding up to the tile size) must never pay for the slow path: nothing beats -FLT_MAX
@@ -241,10 +242,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         list.thr_id = 0;
         if (p.lists_in_smem) {
             list.keys = reinterpret_cast<float *>(smem + C::off_list(STAGES)) + row;
-            list.ids = reinterpret_cast<uint32_t *>(smem + C::off_list(STAGES) + (size_t)p.k * EPI_THREADS * 4) + row;
+            list.ids = reinterpret_cast<uint32_t *>(smem + C::off_list(STAGES) + (size_t)p.list_cap * EPI_THREADS * 4) + row;
         } else {
-            list.keys = p.list_keys_gmem + (size_t)blockIdx.x * p.k * EPI_THREADS + row;
-            list.ids = p.list_ids_gmem + (size_t)blockIdx.x * p.k * EPI_THREADS + row;
+            list.keys = p.list_keys_gmem + (size_t)blockIdx.x * p.list_cap * EPI_THREADS + row;
+            list.ids = p.list_ids_gmem + (size_t)blockIdx.x * p.list_cap * EPI_THREADS + row;
         }
         int as = 0;
         uint32_t aphase = 0;
@@ -340,12 +341,14 @@ template <int CG, int MC>
 static cudaError_t launch_cg(const CUtensorMap &map_q, const CUtensorMap &map_c, const GemmTopkParams &p_in, int grid,
                              cudaStream_t s) {
     GemmTopkParams p = p_in;
-    // Per-thread lists live in shared memory only while they leave a deep operand ring: at k = 100 they squeezed the ring to 2
-    // stages and the launch took 33 ms instead of 11.7 (the inserts are rare after the first tiles; a starved TMA -> MMA pipeline
-    // is paid on every tile).  Below `min_stages` the lists move to global scratch and the ring keeps its full depth.
-    static const int min_stages = getenv("B200_GEMM_LIST_SMEM_MIN_STAGES") ? atoi(getenv("B200_GEMM_LIST_SMEM_MIN_STAGES")) : (CG == 2 ? 5 : 3);
-    p.lists_in_smem = (Cfg<CG>::lists_fit(p.k) && Cfg<CG>::stages_for(p.k) >= min_stages) ? 1 : 0;
-    const int k_smem = p.lists_in_smem ? p.k : 0;
+    // Per-thread lists: k slots + rescan for k <= 16, an append buffer (list_cap_append(k) slots, compacted in lock-step) above.
+    // Rescan-mode lists must sit in shared memory (measured at k = 64 / 100: 22 / 36 ms in shared memory, 72 / 126 ms in global
+    // scratch -- every insert waits for k loads).  Append-mode lists only store on insert, so they may live in global scratch
+    // and leave the operand ring its full depth; they take shared memory while that still leaves `min_stages` stages.
+    static const int min_stages = getenv("B200_GEMM_LIST_SMEM_MIN_STAGES") ? atoi(getenv("B200_GEMM_LIST_SMEM_MIN_STAGES")) : (CG == 2 ? 4 : 3);
+    p.list_cap = list_cap_for(p.k);
+    p.lists_in_smem = (Cfg<CG>::lists_fit(p.list_cap) && (p.list_cap == p.k || Cfg<CG>::stages_for(p.list_cap) >= min_stages)) ? 1 : 0;
+    const int k_smem = p.lists_in_smem ? p.list_cap : 0;
     p.stages = Cfg<CG>::stages_for(k_smem);
     {
         static const int env_kps = getenv("B200_GEMM_KPS") ? atoi(getenv("B200_GEMM_KPS")) : 1;
@@ -375,8 +378,9 @@ static cudaError_t launch_cg(const CUtensorMap &map_q, const CUtensorMap &map_c,
 // how many clusters of CG * MC CTAs of this kernel can be co-resident (persistent grid upper bound)
 template <int CG, int MC>
 static int max_clusters(int k) {
-    static const int min_stages = getenv("B200_GEMM_LIST_SMEM_MIN_STAGES") ? atoi(getenv("B200_GEMM_LIST_SMEM_MIN_STAGES")) : (CG == 2 ? 5 : 3);
-    const int k_smem = (Cfg<CG>::lists_fit(k) && Cfg<CG>::stages_for(k) >= min_stages) ? k : 0;
+    static const int min_stages = getenv("B200_GEMM_LIST_SMEM_MIN_STAGES") ? atoi(getenv("B200_GEMM_LIST_SMEM_MIN_STAGES")) : (CG == 2 ? 4 : 3);
+    const int cap = list_cap_for(k);
+    const int k_smem = (Cfg<CG>::lists_fit(cap) && (cap == k || Cfg<CG>::stages_for(cap) >= min_stages)) ? cap : 0;
     const int stages = Cfg<CG>::stages_for(k_smem);
     const size_t smem = (size_t)Cfg<CG>::off_list(stages) + (size_t)k_smem * EPI_THREADS * 8 + SMEM_ALIGN_SLACK;
     auto kern = gemm_topk_kernel<CG, MC>;

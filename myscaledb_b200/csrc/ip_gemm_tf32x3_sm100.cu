@@ -327,6 +327,7 @@ gemm3_topk_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_cons
         float *scratch = reinterpret_cast<float *>(smem + C::OFF_SCRATCH) + et;
         ThreadTopK list;
         list.k = p.k;
+        list.cap = p.list_cap;
         list.n = 0;
         list.worst = 0;
         // rows past the batch (zero padding up to the tile size) must never pay for the slow path: nothing beats -FLT_MAX
@@ -334,10 +335,10 @@ gemm3_topk_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_cons
         list.thr_id = 0;
         if (p.lists_in_smem) {
             list.keys = reinterpret_cast<float *>(smem + C::OFF_LIST) + row;
-            list.ids = reinterpret_cast<uint32_t *>(smem + C::OFF_LIST + (size_t)p.k * EPI_THREADS * 4) + row;
+            list.ids = reinterpret_cast<uint32_t *>(smem + C::OFF_LIST + (size_t)p.list_cap * EPI_THREADS * 4) + row;
         } else {
-            list.keys = p.list_keys_gmem + (size_t)blockIdx.x * p.k * EPI_THREADS + row;
-            list.ids = p.list_ids_gmem + (size_t)blockIdx.x * p.k * EPI_THREADS + row;
+            list.keys = p.list_keys_gmem + (size_t)blockIdx.x * p.list_cap * EPI_THREADS + row;
+            list.ids = p.list_ids_gmem + (size_t)blockIdx.x * p.list_cap * EPI_THREADS + row;
         }
         int as = 0;
         uint32_t aphase = 0;
@@ -433,9 +434,10 @@ static cudaError_t launch3_cg(const CUtensorMap &map_qhi, const CUtensorMap &map
     using namespace gemm3;
     using C = Cfg3<CG>;
     GemmTopkParams p = p_in;
-    p.lists_in_smem = C::lists_fit(p.k) ? 1 : 0;
+    p.list_cap = list_cap_for(p.k);
+    p.lists_in_smem = C::lists_fit(p.list_cap) ? 1 : 0;
     p.stages = C::STAGES;
-    const size_t smem = (size_t)C::OFF_LIST + (p.lists_in_smem ? (size_t)p.k * EPI_THREADS * 8 : 0) + SMEM_ALIGN_SLACK;
+    const size_t smem = (size_t)C::OFF_LIST + (p.lists_in_smem ? (size_t)p.list_cap * EPI_THREADS * 8 : 0) + SMEM_ALIGN_SLACK;
     auto kern = gemm3_topk_kernel<CG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

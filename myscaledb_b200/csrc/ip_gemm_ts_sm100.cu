@@ -236,6 +236,7 @@ gemm_topk_ts_kernel(const __grid_constant__ CUtensorMap map_c, const GemmTopkPar
         float *scratch = reinterpret_cast<float *>(smem + C::OFF_SCRATCH) + et;
         ThreadTopK list;
         list.k = p.k;
+        list.cap = p.list_cap;
         list.n = 0;
         list.worst = 0;
         // rows past the batch (zero padding up to the tile size) must never pay for the slow path: nothing beats -FLT_MAX
@@ -243,10 +244,10 @@ gemm_topk_ts_kernel(const __grid_constant__ CUtensorMap map_c, const GemmTopkPar
         list.thr_id = 0;
         if (p.lists_in_smem) {
             list.keys = reinterpret_cast<float *>(smem + C::OFF_LIST) + row;
-            list.ids = reinterpret_cast<uint32_t *>(smem + C::OFF_LIST + (size_t)p.k * EPI_THREADS * 4) + row;
+            list.ids = reinterpret_cast<uint32_t *>(smem + C::OFF_LIST + (size_t)p.list_cap * EPI_THREADS * 4) + row;
         } else {
-            list.keys = p.list_keys_gmem + (size_t)blockIdx.x * p.k * EPI_THREADS + row;
-            list.ids = p.list_ids_gmem + (size_t)blockIdx.x * p.k * EPI_THREADS + row;
+            list.keys = p.list_keys_gmem + (size_t)blockIdx.x * p.list_cap * EPI_THREADS + row;
+            list.ids = p.list_ids_gmem + (size_t)blockIdx.x * p.list_cap * EPI_THREADS + row;
         }
         int as = 0;
         uint32_t aphase = 0;
@@ -313,9 +314,10 @@ gemm_topk_ts_kernel(const __grid_constant__ CUtensorMap map_c, const GemmTopkPar
 template <int TBN>
 static cudaError_t launch_ts(const CUtensorMap &map_c, const GemmTopkParams &p_in, int grid, cudaStream_t s) {
     GemmTopkParams p = p_in;
-    p.lists_in_smem = p.k <= 30 ? 1 : 0;
+    p.list_cap = list_cap_for(p.k);
+    p.lists_in_smem = p.list_cap <= 64 ? 1 : 0;
     size_t smem = TsCfg<TBN>::OFF_LIST + SMEM_ALIGN_SLACK;
-    if (p.lists_in_smem) smem += (size_t)p.k * EPI_THREADS * 8;
+    if (p.lists_in_smem) smem += (size_t)p.list_cap * EPI_THREADS * 8;
     cudaError_t e = cudaFuncSetAttribute(gemm_topk_ts_kernel<TBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};

@@ -1695,8 +1695,8 @@ static int search_device_locked(b200_index *ix, const float *d_queries, int64_t 
     gp.dsub = ix->dsub;
     gp.codebook_bytes = ix->payload == IVF_PRODUCER_PQ ? ix->m * 256 * ix->dsub * 2 : 0;
     if (k1 > kGemmSmemK || true) {  // global scratch for lists that do not fit in shared memory (the launcher decides)
-        B200_TRY(ix->w_lk.reserve((size_t)grid * 128 * k1 * 4));
-        B200_TRY(ix->w_li.reserve((size_t)grid * 128 * k1 * 4));
+        B200_TRY(ix->w_lk.reserve((size_t)grid * 128 * list_cap_append(k1) * 4));
+        B200_TRY(ix->w_li.reserve((size_t)grid * 128 * list_cap_append(k1) * 4));
         gp.list_keys_gmem = ix->w_lk.as<float>();
         gp.list_ids_gmem = ix->w_li.as<uint32_t>();
     }

@@ -29,7 +29,7 @@ struct IvfGemmParams {
     uint32_t *part_ids;
     float *part_worst;                // [parts] worst kept key when the list is full, else FLT_MAX
     float scale_const;                // -1 IP / cosine, -2 L2
-    float *list_keys_gmem;            // scratch when the per-thread lists do not fit in shared memory: [grid][k][128]
+    float *list_keys_gmem;            // scratch when the per-thread lists do not fit in shared memory: [grid][list_cap_append(k)][128]
     uint32_t *list_ids_gmem;
     int d_pad, k;
     int producer;                     // IVF_PRODUCER_*
@@ -38,7 +38,7 @@ struct IvfGemmParams {
     const void *codebook_bf16;        // PQ: [m][256][dsub] bf16
     int code_bytes, m, dsub, codebook_bytes;
     // filled in by the launcher
-    int stages, lists_in_smem, codebook_smem_off, coop_smem_off, coop_enabled;
+    int stages, lists_in_smem, list_cap, codebook_smem_off, coop_smem_off, coop_enabled;
 };
 
 // queries_bf16: gathered query rows [n_query_rows][d_pad] (bf16); pool_bf16: page pool [pool_rows][d_pad] (bf16 payload only)

@@ -158,12 +158,13 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         float *scratch = reinterpret_cast<float *>(smem + C::off_scratch(STAGES)) + et;
         ThreadTopK list;
         list.k = p.k;
+        list.cap = p.list_cap;
         if (p.lists_in_smem) {
             list.keys = reinterpret_cast<float *>(smem + C::off_list(STAGES)) + row;
-            list.ids = reinterpret_cast<uint32_t *>(smem + C::off_list(STAGES) + (size_t)p.k * EPI_THREADS * 4) + row;
+            list.ids = reinterpret_cast<uint32_t *>(smem + C::off_list(STAGES) + (size_t)p.list_cap * EPI_THREADS * 4) + row;
         } else {
-            list.keys = p.list_keys_gmem + (size_t)blockIdx.x * p.k * EPI_THREADS + row;
-            list.ids = p.list_ids_gmem + (size_t)blockIdx.x * p.k * EPI_THREADS + row;
+            list.keys = p.list_keys_gmem + (size_t)blockIdx.x * p.list_cap * EPI_THREADS + row;
+            list.ids = p.list_ids_gmem + (size_t)blockIdx.x * p.list_cap * EPI_THREADS + row;
         }
         // cooperative lists (items with <= kCoopMax queries), owned by the warp of TMEM lanes 0..31
         const CoopSmem cs = coop_smem_carve(smem + p.coop_smem_off, smem + C::off_scratch(STAGES), p.k);
@@ -255,6 +256,7 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                     __syncwarp();
                 }
             } else if ((uint32_t)row < item.q_count) {
+                list_compact_if_over(list);   // append form: at most k entries leave the item
                 const size_t part = (size_t)p.pair_part_base[item.q_begin + row] + item.chunk;
                 float *ok = p.part_keys + part * p.k;
                 uint32_t *oi = p.part_ids + part * p.k;
@@ -394,9 +396,12 @@ static cudaError_t launch_ivf(const CUtensorMap &map_q, const CUtensorMap &map_c
     const int coop_used = p.coop_enabled ? coop_bytes : 0;
     int stages = 4;
     p.lists_in_smem = 0;
-    if (p.k <= kGemmSmemK)
+    // every work item starts with empty lists, so inserts are frequent throughout: always the append form (gemm_common.cuh)
+    p.list_cap = list_cap_append(p.k);
+    if (const char *ev = getenv("B200_IVF_LIST_RESCAN")) if (atoi(ev)) p.list_cap = p.k;   // A/B: the round-2 first form
+    if (p.list_cap <= 2 * kGemmSmemK)
         for (int st = 4; st >= 3; st--)
-            if (need(st, p.k) + coop_used <= 232448) {
+            if (need(st, p.list_cap) + coop_used <= 232448) {
                 stages = st;
                 p.lists_in_smem = 1;
                 break;
@@ -406,7 +411,7 @@ static cudaError_t launch_ivf(const CUtensorMap &map_q, const CUtensorMap &map_c
         if (need(stages, 0) + coop_used > 232448) return cudaErrorInvalidValue;
     }
     p.stages = stages;
-    const int k_smem = p.lists_in_smem ? p.k : 0;
+    const int k_smem = p.lists_in_smem ? p.list_cap : 0;
     p.coop_smem_off = (int)round_up(Cfg<1>::off_list(stages) + k_smem * EPI_THREADS * 8, 16);
     p.codebook_smem_off = (int)round_up(p.coop_smem_off + coop_used, 16);
     const size_t smem = (size_t)need(stages, k_smem) + coop_used + 48;

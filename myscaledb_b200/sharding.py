@@ -136,6 +136,20 @@ class Comm:
                                                C.c_void_p(alive_ptr or None), C.c_int64(id_offset), C.c_void_p(out_dis_ptr),
                                                C.c_void_p(out_ids_ptr), C.c_void_p(stream)))
 
+    def gather_merge_host(self, dis, ids, descending: bool):
+        """Per-shard [nq][k] lists held on the host (BM25 top-k) -> the table-wide top-k on every rank."""
+        import numpy as np
+        from ._lib import lib
+        from .search import _check
+        dis = np.ascontiguousarray(dis, np.float32)
+        ids = np.ascontiguousarray(ids, np.int64)
+        nq, k = dis.shape
+        od, oi = np.empty_like(dis), np.empty_like(ids)
+        _check(lib().b200_comm_gather_merge_host(self._h, dis.ctypes.data_as(C.c_void_p), ids.ctypes.data_as(C.c_void_p), C.c_int64(nq),
+                                                 C.c_int(k), C.c_int(1 if descending else 0), od.ctypes.data_as(C.c_void_p),
+                                                 oi.ctypes.data_as(C.c_void_p)))
+        return od, oi
+
     def allreduce_sum_u64(self, counters):
         """In-place sum over the ranks (BM25 table-wide statistics); counters: list / array of non-negative ints."""
         import numpy as np

@@ -46,6 +46,8 @@ def test_filter_bitmaps_built_on_device_feed_the_device_searches():
     import ctypes as C
     torch = pytest.importorskip("torch")
     from myscaledb_b200._lib import lib
+    import myscaledb_b200 as b2
+    import oracle as orc
     from myscaledb_b200.search import _check
     rng = np.random.default_rng(9)
     n, d = 50_007, 64
