@@ -305,11 +305,16 @@ __global__ void __launch_bounds__(256) bm25_score_kernel(const Bm25ScoreParams p
 //      by doc (score added with explicit rn ops in clause order -> bit-identical to the term-at-a-time sums; a bit per matched
 //      query term for AND),
 //   3. sweeps the table: AND mask, alive bitmap, warp-cooperative top-k.
-// W is chosen per query on the host so that a range holds ~384 postings of its clauses together; a range that turns out
+// W is chosen per query on the host so that a range holds ~192 postings of its clauses together; a range that turns out
 // denser than the table can hold is halved on the fly.
 // ------------------------------------------------------------------------------------
-constexpr int kDaatSlots = 1024;          // per warp: doc u32 + score f32 + mask u64 = 16 KB
-constexpr int kDaatFill = 704;            // postings a table takes in one go (load factor ~0.69)
+constexpr int kDaatSlots = 512;           // per warp: doc u32 + score f32 + mask u64 = 8 KB (+ the list of occupied slots)
+constexpr int kDaatFill = 352;            // postings a table takes in one go (load factor ~0.69)
+constexpr int kDaatTarget = 192;          // postings per range the host aims for
+// bytes of shared memory per warp: the table and the u16 list of occupied slots (the sweep visits only those).  The first
+// version used 1024-slot tables (16 KB per warp, 1 CTA per SM) and swept all slots of every range: the kernel was bound by
+// dependent-load latency at 8 warps per SM (1.8 ms for 512 queries x 25 k postings); 8.7 KB per warp keeps 3 CTAs resident.
+constexpr int kDaatWarpBytes = kDaatSlots * 16 + ((kDaatFill * 2 + 15) / 16) * 16;
 constexpr uint32_t kDaatEmpty = 0xffffffffu;
 
 struct Bm25DaatParams {
@@ -346,9 +351,11 @@ __global__ void __launch_bounds__(256) bm25_daat_kernel(const Bm25DaatParams dp)
     __shared__ Clause cl[kMaxClauses];
     __shared__ uint32_t cur_s[8][kMaxClauses], end_s[8][kMaxClauses];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t *t_doc = reinterpret_cast<uint32_t *>(tables + (size_t)warp * kDaatSlots * 16);
+    uint32_t *t_doc = reinterpret_cast<uint32_t *>(tables + (size_t)warp * kDaatWarpBytes);
     float *t_score = reinterpret_cast<float *>(t_doc + kDaatSlots);
     unsigned long long *t_mask = reinterpret_cast<unsigned long long *>(t_score + kDaatSlots);
+    unsigned short *t_occ = reinterpret_cast<unsigned short *>(t_mask + kDaatSlots);   // slots claimed in the current range
+    __shared__ uint32_t n_occ_s[8];
     const uint32_t q = blockIdx.y;
     const uint32_t c0 = p.clause_begin[q], nc = p.clause_begin[q + 1] - c0;
     for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) cl[i] = p.clauses[c0 + i];
@@ -369,6 +376,8 @@ __global__ void __launch_bounds__(256) bm25_daat_kernel(const Bm25DaatParams dp)
             // cursors at the start of the first range
             for (uint32_t c = lane; c < nc; c += 32)
                 cur_s[warp][c] = gallop_lower_bound(p.post_docs + cl[c].offset, 0, cl[c].df, r_begin << lg);
+            for (int i = lane; i < kDaatSlots; i += 32) t_doc[i] = kDaatEmpty;   // once: the sweep leaves the table empty
+            if (lane == 0) n_occ_s[warp] = 0;
             __syncwarp();
             uint64_t d_lo = r_begin << lg;
             const uint64_t d_stop = (r_end << lg) < (uint64_t)p.n_docs ? (r_end << lg) : (uint64_t)p.n_docs;
@@ -394,8 +403,6 @@ __global__ void __launch_bounds__(256) bm25_daat_kernel(const Bm25DaatParams dp)
                 __syncwarp();
                 if (total) {
                     // ---- 2. accumulate clause after clause
-                    for (int i = lane; i < kDaatSlots; i += 32) t_doc[i] = kDaatEmpty;
-                    __syncwarp();
                     for (uint32_t c = 0; c < nc; c++) {
                         const uint32_t b = cur_s[warp][c], e = end_s[warp][c];
                         const uint32_t *docs = p.post_docs + cl[c].offset;
@@ -408,12 +415,13 @@ __global__ void __launch_bounds__(256) bm25_daat_kernel(const Bm25DaatParams dp)
                                 const float tf = (float)tfs[i];
                                 const float norm = p.caches[(size_t)clause_cache(cl[c]) * 256 + p.fieldnorm[(size_t)cl[c].field * p.n_docs + doc]];
                                 const float contrib = __fmul_rn(cl[c].weight, __fdiv_rn(tf, __fadd_rn(tf, norm)));
-                                uint32_t slot = (doc * 2654435761u) >> 22;   // 10 bits
+                                uint32_t slot = (doc * 2654435761u) >> 23;   // 9 bits
                                 for (;;) {
                                     const uint32_t prev = atomicCAS(&t_doc[slot], kDaatEmpty, doc);
                                     if (prev == kDaatEmpty) {   // first clause that contains this doc
                                         t_score[slot] = contrib;
                                         t_mask[slot] = bit;
+                                        t_occ[atomicAdd(&n_occ_s[warp], 1u)] = (unsigned short)slot;
                                         break;
                                     }
                                     if (prev == doc) {          // an earlier clause owns the slot: add in clause order
@@ -428,12 +436,17 @@ __global__ void __launch_bounds__(256) bm25_daat_kernel(const Bm25DaatParams dp)
                         __syncwarp();   // clause c is complete (and visible) before clause c + 1 touches the same docs
                     }
                     // ---- 3. sweep
-                    for (int i0 = 0; i0 < kDaatSlots; i0 += 32) {
-                        const int i = i0 + lane;
-                        const uint32_t doc = t_doc[i];
-                        bool cand = doc != kDaatEmpty;
+                    const int n_occ = (int)n_occ_s[warp];
+                    for (int i0 = 0; i0 < n_occ; i0 += 32) {
+                        const int i = i0 + lane < n_occ ? (int)t_occ[i0 + lane] : -1;
+                        uint32_t doc = kDaatEmpty;
+                        bool cand = i >= 0;
                         float key = FLT_MAX;
-                        if (cand && !p.operator_or && t_mask[i] != full_mask) cand = false;
+                        if (cand) {
+                            doc = t_doc[i];
+                            t_doc[i] = kDaatEmpty;   // leave the table empty for the next range
+                            if (!p.operator_or && t_mask[i] != full_mask) cand = false;
+                        }
                         if (cand) {
                             const uint32_t rid = p.row_id[doc];
                             cand = !p.alive || ((p.alive[rid >> 3] >> (rid & 7)) & 1);
@@ -447,6 +460,7 @@ __global__ void __launch_bounds__(256) bm25_daat_kernel(const Bm25DaatParams dp)
                             list.insert(__shfl_sync(0xffffffffu, key, src), __shfl_sync(0xffffffffu, doc, src));
                         }
                     }
+                    if (lane == 0) n_occ_s[warp] = 0;
                     __syncwarp();
                 }
                 for (uint32_t c = lane; c < nc; c += 32) cur_s[warp][c] = end_s[warp][c];
@@ -812,12 +826,12 @@ extern "C" int b200_bm25_search_batch(b200_bm25 *ix, const char *const *sentence
         B200_CUDA_OK(cudaFuncSetAttribute(bm25_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         bm25_score_kernel<<<dim3(bx, (unsigned)nq), 256, smem, s>>>(sp);
     } else {
-        // range width per query: ~384 postings of all its clauses per range
+        // range width per query: ~kDaatTarget postings of all its clauses per range
         std::vector<uint32_t> range_log2(nq, 8);
         for (int64_t q = 0; q < nq; q++) {
             uint64_t m_q = 0;
             for (uint32_t c = begin[q]; c < begin[q + 1]; c++) m_q += clauses[c].df;
-            const double w = m_q ? 384.0 * (double)nd / (double)m_q : (double)nd;
+            const double w = m_q ? (double)kDaatTarget * (double)nd / (double)m_q : (double)nd;
             uint32_t lg = 8;
             while (lg < 31 && (double)(1ull << (lg + 1)) <= w) lg++;
             range_log2[q] = lg;
@@ -827,7 +841,7 @@ extern "C" int b200_bm25_search_batch(b200_bm25 *ix, const char *const *sentence
         Bm25DaatParams dpp{};
         dpp.base = sp;
         dpp.range_log2 = reinterpret_cast<const uint32_t *>(ix->d_ranges.p);
-        const size_t smem = (size_t)8 * k * 8 + 16 + (size_t)8 * kDaatSlots * 16;
+        const size_t smem = (size_t)8 * k * 8 + 16 + (size_t)8 * kDaatWarpBytes;
         B200_CUDA_OK(cudaFuncSetAttribute(bm25_daat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         bm25_daat_kernel<<<dim3(bx, (unsigned)nq), 256, smem, s>>>(dpp);
     }

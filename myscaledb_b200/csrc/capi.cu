@@ -373,6 +373,14 @@ extern "C" int b200_corpus_size(const b200_corpus *c, int64_t *out_rows) {
     return B200_OK;
 }
 
+namespace b200 {
+// slots of a per-thread top-k list (kernels.h): k, unless B200_LIST_APPEND_MIN_K selects the append form for this k
+int list_cap_for(int k) {
+    static const int min_k = getenv("B200_LIST_APPEND_MIN_K") ? atoi(getenv("B200_LIST_APPEND_MIN_K")) : 0;
+    return (min_k > 0 && k >= min_k) ? list_cap_append(k) : k;
+}
+}  // namespace b200
+
 extern "C" int b200_corpus_set_path(b200_corpus *c, int path) {
     if (!c || path < 0 || path > 7) return fail(B200_ERR_INVALID, "path must be 0..7");
     std::lock_guard<std::mutex> lk(c->mu);
@@ -635,8 +643,8 @@ static int search_core(b200_corpus *c, const void *d_queries, int64_t nq, int k,
         gp.part_keys = c->w_pk.as<float>();
         gp.part_ids = c->w_pi.as<uint32_t>();
         {  // global scratch for the per-thread lists, used when they do not fit in shared memory (large k)
-            B200_TRY(c->w_lk.reserve((size_t)grid * 128 * list_cap_append(k) * 4));
-            B200_TRY(c->w_li.reserve((size_t)grid * 128 * list_cap_append(k) * 4));
+            B200_TRY(c->w_lk.reserve((size_t)grid * 128 * list_cap_for(k) * 4));
+            B200_TRY(c->w_li.reserve((size_t)grid * 128 * list_cap_for(k) * 4));
             gp.list_keys_gmem = c->w_lk.as<float>();
             gp.list_ids_gmem = c->w_li.as<uint32_t>();
         }

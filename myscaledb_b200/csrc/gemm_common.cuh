@@ -222,24 +222,44 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // (~400 cycles per insert, 1.7 ms of start-up "insert storm" per launch, profiles/r01_summary.md).
 // The buffer is sorted once, when the CTA publishes its partial list.
 struct ThreadTopK {
-    float *keys;
+    float *keys;       // entry j of this thread's list: keys[j * stride]
     uint32_t *ids;
     int k, n, worst;
     int cap;           // slots of the buffer: == k -> "rescan" mode, > k (>= k + 32) -> "append" mode, see below
+    int stride;        // EPI_THREADS: lists interleaved (entry j of all 128 lists side by side); 1: each list contiguous
+    int coop;          // warp-uniform: inserts are done by the whole warp, one (lane, candidate) at a time (needs stride 1)
     float thr_key;     // key of the current worst kept element (FLT_MAX while n < k)
     uint32_t thr_id;
 };
 
+// Layout and insert form by k (cap == k only; the append form keeps the interleaved layout):
+//  * k <= kListCoopMinK - 1: interleaved lists, each lane inserts into its own list (a rescan of <= 16 entries is as cheap as
+//    a warp-wide reduction);
+//  * larger k: contiguous lists and COOPERATIVE inserts.  A lane that inserts alone still makes its 31 neighbours wait
+//    (every lane is a different query), so the warp does the work together instead: the accepted candidate of one lane is
+//    broadcast, lane 0 overwrites that list's worst entry, all 32 lanes rescan the list (k / 32 entries each, conflict-free
+//    because the list is contiguous) and a shuffle arg-max yields the new worst -- ~80 cycles against ~8 k cycles for a
+//    one-lane rescan of k entries.  At k = 100 the one-lane form was 2/3 of the launch (36 ms against 12 ms at k = 10).
+constexpr int kListCoopMinK = 17;
+__device__ __forceinline__ void list_bind(ThreadTopK &t, float *keys_base, uint32_t *ids_base, int row, int k, int cap) {
+    t.k = k;
+    t.cap = cap;
+    t.coop = (cap == k && k >= kListCoopMinK) ? 1 : 0;
+    t.stride = t.coop ? 1 : EPI_THREADS;
+    t.keys = keys_base + (t.coop ? (size_t)row * cap : (size_t)row);
+    t.ids = ids_base + (t.coop ? (size_t)row * cap : (size_t)row);
+}
+
 // Two ways to keep the k best:
-//  * rescan (cap == k): an accepted candidate overwrites the worst entry and the list is rescanned for the new worst --
-//    O(k) dependent-free loads per insert.  Right for small k (the k = 10 headline): the threshold is always exact.
-//  * append (cap > k): an accepted candidate is stored behind the others (two stores, nothing to wait for); when some lane
-//    of the warp is within 32 slots of the end, EVERY lane of the warp compacts its own buffer in lock-step (quickselect
-//    for the k-th entry, then one partition pass) and tightens its threshold.  An insert no longer costs the other 31
-//    lanes a k-entry rescan: at k = 100 the rescans were 2/3 of the launch (36 ms against 12 ms at k = 10; 125 ms with
-//    the lists in global scratch), and in the IVF scan, where every work item starts with empty lists, they were most of
-//    the kernel.  Between compactions the threshold is stale (it is the k-th key of the previous compaction), which only
-//    lets a few more candidates through.
+//  * rescan (cap == k, the default): an accepted candidate overwrites the worst entry and the list is rescanned for the new
+//    worst -- O(k) dependent-free loads per insert; the threshold is always exact.
+//  * append (cap >= 2k + 32, opt-in): an accepted candidate is stored behind the others (two stores, nothing to wait for);
+//    when some lane of the warp is within 32 slots of the end, EVERY lane of the warp compacts its own buffer in lock-step
+//    (quickselect for the k-th entry, then one partition pass) and tightens its threshold.  Measured on a synthetic stream
+//    shaped like the flat kernel's epilogue (tests/cuda/list_perf.cu, profiles/r02_list_modes.md): in shared memory it
+//    halves the list cost at k = 100 (+8 ms against +21 ms per launch) and is equal at k <= 30, but it needs twice the
+//    slots -- 200 KB at k = 100, which the operand ring does not leave -- and from global scratch it is no better than
+//    the rescan form in shared memory.  The slack must be real: with k + 32 slots every slow-path event compacts (3x slower).
 // (slot counts: list_cap_for / list_cap_append in kernels.h)
 
 struct ListThr {
@@ -247,24 +267,32 @@ struct ListThr {
     uint32_t id;
 };
 
+// counters for tests/cuda/list_append_test.cu --perf (compiled in only there)
+#ifdef B200_LIST_STATS
+__device__ unsigned long long g_list_stats[4];   // slow-path events, compaction calls (warp level), quickselect rounds, appended entries
+#define B200_LIST_STAT(i, v) atomicAdd(&g_list_stats[i], (unsigned long long)(v))
+#else
+#define B200_LIST_STAT(i, v)
+#endif
+
 // Keep the k best of this thread's n (> k) entries in slots [0, k) and return the k-th (the new threshold).  Entries are
 // distinct (unique ids), so (key, id) is a strict total order and exactly one entry has rank k.  Quickselect without
 // moving data: the pivot's rank is counted in one pass, which also picks the next pivot on either side pseudo-randomly
 // (smallest multiplicative hash of the slot), so sorted input does not degrade it.  All lanes of a warp run this together.
-static __device__ __noinline__ ListThr list_compact(float *keys, uint32_t *ids, int k, int n) {
+static __device__ __noinline__ ListThr list_compact(float *keys, uint32_t *ids, int k, int n, int stride) {
     float lo_k = 0.f, hi_k = 0.f;          // open interval (lo, hi) that still contains the rank-k entry
     uint32_t lo_i = 0, hi_i = 0;
     bool have_lo = false, have_hi = false;
-    float pk = keys[(n - 1) * EPI_THREADS];
-    uint32_t pi = ids[(n - 1) * EPI_THREADS];
+    float pk = keys[(n - 1) * stride];
+    uint32_t pi = ids[(n - 1) * stride];
     uint32_t salt = 0x9E3779B1u;
     for (;;) {
         int rank = 0;
         float ck_lo = 0.f, ck_hi = 0.f;
         uint32_t ci_lo = 0, ci_hi = 0, h_lo = 0xffffffffu, h_hi = 0xffffffffu;
         for (int j = 0; j < n; j++) {
-            const float kj = keys[j * EPI_THREADS];
-            const uint32_t ij = ids[j * EPI_THREADS];
+            const float kj = keys[j * stride];
+            const uint32_t ij = ids[j * stride];
             const uint32_t h = ((uint32_t)j + 1u) * salt;
             if (better(kj, ij, pk, pi)) {
                 rank++;
@@ -282,6 +310,7 @@ static __device__ __noinline__ ListThr list_compact(float *keys, uint32_t *ids, 
             }
         }
         rank++;  // the pivot itself
+        B200_LIST_STAT(2, 1);
         if (rank == k) break;
         if (rank < k) {          // the answer is worse than the pivot
             lo_k = pk; lo_i = pi; have_lo = true;
@@ -296,12 +325,12 @@ static __device__ __noinline__ ListThr list_compact(float *keys, uint32_t *ids, 
     // partition: kept entries found behind slot k fill the slots of dropped entries in front of it
     int dst = 0;
     for (int j = k; j < n; j++) {
-        const float kj = keys[j * EPI_THREADS];
-        const uint32_t ij = ids[j * EPI_THREADS];
+        const float kj = keys[j * stride];
+        const uint32_t ij = ids[j * stride];
         if (!better(pk, pi, kj, ij)) {   // kj <= pivot: kept
-            while (!better(pk, pi, keys[dst * EPI_THREADS], ids[dst * EPI_THREADS])) dst++;   // skip kept entries
-            keys[dst * EPI_THREADS] = kj;
-            ids[dst * EPI_THREADS] = ij;
+            while (!better(pk, pi, keys[dst * stride], ids[dst * stride])) dst++;   // skip kept entries
+            keys[dst * stride] = kj;
+            ids[dst * stride] = ij;
             dst++;
         }
     }
@@ -313,7 +342,7 @@ static __device__ __noinline__ ListThr list_compact(float *keys, uint32_t *ids, 
 
 __device__ __forceinline__ void list_compact_if_over(ThreadTopK &t) {
     if (t.n > t.k) {
-        const ListThr r = list_compact(t.keys, t.ids, t.k, t.n);
+        const ListThr r = list_compact(t.keys, t.ids, t.k, t.n, t.stride);
         t.n = t.k;
         t.thr_key = r.key;
         t.thr_id = r.id;
@@ -323,27 +352,28 @@ __device__ __forceinline__ void list_compact_if_over(ThreadTopK &t) {
 __device__ __forceinline__ void list_insert(ThreadTopK &t, float key, uint32_t id) {
     if (!better(key, id, t.thr_key, t.thr_id)) return;
     if (t.cap > t.k) {   // append mode: the caller keeps n + 32 <= cap before every chunk (epilogue_chunk)
-        t.keys[t.n * EPI_THREADS] = key;
-        t.ids[t.n * EPI_THREADS] = id;
+        B200_LIST_STAT(3, 1);
+        t.keys[t.n * t.stride] = key;
+        t.ids[t.n * t.stride] = id;
         t.n++;
         return;
     }
     if (t.n < t.k) {
-        t.keys[t.n * EPI_THREADS] = key;
-        t.ids[t.n * EPI_THREADS] = id;
+        t.keys[t.n * t.stride] = key;
+        t.ids[t.n * t.stride] = id;
         t.n++;
         if (t.n < t.k) return;
     } else {
-        t.keys[t.worst * EPI_THREADS] = key;
-        t.ids[t.worst * EPI_THREADS] = id;
+        t.keys[t.worst * t.stride] = key;
+        t.ids[t.worst * t.stride] = id;
     }
     // rescan for the worst (largest key, ties -> larger id)
     float wk = t.keys[0];
     uint32_t wi = t.ids[0];
     int wp = 0;
     for (int j = 1; j < t.k; j++) {
-        const float kj = t.keys[j * EPI_THREADS];
-        const uint32_t ij = t.ids[j * EPI_THREADS];
+        const float kj = t.keys[j * t.stride];
+        const uint32_t ij = t.ids[j * t.stride];
         if (better(wk, wi, kj, ij)) {
             wk = kj;
             wi = ij;
@@ -359,21 +389,86 @@ __device__ __forceinline__ void list_insert(ThreadTopK &t, float key, uint32_t i
 static __device__ __noinline__ void list_publish(ThreadTopK &t, float *out_keys, uint32_t *out_ids) {
     list_compact_if_over(t);
     for (int i = 1; i < t.n; i++) {
-        const float ki = t.keys[i * EPI_THREADS];
-        const uint32_t ii = t.ids[i * EPI_THREADS];
+        const float ki = t.keys[i * t.stride];
+        const uint32_t ii = t.ids[i * t.stride];
         int j = i;
-        while (j > 0 && better(ki, ii, t.keys[(j - 1) * EPI_THREADS], t.ids[(j - 1) * EPI_THREADS])) {
-            t.keys[j * EPI_THREADS] = t.keys[(j - 1) * EPI_THREADS];
-            t.ids[j * EPI_THREADS] = t.ids[(j - 1) * EPI_THREADS];
+        while (j > 0 && better(ki, ii, t.keys[(j - 1) * t.stride], t.ids[(j - 1) * t.stride])) {
+            t.keys[j * t.stride] = t.keys[(j - 1) * t.stride];
+            t.ids[j * t.stride] = t.ids[(j - 1) * t.stride];
             j--;
         }
-        t.keys[j * EPI_THREADS] = ki;
-        t.ids[j * EPI_THREADS] = ii;
+        t.keys[j * t.stride] = ki;
+        t.ids[j * t.stride] = ii;
     }
     for (int j = 0; j < t.k; j++) {
-        out_keys[j] = j < t.n ? t.keys[j * EPI_THREADS] : FLT_MAX;
-        out_ids[j] = j < t.n ? t.ids[j * EPI_THREADS] : kNoId;
+        out_keys[j] = j < t.n ? t.keys[j * t.stride] : FLT_MAX;
+        out_ids[j] = j < t.n ? t.ids[j * t.stride] : kNoId;
     }
+}
+
+// Cooperative insert (t.coop): called by the whole warp; lane `src` contributes the candidate and owns the list.
+__device__ __forceinline__ void list_insert_coop(ThreadTopK &t, int src, float key, uint32_t id) {
+    const int lane = threadIdx.x & 31;
+    key = __shfl_sync(0xffffffffu, key, src);
+    id = __shfl_sync(0xffffffffu, id, src);
+    const float thr_key = __shfl_sync(0xffffffffu, t.thr_key, src);
+    const uint32_t thr_id = __shfl_sync(0xffffffffu, t.thr_id, src);
+    if (!better(key, id, thr_key, thr_id)) return;   // warp-uniform
+    const unsigned long long kp = __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(t.keys), src);
+    const unsigned long long ip = __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(t.ids), src);
+    float *lk = reinterpret_cast<float *>((uintptr_t)kp);
+    uint32_t *li = reinterpret_cast<uint32_t *>((uintptr_t)ip);
+    int n = __shfl_sync(0xffffffffu, t.n, src);
+    const int k = t.k;
+    if (n < k) {
+        if (lane == 0) {
+            lk[n] = key;
+            li[n] = id;
+        }
+        n++;
+        if (n < k) {
+            if (lane == src) t.n = n;
+            return;
+        }
+    } else {
+        const int worst = __shfl_sync(0xffffffffu, t.worst, src);
+        if (lane == 0) {
+            lk[worst] = key;
+            li[worst] = id;
+        }
+    }
+    __syncwarp();
+    // the new worst: every lane scans k / 32 entries, then a shuffle arg-max over (key, id)
+    float wk = 0.f;
+    uint32_t wi = 0;
+    int wp = -1;
+    for (int j = lane; j < k; j += 32) {
+        const float kj = lk[j];
+        const uint32_t ij = li[j];
+        if (wp < 0 || better(wk, wi, kj, ij)) {
+            wk = kj;
+            wi = ij;
+            wp = j;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ok = __shfl_xor_sync(0xffffffffu, wk, o);
+        const uint32_t oi = __shfl_xor_sync(0xffffffffu, wi, o);
+        const int op = __shfl_xor_sync(0xffffffffu, wp, o);
+        if (op >= 0 && (wp < 0 || better(wk, wi, ok, oi))) {
+            wk = ok;
+            wi = oi;
+            wp = op;
+        }
+    }
+    if (lane == src) {
+        t.n = n;
+        t.worst = wp;
+        t.thr_key = wk;
+        t.thr_id = wi;
+    }
+    __syncwarp();
 }
 
 // Filter one chunk of 32 accumulator columns of this thread's query row.
@@ -385,8 +480,9 @@ static __device__ __noinline__ void list_publish(ThreadTopK &t, float *out_keys,
 // ~1.3 ms "insert storm" per launch (profiles/r01_summary.md).
 // scratch: this thread's column of a [32][EPI_THREADS] float array.
 __device__ __forceinline__ void epilogue_chunk(ThreadTopK &list, float (&v)[32], bool use_side, const float *scale,
-                                               const float *bias, uint32_t id0, bool tail, int64_t n, float *scratch) {
-    float thr = list.thr_key;
+                                               const float *bias, uint32_t id0, bool tail, int64_t n, float *scratch,
+                                               float ext_bound = FLT_MAX /* a valid upper bound of the k-th key known from elsewhere */) {
+    float thr = fminf(list.thr_key, ext_bound);
     bool mine;
     if (use_side) {
 #pragma unroll
@@ -413,9 +509,11 @@ __device__ __forceinline__ void epilogue_chunk(ThreadTopK &list, float (&v)[32],
         mine = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) >= -thr;
     }
     if (__any_sync(0xffffffffu, mine)) {
+        if ((threadIdx.x & 31) == 0) B200_LIST_STAT(0, 1);
         if (list.cap > list.k && __any_sync(0xffffffffu, list.n + 32 > list.cap)) {
+            if ((threadIdx.x & 31) == 0) B200_LIST_STAT(1, 1);
             list_compact_if_over(list);   // every lane, in lock-step: room for this chunk and a fresh threshold
-            thr = list.thr_key;
+            thr = fminf(list.thr_key, ext_bound);
         }
         uint32_t mask = 0;
 #pragma unroll
@@ -428,11 +526,29 @@ __device__ __forceinline__ void epilogue_chunk(ThreadTopK &list, float (&v)[32],
             const int64_t left = n - (int64_t)id0;
             mask = left >= 32 ? mask : left <= 0 ? 0u : (mask & ((1u << left) - 1u));
         }
-        while (__any_sync(0xffffffffu, mask != 0)) {
-            if (mask) {
-                const int j = __ffs(mask) - 1;
-                mask &= mask - 1;
-                list_insert(list, scratch[j * EPI_THREADS], id0 + (uint32_t)j);
+        if (list.coop) {
+            // one (lane, candidate) at a time, the whole warp inserting
+            unsigned pending = __ballot_sync(0xffffffffu, mask != 0);
+            while (pending) {
+                const int src = __ffs(pending) - 1;
+                float ckey = 0.f;
+                uint32_t cid = 0;
+                if ((int)(threadIdx.x & 31) == src) {
+                    const int j = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    ckey = scratch[j * EPI_THREADS];
+                    cid = id0 + (uint32_t)j;
+                }
+                list_insert_coop(list, src, ckey, cid);
+                pending = __ballot_sync(0xffffffffu, mask != 0);
+            }
+        } else {
+            while (__any_sync(0xffffffffu, mask != 0)) {
+                if (mask) {
+                    const int j = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    list_insert(list, scratch[j * EPI_THREADS], id0 + (uint32_t)j);
+                }
             }
         }
     }

@@ -233,20 +233,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const bool use_side = p.row_scale || p.row_bias || p.alive || p.scale_const != -1.f;
         float *scratch = reinterpret_cast<float *>(smem + C::off_scratch(STAGES)) + et;
         ThreadTopK list;
-        list.k = p.k;
-        list.cap = p.list_cap;
         list.n = 0;
         list.worst = 0;
         // rows past the batch (zero padding up to the tile size) must never pay for the slow path: nothing beats -FLT_MAX
         list.thr_key = (qt * BM + row < p.nq_valid) ? FLT_MAX : -FLT_MAX;
         list.thr_id = 0;
-        if (p.lists_in_smem) {
-            list.keys = reinterpret_cast<float *>(smem + C::off_list(STAGES)) + row;
-            list.ids = reinterpret_cast<uint32_t *>(smem + C::off_list(STAGES) + (size_t)p.list_cap * EPI_THREADS * 4) + row;
-        } else {
-            list.keys = p.list_keys_gmem + (size_t)blockIdx.x * p.list_cap * EPI_THREADS + row;
-            list.ids = p.list_ids_gmem + (size_t)blockIdx.x * p.list_cap * EPI_THREADS + row;
-        }
+        if (p.lists_in_smem)
+            list_bind(list, reinterpret_cast<float *>(smem + C::off_list(STAGES)),
+                      reinterpret_cast<uint32_t *>(smem + C::off_list(STAGES) + (size_t)p.list_cap * EPI_THREADS * 4), row, p.k, p.list_cap);
+        else
+            list_bind(list, p.list_keys_gmem + (size_t)blockIdx.x * p.list_cap * EPI_THREADS,
+                      p.list_ids_gmem + (size_t)blockIdx.x * p.list_cap * EPI_THREADS, row, p.k, p.list_cap);
         int as = 0;
         uint32_t aphase = 0;
         for (int64_t t = worker; t < n_tiles; t += W) {
@@ -341,13 +338,12 @@ template <int CG, int MC>
 static cudaError_t launch_cg(const CUtensorMap &map_q, const CUtensorMap &map_c, const GemmTopkParams &p_in, int grid,
                              cudaStream_t s) {
     GemmTopkParams p = p_in;
-    // Per-thread lists: k slots + rescan for k <= 16, an append buffer (list_cap_append(k) slots, compacted in lock-step) above.
-    // Rescan-mode lists must sit in shared memory (measured at k = 64 / 100: 22 / 36 ms in shared memory, 72 / 126 ms in global
-    // scratch -- every insert waits for k loads).  Append-mode lists only store on insert, so they may live in global scratch
-    // and leave the operand ring its full depth; they take shared memory while that still leaves `min_stages` stages.
-    static const int min_stages = getenv("B200_GEMM_LIST_SMEM_MIN_STAGES") ? atoi(getenv("B200_GEMM_LIST_SMEM_MIN_STAGES")) : (CG == 2 ? 4 : 3);
+    // Per-thread lists sit in shared memory whenever they fit, even when that squeezes the operand ring: every insert rescans
+    // the list, and from global scratch that is k L2 round trips (measured at k = 64 / 100: 22 / 36 ms per launch with the lists
+    // in shared memory, 72 / 126 ms in global scratch; B200_GEMM_LIST_SMEM_MIN_STAGES raises the bar for experiments).
+    static const int min_stages = getenv("B200_GEMM_LIST_SMEM_MIN_STAGES") ? atoi(getenv("B200_GEMM_LIST_SMEM_MIN_STAGES")) : 2;
     p.list_cap = list_cap_for(p.k);
-    p.lists_in_smem = (Cfg<CG>::lists_fit(p.list_cap) && (p.list_cap == p.k || Cfg<CG>::stages_for(p.list_cap) >= min_stages)) ? 1 : 0;
+    p.lists_in_smem = (Cfg<CG>::lists_fit(p.list_cap) && Cfg<CG>::stages_for(p.list_cap) >= min_stages) ? 1 : 0;
     const int k_smem = p.lists_in_smem ? p.list_cap : 0;
     p.stages = Cfg<CG>::stages_for(k_smem);
     {
@@ -378,9 +374,9 @@ static cudaError_t launch_cg(const CUtensorMap &map_q, const CUtensorMap &map_c,
 // how many clusters of CG * MC CTAs of this kernel can be co-resident (persistent grid upper bound)
 template <int CG, int MC>
 static int max_clusters(int k) {
-    static const int min_stages = getenv("B200_GEMM_LIST_SMEM_MIN_STAGES") ? atoi(getenv("B200_GEMM_LIST_SMEM_MIN_STAGES")) : (CG == 2 ? 4 : 3);
+    static const int min_stages = getenv("B200_GEMM_LIST_SMEM_MIN_STAGES") ? atoi(getenv("B200_GEMM_LIST_SMEM_MIN_STAGES")) : 2;
     const int cap = list_cap_for(k);
-    const int k_smem = (Cfg<CG>::lists_fit(cap) && (cap == k || Cfg<CG>::stages_for(cap) >= min_stages)) ? cap : 0;
+    const int k_smem = (Cfg<CG>::lists_fit(cap) && Cfg<CG>::stages_for(cap) >= min_stages) ? cap : 0;
     const int stages = Cfg<CG>::stages_for(k_smem);
     const size_t smem = (size_t)Cfg<CG>::off_list(stages) + (size_t)k_smem * EPI_THREADS * 8 + SMEM_ALIGN_SLACK;
     auto kern = gemm_topk_kernel<CG, MC>;

@@ -326,20 +326,17 @@ gemm3_topk_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_cons
         const bool use_side = p.row_scale || p.row_bias || p.alive || p.scale_const != -1.f;
         float *scratch = reinterpret_cast<float *>(smem + C::OFF_SCRATCH) + et;
         ThreadTopK list;
-        list.k = p.k;
-        list.cap = p.list_cap;
         list.n = 0;
         list.worst = 0;
         // rows past the batch (zero padding up to the tile size) must never pay for the slow path: nothing beats -FLT_MAX
         list.thr_key = (qt * BM + row < p.nq_valid) ? FLT_MAX : -FLT_MAX;
         list.thr_id = 0;
-        if (p.lists_in_smem) {
-            list.keys = reinterpret_cast<float *>(smem + C::OFF_LIST) + row;
-            list.ids = reinterpret_cast<uint32_t *>(smem + C::OFF_LIST + (size_t)p.list_cap * EPI_THREADS * 4) + row;
-        } else {
-            list.keys = p.list_keys_gmem + (size_t)blockIdx.x * p.list_cap * EPI_THREADS + row;
-            list.ids = p.list_ids_gmem + (size_t)blockIdx.x * p.list_cap * EPI_THREADS + row;
-        }
+        if (p.lists_in_smem)
+            list_bind(list, reinterpret_cast<float *>(smem + C::OFF_LIST),
+                      reinterpret_cast<uint32_t *>(smem + C::OFF_LIST + (size_t)p.list_cap * EPI_THREADS * 4), row, p.k, p.list_cap);
+        else
+            list_bind(list, p.list_keys_gmem + (size_t)blockIdx.x * p.list_cap * EPI_THREADS,
+                      p.list_ids_gmem + (size_t)blockIdx.x * p.list_cap * EPI_THREADS, row, p.k, p.list_cap);
         int as = 0;
         uint32_t aphase = 0;
         for (int64_t t = worker; t < n_tiles; t += W) {

@@ -813,7 +813,7 @@ struct b200_index {
     std::mutex mu;
     // workspaces (grow-only)
     DevArr w_rows, w_assign_i, w_assign_d, w_u32a, w_u32b, w_u32c, w_u32d, w_cnt, w_plan, w_sort, w_q, w_qraw, w_probe, w_pd, w_items,
-        w_qbuf, w_inv, w_ppb, w_pconst, w_qconst, w_pk, w_pi, w_pw, w_lk, w_li, w_alive, w_od, w_oi, w_cand, w_host_q;
+        w_qbuf, w_inv, w_ppb, w_pconst, w_qconst, w_qb, w_pk, w_pi, w_pw, w_lk, w_li, w_alive, w_od, w_oi, w_cand, w_host_q;
     // statistics of the last search (tests, bench roofline): rows x payload bytes the scan kernel was asked to stream
     int64_t last_scan_rows = 0, last_items = 0;
     bool timing = false, timed_pending = false;
@@ -910,7 +910,7 @@ extern "C" int b200_index_free(b200_index *ix) {
                     (void *)ix->d_pages_used, (void *)ix->d_flag, (void *)ix->d_list_page_off, (void *)ix->d_list_pages, (void *)ix->d_list_order})
         if (p) cudaFree(p);
     for (DevArr *a : {&ix->w_rows, &ix->w_assign_i, &ix->w_assign_d, &ix->w_u32a, &ix->w_u32b, &ix->w_u32c, &ix->w_u32d, &ix->w_cnt, &ix->w_plan,
-                      &ix->w_sort, &ix->w_q, &ix->w_qraw, &ix->w_probe, &ix->w_pd, &ix->w_items, &ix->w_qbuf, &ix->w_inv, &ix->w_ppb, &ix->w_pconst,
+                      &ix->w_sort, &ix->w_q, &ix->w_qraw, &ix->w_probe, &ix->w_pd, &ix->w_items, &ix->w_qbuf, &ix->w_inv, &ix->w_ppb, &ix->w_pconst, &ix->w_qb,
                       &ix->w_qconst, &ix->w_pk, &ix->w_pi, &ix->w_pw, &ix->w_lk, &ix->w_li, &ix->w_alive, &ix->w_od, &ix->w_oi, &ix->w_cand,
                       &ix->w_host_q})
         a->release();
@@ -1563,7 +1563,8 @@ static int search_device_locked(b200_index *ix, const float *d_queries, int64_t 
         // table bytes per 8-query pass) undercuts ~1 us per (query, 32 probes) of the tensor-core path.
         const double t_scan = (double)ceil_div(nq, 8) * nl * ix->d_pad * 4.0 / 1.4e12;
         const double t_gemm = 1e-6 * (double)nq * std::max(1.0, nprobe / 32.0) + 30e-6;
-        const bool use_scan = nprobe > 8 && t_scan < t_gemm;
+        bool use_scan = nprobe > 8 && t_scan < t_gemm;
+        if (const int forced = parse_int_param(params, "coarse_path", 0)) use_scan = forced == 1;   // A/B: 1 scan kernel, 2 tensor-core path
         b200_corpus_set_path(ix->coarse, use_scan ? 1 : 0);
         const int rc = b200_corpus_search_device(ix->coarse, ix->w_qraw.as<float>(), nq, nprobe, nullptr, 0, ix->w_pd.as<float>(), ix->w_probe.as<int64_t>(), s);
         b200_corpus_set_path(ix->coarse, 0);
@@ -1684,6 +1685,17 @@ static int search_device_locked(b200_index *ix, const float *d_queries, int64_t 
     gp.part_keys = ix->w_pk.as<float>();
     gp.part_ids = ix->w_pi.as<uint32_t>();
     gp.part_worst = ix->w_pw.as<float>();
+    {   // shared per-query bound across the items of this launch (ivf_gemm.h); nothing to share with one list per query
+        static const bool bound_on = !(getenv("B200_IVF_BOUND") && atoi(getenv("B200_IVF_BOUND")) == 0);
+        if (bound_on && nprobe > 1 && parse_int_param(params, "shared_bound", 1) != 0) {   // shared_bound=0: A/B switch
+            B200_TRY(ix->w_qb.reserve((size_t)nq * 4));
+            B200_CUDA_OK(cudaMemsetAsync(ix->w_qb.p, 0xff, (size_t)nq * 4, s));
+            gp.query_bound = ix->w_qb.as<uint32_t>();
+            gp.sorted_pair = ix->w_u32d.as<uint32_t>();
+            gp.pair_const = ix->w_pconst.as<float>();
+            gp.nprobe = nprobe;
+        }
+    }
     gp.scale_const = ix->metric == B200_METRIC_L2 ? -2.f : -1.f;
     gp.d_pad = ix->d_pad64;
     gp.k = k1;
@@ -1695,8 +1707,8 @@ static int search_device_locked(b200_index *ix, const float *d_queries, int64_t 
     gp.dsub = ix->dsub;
     gp.codebook_bytes = ix->payload == IVF_PRODUCER_PQ ? ix->m * 256 * ix->dsub * 2 : 0;
     if (k1 > kGemmSmemK || true) {  // global scratch for lists that do not fit in shared memory (the launcher decides)
-        B200_TRY(ix->w_lk.reserve((size_t)grid * 128 * list_cap_append(k1) * 4));
-        B200_TRY(ix->w_li.reserve((size_t)grid * 128 * list_cap_append(k1) * 4));
+        B200_TRY(ix->w_lk.reserve((size_t)grid * 128 * list_cap_for(k1) * 4));
+        B200_TRY(ix->w_li.reserve((size_t)grid * 128 * list_cap_for(k1) * 4));
         gp.list_keys_gmem = ix->w_lk.as<float>();
         gp.list_ids_gmem = ix->w_li.as<uint32_t>();
     }

@@ -29,7 +29,7 @@ struct IvfGemmParams {
     uint32_t *part_ids;
     float *part_worst;                // [parts] worst kept key when the list is full, else FLT_MAX
     float scale_const;                // -1 IP / cosine, -2 L2
-    float *list_keys_gmem;            // scratch when the per-thread lists do not fit in shared memory: [grid][list_cap_append(k)][128]
+    float *list_keys_gmem;            // scratch when the per-thread lists do not fit in shared memory: [grid][list_cap_for(k)][128]
     uint32_t *list_ids_gmem;
     int d_pad, k;
     int producer;                     // IVF_PRODUCER_*
@@ -38,6 +38,13 @@ struct IvfGemmParams {
     const void *codebook_bf16;        // PQ: [m][256][dsub] bf16
     int code_bytes, m, dsub, codebook_bytes;
     // filled in by the launcher
+    // Per-query bound shared by all the work items of a launch (nprobe > 1): query_bound[q] is the smallest k-th key
+    // (order-preserving u32 encoding, 0xffffffff = none yet) any FULL partial list of query q has published, in absolute key space
+    // (item key + pair_const).  Items read it once per page and filter with it: far lists stop inserting once a near list is done.
+    uint32_t *query_bound;            // [nq] or null
+    const uint32_t *sorted_pair;      // [n_pairs] sorted position -> original pair index (query = pair / nprobe)
+    const float *pair_const;          // [n_pairs]
+    int nprobe;
     int stages, lists_in_smem, list_cap, codebook_smem_off, coop_smem_off, coop_enabled;
 };
 

@@ -35,6 +35,13 @@ constexpr int IVF_DEC_WARPS = 4;           // extra decoder warps of the code pa
 constexpr int IVF_THREADS_DEC = IVF_THREADS_TMA + IVF_DEC_WARPS * 32;
 
 // smem (PRODUCER_TMA): the Cfg<1> layout of ip_gemm_sm100.cu.  Code payloads add a codebook region behind the lists.
+// order-preserving float <-> u32 (atomicMin on the encoding = min of the floats)
+__device__ __forceinline__ uint32_t bound_encode(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float bound_decode(uint32_t u) { return (u & 0x80000000u) ? __uint_as_float(u & 0x7fffffffu) : __uint_as_float(~u); }
+
 template <int PRODUCER, int DSUB>
 __global__ void __launch_bounds__(PRODUCER == IVF_PRODUCER_TMA ? IVF_THREADS_TMA : IVF_THREADS_DEC, 1)
 ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c, const IvfGemmParams p) {
@@ -157,15 +164,12 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const int et = threadIdx.x - 64;
         float *scratch = reinterpret_cast<float *>(smem + C::off_scratch(STAGES)) + et;
         ThreadTopK list;
-        list.k = p.k;
-        list.cap = p.list_cap;
-        if (p.lists_in_smem) {
-            list.keys = reinterpret_cast<float *>(smem + C::off_list(STAGES)) + row;
-            list.ids = reinterpret_cast<uint32_t *>(smem + C::off_list(STAGES) + (size_t)p.list_cap * EPI_THREADS * 4) + row;
-        } else {
-            list.keys = p.list_keys_gmem + (size_t)blockIdx.x * p.list_cap * EPI_THREADS + row;
-            list.ids = p.list_ids_gmem + (size_t)blockIdx.x * p.list_cap * EPI_THREADS + row;
-        }
+        if (p.lists_in_smem)
+            list_bind(list, reinterpret_cast<float *>(smem + C::off_list(STAGES)),
+                      reinterpret_cast<uint32_t *>(smem + C::off_list(STAGES) + (size_t)p.list_cap * EPI_THREADS * 4), row, p.k, p.list_cap);
+        else
+            list_bind(list, p.list_keys_gmem + (size_t)blockIdx.x * p.list_cap * EPI_THREADS,
+                      p.list_ids_gmem + (size_t)blockIdx.x * p.list_cap * EPI_THREADS, row, p.k, p.list_cap);
         // cooperative lists (items with <= kCoopMax queries), owned by the warp of TMEM lanes 0..31
         const CoopSmem cs = coop_smem_carve(smem + p.coop_smem_off, smem + C::off_scratch(STAGES), p.k);
         float *tile_row = cs.tilebuf + (size_t)(lane < kCoopMax ? lane : 0) * kTileBufStride;
@@ -179,6 +183,13 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             list.thr_key = ((uint32_t)row < item.q_count) ? FLT_MAX : -FLT_MAX;   // padding slots never enter the slow path
             list.thr_id = 0;
             float coop_thr = list.thr_key;
+            // shared per-query bound (nprobe > 1): this lane's query and the constant that makes its keys absolute
+            uint32_t *bound_slot = nullptr;
+            float pc = 0.f, last_pub = FLT_MAX;
+            if (p.query_bound && (uint32_t)row < item.q_count) {
+                bound_slot = p.query_bound + p.sorted_pair[item.q_begin + row] / (uint32_t)p.nprobe;
+                pc = p.pair_const ? p.pair_const[item.q_begin + row] : 0.f;
+            }
             if (coop && quarter == 0) {
                 if (lane < kCoopMax) {
                     CoopState st;
@@ -195,6 +206,8 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 const uint32_t page = p.list_pages[item.page_begin + j];
                 const uint32_t row0 = page * (uint32_t)BN;
                 const uint32_t valid = item.row_limit - j * (uint32_t)BN;   // rows of the list left from this page on (>= 1)
+                uint32_t bound_u = 0xffffffffu;
+                if (bound_slot) bound_u = __ldcg(bound_slot);   // in flight while the side arrays are built
                 asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers done
                 for (int c = et; c < BN; c += EPI_THREADS) {
                     bool ok = (uint32_t)c < valid;
@@ -211,6 +224,14 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
                 float va[32], vb[32];
                 uint32_t chunk_mask = 0;
+                // the bound in this item's key space, a few ulps loose (the merge adds pair_const back in fp32); superset-safe
+                float ext = FLT_MAX;
+                if (bound_u != 0xffffffffu) {
+                    const float g = bound_decode(bound_u);
+                    ext = g - pc;
+                    ext += (fabsf(ext) + fabsf(pc) + fabsf(g)) * 4e-7f;
+                }
+                const float coop_flt = (coop_thr != coop_thr) ? coop_thr : fminf(coop_thr, ext);   // NaN (no query on this lane) stays NaN
                 __syncwarp();
                 tmem_ld32_issue(taddr, va);
                 tmem_ld_wait();
@@ -218,20 +239,28 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 for (int chunk = 0; chunk < BN / 32; chunk += 2) {
                     __syncwarp();
                     tmem_ld32_issue(taddr + (chunk + 1) * 32, vb);
-                    if (coop) coop_stage_chunk(coop_thr, va, side_scale + chunk * 32, side_bias + chunk * 32, tile_row, chunk, chunk_mask, lane);
-                    else epilogue_chunk(list, va, true, side_scale + chunk * 32, side_bias + chunk * 32, row0 + chunk * 32, false, 0, scratch);
+                    if (coop) coop_stage_chunk(coop_flt, va, side_scale + chunk * 32, side_bias + chunk * 32, tile_row, chunk, chunk_mask, lane);
+                    else epilogue_chunk(list, va, true, side_scale + chunk * 32, side_bias + chunk * 32, row0 + chunk * 32, false, 0, scratch, ext);
                     tmem_ld_wait();
                     __syncwarp();
                     if (chunk + 2 < BN / 32) tmem_ld32_issue(taddr + (chunk + 2) * 32, va);
-                    if (coop) coop_stage_chunk(coop_thr, vb, side_scale + (chunk + 1) * 32, side_bias + (chunk + 1) * 32, tile_row, chunk + 1, chunk_mask, lane);
+                    if (coop) coop_stage_chunk(coop_flt, vb, side_scale + (chunk + 1) * 32, side_bias + (chunk + 1) * 32, tile_row, chunk + 1, chunk_mask, lane);
                     else epilogue_chunk(list, vb, true, side_scale + (chunk + 1) * 32, side_bias + (chunk + 1) * 32,
-                                        row0 + (chunk + 1) * 32, false, 0, scratch);
+                                        row0 + (chunk + 1) * 32, false, 0, scratch, ext);
                     tmem_ld_wait();
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);   // the accumulator is free: the merge below runs beside the next tile's MMAs
                 if (coop && quarter == 0) coop_merge_tile(cs, p.k, (int)item.q_count, chunk_mask, row0, lane, coop_thr);
+                // publish: a full list's k-th key bounds the query's k-th key over all its lists
+                if (bound_slot) {
+                    const float mine_thr = coop ? coop_thr : (list.n == list.k ? list.thr_key : FLT_MAX);
+                    if (mine_thr < last_pub) {
+                        last_pub = mine_thr;
+                        atomicMin(bound_slot, bound_encode(mine_thr + pc));
+                    }
+                }
                 if (++as == ACC_STAGES) {
                     as = 0;
                     aphase ^= 1;
@@ -262,8 +291,8 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 uint32_t *oi = p.part_ids + part * p.k;
                 for (int e = 0; e < p.k; e++) {
                     const bool have = e < list.n;
-                    ok[e] = have ? list.keys[e * EPI_THREADS] : FLT_MAX;
-                    oi[e] = have ? p.row_ids[list.ids[e * EPI_THREADS]] : kNoId;
+                    ok[e] = have ? list.keys[e * list.stride] : FLT_MAX;
+                    oi[e] = have ? p.row_ids[list.ids[e * list.stride]] : kNoId;
                 }
                 p.part_worst[part] = list.n == p.k ? list.thr_key : FLT_MAX;
             }
@@ -396,9 +425,7 @@ static cudaError_t launch_ivf(const CUtensorMap &map_q, const CUtensorMap &map_c
     const int coop_used = p.coop_enabled ? coop_bytes : 0;
     int stages = 4;
     p.lists_in_smem = 0;
-    // every work item starts with empty lists, so inserts are frequent throughout: always the append form (gemm_common.cuh)
-    p.list_cap = list_cap_append(p.k);
-    if (const char *ev = getenv("B200_IVF_LIST_RESCAN")) if (atoi(ev)) p.list_cap = p.k;   // A/B: the round-2 first form
+    p.list_cap = list_cap_for(p.k);
     if (p.list_cap <= 2 * kGemmSmemK)
         for (int st = 4; st >= 3; st--)
             if (need(st, p.list_cap) + coop_used <= 232448) {

@@ -83,7 +83,7 @@ struct GemmTopkParams {
     const uint8_t *alive;      // LSB-first bitmap or null
     float *part_keys;          // [gridDim.x][128][k]
     uint32_t *part_ids;
-    float *list_keys_gmem;     // scratch for lists that do not fit in shared memory: [gridDim.x][list_cap_append(k)][128]
+    float *list_keys_gmem;     // scratch for lists that do not fit in shared memory: [gridDim.x][list_cap_for(k)][128]
     uint32_t *list_ids_gmem;
     int64_t n;
     int nq_pad, d_pad, k;
@@ -102,11 +102,11 @@ struct GemmTopkParams {
 // per-thread top-k lists live in shared memory up to this k (the smem ring gets shallower: 6 stages up to k = 14,
 // 5 up to 46, 4 up to 78, 3 up to 110, 2 up to 128 for CTA pairs); larger k uses global scratch
 constexpr int kGemmSmemK = 128;
-// per-thread top-k lists (gemm_common.cuh, ThreadTopK): k slots and a rescan per insert for small k, an append buffer of
-// max(2k, k + 32) slots compacted in lock-step for larger k
-constexpr int kListRescanMaxK = 16;
-__host__ __device__ inline int list_cap_append(int k) { return 2 * k > k + 32 ? 2 * k : k + 32; }
-__host__ __device__ inline int list_cap_for(int k) { return k <= kListRescanMaxK ? k : list_cap_append(k); }
+// per-thread top-k lists (gemm_common.cuh, ThreadTopK): k slots and a rescan per insert (the default), or an append buffer
+// of 2k + 32 slots compacted in lock-step (B200_LIST_APPEND_MIN_K=<k>: lists of at least that k use it; measured in
+// profiles/r02_list_modes.md -- it only pays when the doubled buffer still fits in shared memory, which it does not at k = 100)
+__host__ __device__ inline int list_cap_append(int k) { return 2 * k + 32; }
+int list_cap_for(int k);   // capi.cu: k, or list_cap_append(k) when the environment asks for the append form
 int gemm_topk_grid(int q_tiles, int64_t n, int num_sms);
 // returns cudaSuccess or an error; tensor maps are encoded inside
 cudaError_t launch_gemm_topk(const GemmTopkParams &p, int grid, cudaStream_t s, const char **err_detail);

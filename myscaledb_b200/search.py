@@ -336,6 +336,31 @@ def hybrid_fusion_batch(fusion_type, vec_lists, txt_lists, top_k, fusion_weight=
             for q in range(nq)]
 
 
+def hybrid_fusion_arrays(fusion_type, vec_ids, vec_scores, txt_ids, txt_scores, top_k, fusion_weight=0.5, fusion_k=60,
+                         vector_scan_direction=1):
+    """Array form of hybrid_fusion_batch for one shard / part space: [nq][kv] vector ids (int64, -1 = unused slot) + distances and
+    [nq][kt] text ids + bm25 scores, both globally ordered.  Returns ([nq][top_k] ids (-1 padded), [nq][top_k] fused scores, counts)."""
+    vec_ids = np.ascontiguousarray(vec_ids, np.int64); txt_ids = np.ascontiguousarray(txt_ids, np.int64)
+    nq, kv = vec_ids.shape
+    kt = txt_ids.shape[1]
+    v_cnt = (vec_ids >= 0).sum(1).astype(np.uint32); t_cnt = (txt_ids >= 0).sum(1).astype(np.uint32)
+    v_la = np.where(vec_ids >= 0, vec_ids, 0).astype(np.uint64); t_la = np.where(txt_ids >= 0, txt_ids, 0).astype(np.uint64)
+    v_sc = np.ascontiguousarray(vec_scores, np.float32); t_sc = np.ascontiguousarray(np.where(txt_ids >= 0, txt_scores, 0), np.float32)
+    v_sh = np.zeros((nq, kv), np.uint32); v_pa = np.zeros((nq, kv), np.uint64)
+    t_sh = np.zeros((nq, kt), np.uint32); t_pa = np.zeros((nq, kt), np.uint64)
+    o_sh = np.zeros((nq, top_k), np.uint32); o_pa = np.zeros((nq, top_k), np.uint64)
+    o_la = np.zeros((nq, top_k), np.uint64); o_sc = np.zeros((nq, top_k), np.float32); o_cnt = np.zeros(nq, np.uint32)
+    ft = {"rsf": 0, "rrf": 1}[fusion_type.lower()]
+    _check(lib().b200_hybrid_fusion_batch(
+        C.c_int(ft), C.c_int64(nq), _p(v_sh, C.c_uint32), _p(v_pa, C.c_uint64), _p(v_la, C.c_uint64), _p(v_sc, C.c_float),
+        _p(v_cnt, C.c_uint32), C.c_int64(kv), _p(t_sh, C.c_uint32), _p(t_pa, C.c_uint64), _p(t_la, C.c_uint64),
+        _p(t_sc, C.c_float), _p(t_cnt, C.c_uint32), C.c_int64(kt), C.c_float(fusion_weight), C.c_uint64(fusion_k),
+        C.c_int(vector_scan_direction), C.c_uint32(top_k), _p(o_sh, C.c_uint32), _p(o_pa, C.c_uint64), _p(o_la, C.c_uint64),
+        _p(o_sc, C.c_float), _p(o_cnt, C.c_uint32)))
+    ids = np.where(np.arange(top_k)[None, :] < o_cnt[:, None], o_la.astype(np.int64), -1)
+    return ids, o_sc, o_cnt
+
+
 class VectorIndex:
     """Mirror of Search::VectorIndex as driven by VIWithColumnInPart (build / search / computeTopDistanceSubset,
     src/VectorIndex/Common/VIWithDataPart.cpp:131, :926, :838-856).  type: FLAT, IVFFLAT, IVFSQ, IVFPQ, MSTG, SCANN, HNSW*."""

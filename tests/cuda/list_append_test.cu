@@ -1,7 +1,8 @@
 // Unit test of the per-thread top-k list in its append form (csrc/gemm_common.cuh: list_insert / list_compact / epilogue_chunk /
 // list_publish) outside the tensor-core kernels: 128 threads = 128 independent "queries", each shown the same number of 32-wide
 // chunks of synthetic keys (heavy ties included); the published list of every thread must equal the k smallest (key, id) of
-// what it was shown -- for k in rescan mode (cap == k) and append mode, lists in shared or global memory.
+// what it was shown -- in the default form for the k (one-lane rescan up to 16, warp-cooperative above), the append form and the
+// one-lane form at every k.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -I myscaledb_b200/csrc tests/cuda/list_append_test.cu -o tests/cuda/list_append_test
 #include <algorithm>
 #include <cstdio>
@@ -13,19 +14,22 @@
 using namespace b200;
 using namespace b200::gemm;
 
-__global__ void list_test_kernel(const float *keys /*[chunks][128][32]*/, int chunks, int k, int cap, float *list_keys, uint32_t *list_ids,
+__global__ void list_test_kernel(const float *keys /*[chunks][128][32]*/, int chunks, int k, int cap, int force_single, float *list_keys, uint32_t *list_ids,
                                  float *out_keys, uint32_t *out_ids) {
     __shared__ float scratch_all[32 * EPI_THREADS];
     const int t = threadIdx.x;
     ThreadTopK list;
-    list.k = k;
-    list.cap = cap;
     list.n = 0;
     list.worst = 0;
     list.thr_key = FLT_MAX;
     list.thr_id = 0;
-    list.keys = list_keys + t;
-    list.ids = list_ids + t;
+    list_bind(list, list_keys, list_ids, t, k, cap);
+    if (force_single) {   // the one-lane form on interleaved lists, whatever k
+        list.coop = 0;
+        list.stride = EPI_THREADS;
+        list.keys = list_keys + t;
+        list.ids = list_ids + t;
+    }
     float one[32], zero[32];
     for (int j = 0; j < 32; j++) {
         one[j] = 1.f;
@@ -44,8 +48,8 @@ int main() {
     std::mt19937 rng(1234);
     int cases = 0, bad = 0;
     for (int k : {1, 10, 16, 17, 30, 64, 100, 256}) {
-        for (int mode = 0; mode < 2; mode++) {
-            const int cap = mode ? list_cap_append(k) : list_cap_for(k);
+        for (int mode = 0; mode < 3; mode++) {   // 0: default form for this k (cooperative from k = 17), 1: append, 2: one-lane rescan
+            const int cap = mode == 1 ? list_cap_append(k) : k;
             for (int dist = 0; dist < 4; dist++) {
                 const int chunks = dist == 3 ? 3 : 200;
                 std::vector<float> h((size_t)chunks * EPI_THREADS * 32);
@@ -66,7 +70,7 @@ int main() {
                 cudaMalloc(&d_ok, (size_t)k * EPI_THREADS * 4);
                 cudaMalloc(&d_oi, (size_t)k * EPI_THREADS * 4);
                 cudaMemcpy(d_keys, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
-                list_test_kernel<<<1, EPI_THREADS>>>(d_keys, chunks, k, cap, d_lk, d_li, d_ok, d_oi);
+                list_test_kernel<<<1, EPI_THREADS>>>(d_keys, chunks, k, cap, mode == 2, d_lk, d_li, d_ok, d_oi);
                 if (cudaDeviceSynchronize() != cudaSuccess) {
                     printf("kernel failed: %s\n", cudaGetErrorString(cudaGetLastError()));
                     return 2;
@@ -86,7 +90,7 @@ int main() {
                         const uint32_t wi = have ? all[e].second : kNoId;
                         if (ok[(size_t)t * k + e] != wk || oi[(size_t)t * k + e] != wi) {
                             if (bad < 10)
-                                printf("MISMATCH k %d cap %d dist %d thread %d slot %d: got (%g, %u) want (%g, %u)\n", k, cap, dist, t, e,
+                                printf("MISMATCH mode %d k %d cap %d dist %d thread %d slot %d: got (%g, %u) want (%g, %u)\n", mode, k, cap, dist, t, e,
                                        ok[(size_t)t * k + e], oi[(size_t)t * k + e], wk, wi);
                             bad++;
                             break;

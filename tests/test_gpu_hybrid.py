@@ -89,6 +89,27 @@ def test_random_lists_match_oracle_bitexact(ft, direction):
         assert [(a, b, c, float(F32(d))) for a, b, c, d in got[q]] == [(a, b, c, float(F32(d))) for a, b, c, d in exp], q
 
 
+def test_array_form_of_the_fusion_equals_the_list_form():
+    from myscaledb_b200 import search as S
+    rng = np.random.default_rng(23)
+    nq, kv, kt = 40, 30, 30
+    v_ids = np.full((nq, kv), -1, np.int64); t_ids = np.full((nq, kt), -1, np.int64)
+    v_sc = np.zeros((nq, kv), F32); t_sc = np.full((nq, kt), -np.inf, F32)
+    vecs, txts = [], []
+    for q in range(nq):
+        nv, nt = int(rng.integers(0, kv + 1)), int(rng.integers(0, kt + 1))
+        v_ids[q, :nv] = rng.permutation(100)[:nv]; t_ids[q, :nt] = rng.permutation(100)[:nt]
+        v_sc[q, :nv] = np.sort(rng.random(nv).astype(F32)); t_sc[q, :nt] = np.sort(rng.random(nt).astype(F32))[::-1]
+        vecs.append([(0, 0, int(i), float(s)) for i, s in zip(v_ids[q, :nv], v_sc[q, :nv])])
+        txts.append([(0, 0, int(i), float(s)) for i, s in zip(t_ids[q, :nt], t_sc[q, :nt])])
+    for ft in ("rrf", "rsf"):
+        want = b2.hybrid_fusion_batch(ft, vecs, txts, 10, fusion_weight=0.4, fusion_k=60, vector_scan_direction=1)
+        ids, sc, cnt = S.hybrid_fusion_arrays(ft, v_ids, v_sc, t_ids, t_sc, 10, fusion_weight=0.4, fusion_k=60, vector_scan_direction=1)
+        for q in range(nq):
+            assert [(int(i), float(x)) for i, x in zip(ids[q, :cnt[q]], sc[q, :cnt[q]])] == [(c, float(F32(d))) for _, _, c, d in want[q]], (ft, q)
+            assert (ids[q, cnt[q]:] == -1).all()
+
+
 def test_reference_call_sites_run_on_gpu():
     """The reference's own call expressions (createVectorIndex, reader-driven build, search with a filter, serialize / load
     through the stream classes, computeTopDistanceSubset, faiss::knn_*, TANTIVY::ffi_*) end to end on the GPU."""

@@ -157,9 +157,8 @@ def main():
         # 5. fusion on the initiator
         fused = None
         if rank == 0:
-            vec_lists = [[(0, 0, int(i), float(d)) for d, i in zip(hv_d[q], hv_i[q]) if i >= 0] for q in range(a.nq)]
-            txt_lists = [[(0, 0, int(i), float(d)) for d, i in zip(td[q], ti[q]) if i >= 0] for q in range(a.nq)]
-            fused = S.hybrid_fusion_batch("rrf", vec_lists, txt_lists, a.limit, fusion_k=60, vector_scan_direction=1)
+            f_ids, f_sc, _ = S.hybrid_fusion_arrays("rrf", hv_i, hv_d, ti, td, a.limit, fusion_k=60, vector_scan_direction=1)
+            fused = (f_ids, f_sc)
         t.append(time.perf_counter())
         if record:
             for name, d in zip(phase, np.diff(t)):
@@ -187,7 +186,7 @@ def main():
                "phase_ms_rank0": {k_: v / a.steps * 1e3 for k_, v in phase.items()},
                "text_build_s_per_rank": t_text, "vector_build_s_per_rank": t_vec,
                "text_checksum": zlib.crc32(np.ascontiguousarray(ids).tobytes()),
-               "text_hits": int((ids >= 0).sum()), "fused_first": fused[0][:3] if fused else None,
+               "text_hits": int((ids >= 0).sum()), "fused_first": [fused[0][0][:3].tolist(), fused[1][0][:3].tolist()] if fused else None,
                "timing": "host wall clock around the whole batch (tokenise + all-reduce + score + gather + vector scan + fusion), max over ranks"}
         print(json.dumps(out))
     tix.close()
