@@ -232,15 +232,18 @@ struct ThreadTopK {
     uint32_t thr_id;
 };
 
-// Layout and insert form by k (cap == k only; the append form keeps the interleaved layout):
-//  * k <= kListCoopMinK - 1: interleaved lists, each lane inserts into its own list (a rescan of <= 16 entries is as cheap as
-//    a warp-wide reduction);
-//  * larger k: contiguous lists and COOPERATIVE inserts.  A lane that inserts alone still makes its 31 neighbours wait
-//    (every lane is a different query), so the warp does the work together instead: the accepted candidate of one lane is
-//    broadcast, lane 0 overwrites that list's worst entry, all 32 lanes rescan the list (k / 32 entries each, conflict-free
-//    because the list is contiguous) and a shuffle arg-max yields the new worst -- ~80 cycles against ~8 k cycles for a
-//    one-lane rescan of k entries.  At k = 100 the one-lane form was 2/3 of the launch (36 ms against 12 ms at k = 10).
-constexpr int kListCoopMinK = 17;
+// Layout and insert form (cap == k only; the append form keeps the interleaved layout):
+//  * interleaved lists, each lane inserts into its own list -- the default at every k;
+//  * contiguous lists and COOPERATIVE inserts (k >= B200_LIST_COOP_MIN_K, off by default): the accepted candidate of one lane
+//    is broadcast, lane 0 overwrites that list's worst entry, all 32 lanes rescan the list (k / 32 entries each) and a shuffle
+//    arg-max yields the new worst.  Measured (profiles/r02_list_modes.md): it does NOT pay.  A slow-path event carries ~5
+//    candidates spread over the lanes; the one-lane form retires them in ~1.5 parallel rounds of one k-entry rescan each, the
+//    cooperative form in ~5 serial steps of ~100 instructions -- 15.6 vs 13.2 ms per launch at k = 17 / 16, 17.9 vs 14.4 at
+//    k = 30, equal at k = 100.  Kept for the unit test and the record.
+#ifndef B200_LIST_COOP_MIN_K
+#define B200_LIST_COOP_MIN_K (1 << 30)
+#endif
+constexpr int kListCoopMinK = B200_LIST_COOP_MIN_K;
 __device__ __forceinline__ void list_bind(ThreadTopK &t, float *keys_base, uint32_t *ids_base, int row, int k, int cap) {
     t.k = k;
     t.cap = cap;

@@ -251,12 +251,22 @@ class BM25Index:
         _check(lib().b200_bm25_doc_freq(self._h, C.c_uint32(field), term.encode(), C.byref(v)))
         return v.value
 
+    _qt_tls = __import__("threading").local()   # per-thread scratch of query_terms (ctypes drops the GIL during the call)
+
     @staticmethod
     def query_terms(sentence):
-        buf = C.create_string_buffer(4096)
-        n = C.c_uint32()
+        tls = BM25Index._qt_tls
+        if not hasattr(tls, "buf"):
+            tls.buf = (C.create_string_buffer(4096), C.c_uint32())
+        buf, n = tls.buf
         _check(lib().b200_bm25_query_terms(sentence.encode(), buf, C.c_size_t(4096), C.byref(n)))
-        return [t.decode() for t in buf.raw.split(b"\0")[:n.value]]
+        out, off = [], 0
+        base = C.addressof(buf)
+        for _ in range(n.value):
+            t = C.string_at(base + off)
+            out.append(t.decode())
+            off += len(t) + 1
+        return out
 
     def search_batch(self, sentences, topk, fields=(0,), alive_bits=None, operator_or=True, stats=None):
         nq = len(sentences)
