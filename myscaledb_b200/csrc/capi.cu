@@ -816,6 +816,10 @@ static int search_host_fused(b200_corpus *c, const float *queries, int64_t nq, i
     sp.done_value = ++c->fused_seq ? c->fused_seq : ++c->fused_seq;   // never 0
     sp.q_inline = q_inline ? 1 : 0;
     if (q_inline) memcpy(sp.qinline, queries, (size_t)nq * c->d * 4);
+    static unsigned long long *dbg_ts = nullptr;   // B200_FUSED_DEBUG_TS=1: phase stamps of the kernel, printed every 64th call
+    static const bool dbg_on = getenv("B200_FUSED_DEBUG_TS") && atoi(getenv("B200_FUSED_DEBUG_TS"));
+    if (dbg_on && !dbg_ts) cudaMallocManaged(&dbg_ts, 16 * sizeof(unsigned long long));
+    sp.debug_ts = dbg_on ? dbg_ts : nullptr;
     *h_flag = 0;
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     timing_begin(c, s, ev);
@@ -836,6 +840,13 @@ static int search_host_fused(b200_corpus *c, const float *queries, int64_t nq, i
 #if defined(__x86_64__)
         __builtin_ia32_pause();
 #endif
+    }
+    if (dbg_on && (c->fused_seq & 63) == 0) {
+        cudaStreamSynchronize(s);
+        fprintf(stderr, "fused ts (us since block 0 start): scan_done %.1f tail_start %.1f fence %.1f staged %.1f bounds %.1f compacted %.1f lists %.1f merged %.1f written %.1f sysfence %.1f survivors %llu\n",
+                (dbg_ts[1] - dbg_ts[0]) * 1e-3, (dbg_ts[2] - dbg_ts[0]) * 1e-3, (dbg_ts[3] - dbg_ts[0]) * 1e-3, (dbg_ts[4] - dbg_ts[0]) * 1e-3,
+                (dbg_ts[5] - dbg_ts[0]) * 1e-3, (dbg_ts[6] - dbg_ts[0]) * 1e-3, (dbg_ts[7] - dbg_ts[0]) * 1e-3, (dbg_ts[8] - dbg_ts[0]) * 1e-3,
+                (dbg_ts[9] - dbg_ts[0]) * 1e-3, (dbg_ts[10] - dbg_ts[0]) * 1e-3, dbg_ts[15]);
     }
     memcpy(out_dis, h_dis, (size_t)nq * k * 4);
     memcpy(out_ids, h_ids, (size_t)nq * k * 8);

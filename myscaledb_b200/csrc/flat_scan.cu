@@ -52,6 +52,17 @@ struct ChunkTraits<true> {
 // every lane keeps U * CU independent 128-bit loads in flight (the first version issued U and
 // reached 3.9 TB/s = 61 % of the measured HBM peak at 25 % occupancy, profiles/r01_flat_scan_v1).
 // L2 = squared-L2 vs inner product (cosine = inner product scaled by the stored inverse row norm).
+// candidate read of the fused tail: partial lists in global memory written by other blocks (L2, .cg) or staged in shared memory
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define B200_TS(i) do { if (p.debug_ts && threadIdx.x == 0) p.debug_ts[i] = gtimer(); } while (0)
+
+template <typename T>
+__device__ __forceinline__ T ld_cand(const T *p, bool staged) { return staged ? *p : __ldcg(p); }
+
 template <int QT, int U, int CU, bool L2, bool BF16>
 __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanParams p) {
     using CT = ChunkTraits<BF16>;
@@ -61,6 +72,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanPa
     float *lk = qs + (size_t)QT * p.d_pad;                                   // [warps][QT][k]
     uint32_t *li = reinterpret_cast<uint32_t *>(lk + (size_t)kScanWarps * QT * p.k);
 
+    if (p.fused && blockIdx.x == 0 && blockIdx.y == 0) B200_TS(0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t q0 = (int64_t)blockIdx.y * QT;
     const int nq_here = (int)min((int64_t)QT, p.nq - q0);
@@ -204,6 +216,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanPa
                          p.part_keys + ((q0 + q) * (int64_t)gridDim.x + blockIdx.x) * p.k,
                          p.part_ids + ((q0 + q) * (int64_t)gridDim.x + blockIdx.x) * p.k);
     if (!p.fused) return;
+    if (blockIdx.x == 0 && blockIdx.y == 0) B200_TS(1);   // block 0: scan + block merge done
     // ---- fused form: the last block of this query tile merges the gridDim.x partial lists of each of its queries
     __shared__ unsigned int s_ticket;
     __threadfence();
@@ -211,7 +224,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanPa
     if (threadIdx.x == 0) s_ticket = atomicAdd(&p.tickets[blockIdx.y], 1u);
     __syncthreads();
     if (s_ticket != gridDim.x - 1) return;
+    B200_TS(2);   // tail starts
     __threadfence();
+    B200_TS(3);
     // the staging area is free now: [warps][k] keys + ids, merged list behind it (launch reserves (warps + 1) * k * 8 bytes)
     float *mk = reinterpret_cast<float *>(smem_raw);
     uint32_t *mi = reinterpret_cast<uint32_t *>(mk + (size_t)kScanWarps * p.k);
@@ -226,36 +241,100 @@ __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanPa
         const float *pkeys = p.part_keys + (q0 + q) * (int64_t)gridDim.x * p.k;
         const uint32_t *pids = p.part_ids + (q0 + q) * (int64_t)gridDim.x * p.k;
         const int64_t ncand = (int64_t)gridDim.x * p.k;
-        {   // every block's list is sorted and complete: the smallest k-th key over the blocks bounds the global k-th key
-            __shared__ float bound_s[kScanWarps];
-            float b = FLT_MAX;
-            for (int l = threadIdx.x; l < (int)gridDim.x; l += kScanThreads)
-                if (__ldcg(pids + (int64_t)l * p.k + (p.k - 1)) != kNoId) b = fminf(b, __ldcg(pkeys + (int64_t)l * p.k + (p.k - 1)));
+        const bool staged = p.stage_cap >= ncand;
+        if (staged) {
+            // Staged form.  The tail is ONE block and latency-bound (ncu: 45 us kernel of which the SMs are busy for ~10): every
+            // L2 round trip on its critical path counts.  All candidates come in with independent loads, 4 per thread in flight;
+            // the bound, the survivor compaction and the warp lists then work from shared memory.
+            float *sk = reinterpret_cast<float *>(fi + p.k);
+            uint32_t *si = reinterpret_cast<uint32_t *>(sk + p.stage_cap);
+            for (int64_t c0 = threadIdx.x; c0 < ncand; c0 += kScanThreads * 4) {
+                float kk[4];
+                uint32_t ii[4];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) b = fminf(b, __shfl_xor_sync(0xffffffffu, b, o));
-            if (lane == 0) bound_s[warp] = b;
+                for (int u = 0; u < 4; u++) {
+                    const int64_t c = c0 + (int64_t)u * kScanThreads;
+                    kk[u] = c < ncand ? __ldcg(pkeys + c) : FLT_MAX;
+                    ii[u] = c < ncand ? __ldcg(pids + c) : kNoId;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int64_t c = c0 + (int64_t)u * kScanThreads;
+                    if (c < ncand) {
+                        sk[c] = kk[u];
+                        si[c] = ii[u];
+                    }
+                }
+            }
             __syncthreads();
-            b = bound_s[0];
+            B200_TS(4);   // staged
+            pkeys = sk;
+            pids = si;
+        }
+        __shared__ float cand_k[1024];
+        __shared__ uint32_t cand_i[1024];
+        __shared__ int cand_n;
+        {
+            __shared__ float bound_s[kScanWarps];
+            __shared__ float bound2_s;
+            float b = FLT_MAX;
+            if (staged && (int)gridDim.x >= p.k) {
+                // Bound = the k-th smallest of the blocks' BEST keys: at least k candidates (those minima) are <= it, so it bounds
+                // the global k-th key -- and it is tight even when every block saw only a few rows (cfg 1: 34 rows per block; a
+                // block's own k-th key would let ~30 % of all candidates through).  The minima are gathered into a compact array
+                // (reusing the survivor buffer) so that the rank count is one LDS.128 per four comparisons.
+                float *mins = cand_k;   // gridDim.x <= 8192 / k <= 1024 when k >= 8; guarded below
+                const int nb = (int)gridDim.x;
+                const bool fits = nb <= 1024;
+                if (fits) {
+                    for (int l = threadIdx.x; l < ((nb + 3) & ~3); l += kScanThreads)
+                        mins[l] = (l < nb && pids[(int64_t)l * p.k] != kNoId) ? pkeys[(int64_t)l * p.k] : FLT_MAX;
+                    if (threadIdx.x == 0) bound2_s = FLT_MAX;
+                    __syncthreads();
+                    for (int l = threadIdx.x; l < nb; l += kScanThreads) {
+                        const float m = mins[l];
+                        int rank = 0;
+                        for (int o = 0; o < nb; o += 4) {
+                            const float4 v = *reinterpret_cast<const float4 *>(mins + o);
+                            rank += (v.x < m || (v.x == m && o < l)) ? 1 : 0;
+                            rank += (v.y < m || (v.y == m && o + 1 < l)) ? 1 : 0;
+                            rank += (v.z < m || (v.z == m && o + 2 < l)) ? 1 : 0;
+                            rank += (v.w < m || (v.w == m && o + 3 < l)) ? 1 : 0;
+                        }
+                        if (rank == p.k - 1) bound2_s = m;
+                    }
+                    __syncthreads();
+                    b = bound2_s;
+                }
+            }
+            if (!(b < FLT_MAX)) {
+                // every block's list is sorted and complete: the smallest k-th key over the blocks also bounds the global k-th key
+                for (int l = threadIdx.x; l < (int)gridDim.x; l += kScanThreads)
+                    if (ld_cand(pids + (int64_t)l * p.k + (p.k - 1), staged) != kNoId) b = fminf(b, ld_cand(pkeys + (int64_t)l * p.k + (p.k - 1), staged));
 #pragma unroll
-            for (int w = 1; w < kScanWarps; w++) b = fminf(b, bound_s[w]);
+                for (int o = 16; o > 0; o >>= 1) b = fminf(b, __shfl_xor_sync(0xffffffffu, b, o));
+                if (lane == 0) bound_s[warp] = b;
+                __syncthreads();
+                b = bound_s[0];
+#pragma unroll
+                for (int w = 1; w < kScanWarps; w++) b = fminf(b, bound_s[w]);
+            }
             if (b < FLT_MAX) {
                 list.thr_key = b;
                 list.thr_id = kNoId;
             }
             __syncthreads();
         }
+        B200_TS(5);   // bounds
         // Survivors of the bound are few (~k): every thread first sweeps its share of the candidates with independent loads
         // (no vote between them, so the L2 latencies overlap) and appends survivors to a compact shared array; only those go
         // through the warp lists.  (The first version voted after every load: 12 dependent L2 round trips, ~12 us of a 45 us call.)
-        __shared__ float cand_k[1024];
-        __shared__ uint32_t cand_i[1024];
-        __shared__ int cand_n;
         if (threadIdx.x == 0) cand_n = 0;
         __syncthreads();
         const float bound_key = list.thr_key;
         for (int64_t c = threadIdx.x; c < ncand; c += kScanThreads) {
-            const uint32_t id = __ldcg(pids + c);
-            const float key = __ldcg(pkeys + c);
+            const uint32_t id = ld_cand(pids + c, staged);
+            const float key = ld_cand(pkeys + c, staged);
             if (id != kNoId && key <= bound_key) {
                 const int pos = atomicAdd(&cand_n, 1);
                 if (pos < 1024) {
@@ -265,8 +344,29 @@ __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanPa
             }
         }
         __syncthreads();
+        B200_TS(6);   // survivors compacted
+        if (p.debug_ts && threadIdx.x == 0) p.debug_ts[15] = (unsigned long long)cand_n;
         const int n_surv = cand_n;
-        if (n_surv <= 1024) {
+        bool ranked = false;
+        if (n_surv <= kScanThreads) {
+            // few survivors (the usual case, ~k): rank each among the others and write the result in order -- no warp lists, no merge
+            for (int j = threadIdx.x; j < p.k; j += kScanThreads) {
+                fk[j] = FLT_MAX;
+                fi[j] = kNoId;
+            }
+            __syncthreads();
+            if ((int)threadIdx.x < n_surv) {
+                const float key = cand_k[threadIdx.x];
+                const uint32_t id = cand_i[threadIdx.x];
+                int rank = 0;
+                for (int o = 0; o < n_surv; o++) rank += better(cand_k[o], cand_i[o], key, id) ? 1 : 0;
+                if (rank < p.k) {
+                    fk[rank] = key;
+                    fi[rank] = id;
+                }
+            }
+            ranked = true;
+        } else if (n_surv <= 1024) {
             for (int c0 = warp * 32; c0 < n_surv; c0 += kScanThreads) {
                 const int c = c0 + lane;
                 const float key = c < n_surv ? cand_k[c] : FLT_MAX;
@@ -286,8 +386,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanPa
                 uint32_t id = kNoId;
                 bool cand = false;
                 if (c < ncand) {
-                    key = __ldcg(pkeys + c);
-                    id = __ldcg(pids + c);
+                    key = ld_cand(pkeys + c, staged);
+                    id = ld_cand(pids + c, staged);
                     cand = id != kNoId && list.passes(key, id);
                 }
                 unsigned m = __ballot_sync(0xffffffffu, cand);
@@ -299,8 +399,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanPa
             }
         }
         __syncthreads();
-        block_rank_merge(mk, mi, kScanWarps, p.k, p.k, fk, fi);
+        B200_TS(7);   // warp lists
+        if (!ranked) block_rank_merge(mk, mi, kScanWarps, p.k, p.k, fk, fi);
         __syncthreads();
+        B200_TS(8);   // merged
         for (int j = threadIdx.x; j < p.k; j += kScanThreads) {
             float dis;
             int64_t id;
@@ -323,8 +425,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanPa
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        B200_TS(9);   // results written
         p.tickets[blockIdx.y] = 0;            // ready for the next call
-        __threadfence_system();               // results (mapped host memory) before the flag
+        __threadfence_system();
+        B200_TS(10);  // system fence               // results (mapped host memory) before the flag
         const unsigned int t = atomicAdd(p.tiles_done, 1u);
         if (t == gridDim.y - 1) {
             *p.tiles_done = 0;
@@ -674,9 +778,17 @@ size_t scan_smem_bytes(int qt, int d_pad, int k) {
     return std::max((size_t)qt * d_pad * 4 + (size_t)kScanWarps * qt * k * 8, (size_t)(kScanWarps + 1) * k * 8);
 }
 
-cudaError_t launch_flat_scan(const ScanParams &p, int qt, int blocks_x, cudaStream_t s) {
+cudaError_t launch_flat_scan(const ScanParams &p_in, int qt, int blocks_x, cudaStream_t s) {
+    ScanParams p = p_in;
     const dim3 grid(blocks_x, (unsigned)ceil_div(p.nq, qt));
-    const size_t smem = scan_smem_bytes(qt, p.d_pad, p.k);
+    size_t smem = scan_smem_bytes(qt, p.d_pad, p.k);
+    p.stage_cap = 0;
+    if (p.fused && (size_t)blocks_x * p.k <= 8192) {
+        // the last block stages every partial list in shared memory with independent loads (one L2 round trip instead of one per
+        // 256 candidates): [warps + 1][k] lists, then blocks_x * k keys and ids
+        p.stage_cap = blocks_x * p.k;
+        smem = std::max(smem, (size_t)(kScanWarps + 1) * p.k * 8 + (size_t)p.stage_cap * 8);
+    }
     const int elems = p.bf16 ? 8 : 4;
     const int cpl = (int)ceil_div(p.d_pad / elems, p.group);  // 16-byte chunks per lane and row
     // loads in flight per lane: short rows -> 4 rows x 1 chunk; long rows -> 4 chunks x (4 | 2) rows

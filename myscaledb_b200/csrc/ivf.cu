@@ -518,6 +518,87 @@ __global__ void __launch_bounds__(1024) search_plan_kernel(const SearchPlan p) {
     }
 }
 
+// ------------------------------------------------------------------------------------
+// Coarse probe for nprobe > 8: the centroid table is small (nlist x d fp32, L2-resident) and nprobe is a large k for it --
+// the fused top-k kernels keep one k-entry list per query and, with only nlist / workers rows per list, almost every row is
+// an insert (measured 21 ms for 10 000 queries x 4 096 centroids x 96, nprobe 32, on either path).  Here the ranking keys
+// ||c||^2 - 2 <x, c> of a chunk of queries are written out by a plain fp32 tile kernel (64 x 64 tiles, 4 x 4 per thread) and
+// one warp per query selects its nprobe smallest with a sorted warp list: scores are read once, coalesced, and an insert is
+// O(nprobe / 32).
+// ------------------------------------------------------------------------------------
+constexpr int kCoarseTile = 64, kCoarseTK = 16;
+
+__global__ void __launch_bounds__(256) coarse_scores_kernel(const float *x, int64_t ldx, const float *cent, const float *cnorm, int64_t nq,
+                                                            int nl, int d, float *out /*[nq][nl]*/) {
+    __shared__ float sx[kCoarseTK][kCoarseTile + 4], sc[kCoarseTK][kCoarseTile + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int64_t q0 = (int64_t)blockIdx.y * kCoarseTile;
+    const int c0 = blockIdx.x * kCoarseTile;
+    float acc[4][4] = {};
+    // loads: thread t fetches element (row t / 16 + 16 r, column t % 16) of each 64 x 16 operand tile, r = 0..3
+    const int lr = threadIdx.x >> 4, lc = threadIdx.x & 15;
+    for (int k0 = 0; k0 < d; k0 += kCoarseTK) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int row = lr + 16 * r;
+            const int64_t q = q0 + row;
+            const int c = c0 + row;
+            const int kk = k0 + lc;
+            sx[lc][row] = (q < nq && kk < d) ? x[q * ldx + kk] : 0.f;
+            sc[lc][row] = (c < nl && kk < d) ? cent[(size_t)c * d + kk] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kCoarseTK; kk++) {
+            const float4 a = *reinterpret_cast<const float4 *>(&sx[kk][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4 *>(&sc[kk][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int64_t q = q0 + ty * 4 + i;
+        if (q >= nq) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int c = c0 + tx * 4 + j;
+            if (c < nl) out[q * nl + c] = fmaf(-2.f, acc[i][j], cnorm[c]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) coarse_select_kernel(const float *scores, int64_t nq, int nl, int k, float *out_key, int64_t *out_ids) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *lk = reinterpret_cast<float *>(smem_raw) + (size_t)warp * k;
+    uint32_t *li = reinterpret_cast<uint32_t *>(reinterpret_cast<float *>(smem_raw) + (size_t)8 * k) + (size_t)warp * k;
+    const int64_t q = (int64_t)blockIdx.x * 8 + warp;
+    if (q >= nq) return;
+    WarpTopK list;
+    list.init(lk, li, k);
+    const float *row = scores + q * nl;
+    for (int c0 = 0; c0 < nl; c0 += 32) {
+        const int c = c0 + lane;
+        const float key = c < nl ? row[c] : FLT_MAX;
+        unsigned m = __ballot_sync(0xffffffffu, c < nl && list.passes(key, (uint32_t)c));
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            list.insert(__shfl_sync(0xffffffffu, key, src), (uint32_t)(c0 + src));
+        }
+    }
+    __syncwarp();
+    for (int j = lane; j < k; j += 32) {
+        out_key[q * k + j] = j < list.n ? lk[j] : FLT_MAX;
+        out_ids[q * k + j] = j < list.n ? (int64_t)li[j] : -1;
+    }
+}
+
 // One warp per sorted pair: gather (and for SQ8 scale) the query into the bf16 A-operand buffer, record where the pair's
 // partial lists start, the inverse permutation, and the pair's additive constant (PQ: ||q - c||^2 or -<q, c>).
 struct PairFill {
@@ -795,6 +876,7 @@ struct b200_index {
     b200_corpus *raw = nullptr;     // fp32 rows in id order (cosine: unit vectors), metric L2 or IP
     b200_corpus *coarse = nullptr;  // centroid table as a FLAT corpus (L2)
     float *d_centroids = nullptr;   // [nlist][d]
+    float *d_cnorm = nullptr;       // [nlist] ||c||^2 (coarse probe)
     float *d_pq = nullptr;          // [m][256][dsub] fp32
     __nv_bfloat16 *d_pq_bf16 = nullptr;
     float *d_sq = nullptr;          // [4][d]: lo, step, 1/step, mid
@@ -813,7 +895,7 @@ struct b200_index {
     std::mutex mu;
     // workspaces (grow-only)
     DevArr w_rows, w_assign_i, w_assign_d, w_u32a, w_u32b, w_u32c, w_u32d, w_cnt, w_plan, w_sort, w_q, w_qraw, w_probe, w_pd, w_items,
-        w_qbuf, w_inv, w_ppb, w_pconst, w_qconst, w_qb, w_pk, w_pi, w_pw, w_lk, w_li, w_alive, w_od, w_oi, w_cand, w_host_q;
+        w_qbuf, w_inv, w_ppb, w_pconst, w_qconst, w_qb, w_cs, w_pk, w_pi, w_pw, w_lk, w_li, w_alive, w_od, w_oi, w_cand, w_host_q;
     // statistics of the last search (tests, bench roofline): rows x payload bytes the scan kernel was asked to stream
     int64_t last_scan_rows = 0, last_items = 0;
     bool timing = false, timed_pending = false;
@@ -905,12 +987,12 @@ extern "C" int b200_index_free(b200_index *ix) {
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     if (ix->raw) b200_corpus_free(ix->raw);
     if (ix->coarse) b200_corpus_free(ix->coarse);
-    for (void *p : {(void *)ix->d_centroids, (void *)ix->d_pq, (void *)ix->d_pq_bf16, (void *)ix->d_sq, ix->d_pool, (void *)ix->d_row_bias,
+    for (void *p : {(void *)ix->d_centroids, (void *)ix->d_cnorm, (void *)ix->d_pq, (void *)ix->d_pq_bf16, (void *)ix->d_sq, ix->d_pool, (void *)ix->d_row_bias,
                     (void *)ix->d_row_ids, (void *)ix->d_list_len, (void *)ix->d_tail_page, (void *)ix->d_page_owner, (void *)ix->d_page_seq,
                     (void *)ix->d_pages_used, (void *)ix->d_flag, (void *)ix->d_list_page_off, (void *)ix->d_list_pages, (void *)ix->d_list_order})
         if (p) cudaFree(p);
     for (DevArr *a : {&ix->w_rows, &ix->w_assign_i, &ix->w_assign_d, &ix->w_u32a, &ix->w_u32b, &ix->w_u32c, &ix->w_u32d, &ix->w_cnt, &ix->w_plan,
-                      &ix->w_sort, &ix->w_q, &ix->w_qraw, &ix->w_probe, &ix->w_pd, &ix->w_items, &ix->w_qbuf, &ix->w_inv, &ix->w_ppb, &ix->w_pconst, &ix->w_qb,
+                      &ix->w_sort, &ix->w_q, &ix->w_qraw, &ix->w_probe, &ix->w_pd, &ix->w_items, &ix->w_qbuf, &ix->w_inv, &ix->w_ppb, &ix->w_pconst, &ix->w_qb, &ix->w_cs,
                       &ix->w_qconst, &ix->w_pk, &ix->w_pi, &ix->w_pw, &ix->w_lk, &ix->w_li, &ix->w_alive, &ix->w_od, &ix->w_oi, &ix->w_cand,
                       &ix->w_host_q})
         a->release();
@@ -1029,6 +1111,10 @@ static int upload_coarse(b200_index *ix, cudaStream_t s) {
     ix->coarse = nullptr;
     // L2 for every metric (unit vectors under cosine; IP indexes probe by L2 too, like Faiss's default quantiser)
     B200_TRY(b200_corpus_create(B200_METRIC_L2, B200_DTYPE_F32, ix->d, ix->nlist, &ix->coarse));
+    if (ix->d_cnorm) cudaFree(ix->d_cnorm);
+    ix->d_cnorm = nullptr;
+    B200_CUDA_OK(cudaMalloc(&ix->d_cnorm, (size_t)ix->nlist * 4));
+    B200_CUDA_OK(launch_row_norms(ix->d_centroids, 0, ix->d, ix->nlist, 0, ix->d_cnorm, s));
     return corpus_append_device(ix->coarse, ix->d_centroids, ix->nlist, s);
 }
 
@@ -1564,11 +1650,29 @@ static int search_device_locked(b200_index *ix, const float *d_queries, int64_t 
         const double t_scan = (double)ceil_div(nq, 8) * nl * ix->d_pad * 4.0 / 1.4e12;
         const double t_gemm = 1e-6 * (double)nq * std::max(1.0, nprobe / 32.0) + 30e-6;
         bool use_scan = nprobe > 8 && t_scan < t_gemm;
-        if (const int forced = parse_int_param(params, "coarse_path", 0)) use_scan = forced == 1;   // A/B: 1 scan kernel, 2 tensor-core path
-        b200_corpus_set_path(ix->coarse, use_scan ? 1 : 0);
-        const int rc = b200_corpus_search_device(ix->coarse, ix->w_qraw.as<float>(), nq, nprobe, nullptr, 0, ix->w_pd.as<float>(), ix->w_probe.as<int64_t>(), s);
-        b200_corpus_set_path(ix->coarse, 0);
-        B200_TRY(rc);
+        // nprobe > 8: full ranking keys + warp select (coarse_scores_kernel / coarse_select_kernel above)
+        int coarse_path = nprobe > 8 && nprobe <= 1024 ? 3 : use_scan ? 1 : 2;
+        if (const int forced = parse_int_param(params, "coarse_path", 0)) coarse_path = forced;   // A/B: 1 scan kernel, 2 tensor-core path, 3 select
+        if (coarse_path == 3) {
+            const int64_t chunk = std::max<int64_t>(64, std::min<int64_t>(nq, ((int64_t)64 << 20) / std::max(1, nl)));   // <= 256 MB of keys
+            B200_TRY(ix->w_cs.reserve((size_t)chunk * nl * 4));
+            const size_t sel_smem = (size_t)8 * nprobe * 8;
+            if (sel_smem > 48 * 1024) B200_CUDA_OK(cudaFuncSetAttribute(coarse_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+            for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
+                const int64_t nqc = std::min(chunk, nq - q0);
+                coarse_scores_kernel<<<dim3((unsigned)ceil_div(nl, kCoarseTile), (unsigned)ceil_div(nqc, kCoarseTile)), 256, 0, s>>>(
+                    d_q + q0 * ix->d_pad, ix->d_pad, ix->d_centroids, ix->d_cnorm, nqc, nl, ix->d, ix->w_cs.as<float>());
+                coarse_select_kernel<<<(unsigned)ceil_div(nqc, 8), 256, sel_smem, s>>>(ix->w_cs.as<float>(), nqc, nl, nprobe, ix->w_pd.as<float>() + q0 * nprobe,
+                                                                                       ix->w_probe.as<int64_t>() + q0 * nprobe);
+                g_launches += 2;
+            }
+            B200_CUDA_OK(cudaGetLastError());
+        } else {
+            b200_corpus_set_path(ix->coarse, coarse_path == 1 ? 1 : 0);
+            const int rc = b200_corpus_search_device(ix->coarse, ix->w_qraw.as<float>(), nq, nprobe, nullptr, 0, ix->w_pd.as<float>(), ix->w_probe.as<int64_t>(), s);
+            b200_corpus_set_path(ix->coarse, 0);
+            B200_TRY(rc);
+        }
     }
 
     if (ix->timing) cudaEventRecord(ix->ev_ph[1], s);

@@ -358,6 +358,46 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                                 const uint2 v = (j0 < p.code_bytes) ? *reinterpret_cast<const uint2 *>(code_r + j0) : make_uint2(0, 0);
                                 cw[0] = v.x; cw[1] = v.y;
                             }
+                            constexpr int PER_CHUNK_F = 16 / BYTES_PER;
+                            const int valid = min(NSUB, p.m - j0);          // sub-quantisers of this k-block that exist
+                            if (valid % PER_CHUNK_F == 0) {
+                                // Fast form (whole 16-byte chunks valid or absent): 32-bit shared addresses and ld.shared, one
+                                // predicate per chunk.  The first form computed 64-bit generic addresses and a predicate per
+                                // code: 14 k warp-instructions per page at dsub = 1 -- 53 % of the kernel's issue slots at the
+                                // cfg-4 shape (profiles/r02_ivfpq_cfg4.md).
+                                const int valid_chunks = valid > 0 ? valid / PER_CHUNK_F : 0;
+                                const uint32_t cb_s = smem_u32(cb) + (uint32_t)j0 * 256u * BYTES_PER;
+#pragma unroll
+                                for (int chunk = 0; chunk < NSUB / PER_CHUNK_F; chunk++) {
+                                    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+                                    if (chunk < valid_chunks) {
+#pragma unroll
+                                        for (int t = 0; t < PER_CHUNK_F; t++) {
+                                            const int s = chunk * PER_CHUNK_F + t;
+                                            const uint32_t byte = __byte_perm(cw[s >> 2], 0, 0x4440 | (s & 3));
+                                            const uint32_t addr = cb_s + byte * BYTES_PER + (uint32_t)s * 256u * BYTES_PER;
+                                            if (DSUB == 8) {
+                                                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(addr));
+                                            } else if (DSUB == 4) {
+                                                uint32_t a0, a1;
+                                                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a0), "=r"(a1) : "r"(addr));
+                                                if (t == 0) { w0 = a0; w1 = a1; } else { w2 = a0; w3 = a1; }
+                                            } else if (DSUB == 2) {
+                                                uint32_t a0;
+                                                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a0) : "r"(addr));
+                                                if (t == 0) w0 = a0; else if (t == 1) w1 = a0; else if (t == 2) w2 = a0; else w3 = a0;
+                                            } else {
+                                                uint32_t a0;
+                                                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(a0) : "r"(addr));
+                                                uint32_t &dst = t < 2 ? w0 : t < 4 ? w1 : t < 6 ? w2 : w3;
+                                                dst = (t & 1) ? __byte_perm(dst, a0, 0x5410) : a0;
+                                            }
+                                        }
+                                    }
+                                    *reinterpret_cast<uint4 *>(rowp + ((chunk ^ (r & 7)) << 4)) = make_uint4(w0, w1, w2, w3);
+                                }
+                                continue;   // next row pass
+                            }
                             uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
                             for (int s = 0; s < NSUB; s++) {

@@ -31,6 +31,8 @@ struct ScanParams {
     unsigned int done_value;
     unsigned int *tiles_done;          // fused: one zeroed counter (reset by the last tile)
     int q_inline;                      // fused: the queries travel in the kernel parameters (nq * q_dim <= 256 floats)
+    unsigned long long *debug_ts;      // fused, debugging (B200_FUSED_DEBUG_TS=1): %globaltimer stamps of block 0's start and the tail's phases
+    int stage_cap;                     // fused: candidates (gridDim.x * k) the last block may stage in shared memory, 0 = none (set by the launcher)
     float qinline[256];
 };
 

@@ -123,7 +123,9 @@ def main():
     d_q = torch.empty((a.nq, a.dim), device=dev)
     v_dis = torch.empty((a.nq, k_cand), device=dev)
     v_ids = torch.empty((a.nq, k_cand), dtype=torch.int64, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    tstream = torch.cuda.Stream(dev)            # the sharded entry points want a real (non-NULL) stream
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
     phase = {"stats": 0.0, "text": 0.0, "text_merge": 0.0, "vector": 0.0, "fusion": 0.0}
     uniq_terms = sorted({t for s in sentences for t in tix.query_terms(s)})
 
