@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanPa
             pkeys = sk;
             pids = si;
         }
-        __shared__ float cand_k[1024];
+        __shared__ __align__(16) float cand_k[1024];
         __shared__ uint32_t cand_i[1024];
         __shared__ int cand_n;
         {
@@ -284,8 +284,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanPa
                 // block's own k-th key would let ~30 % of all candidates through).  The minima are gathered into a compact array
                 // (reusing the survivor buffer) so that the rank count is one LDS.128 per four comparisons.
                 float *mins = cand_k;   // gridDim.x <= 8192 / k <= 1024 when k >= 8; guarded below
-                const int nb = (int)gridDim.x;
-                const bool fits = nb <= 1024;
+                // any k candidates bound the k-th key: the minima of the first 256 blocks are enough (one round of the rank count)
+                const int nb = min((int)gridDim.x, kScanThreads);
+                const bool fits = true;
                 if (fits) {
                     for (int l = threadIdx.x; l < ((nb + 3) & ~3); l += kScanThreads)
                         mins[l] = (l < nb && pids[(int64_t)l * p.k] != kNoId) ? pkeys[(int64_t)l * p.k] : FLT_MAX;
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) flat_scan_kernel(const ScanPa
                     for (int l = threadIdx.x; l < nb; l += kScanThreads) {
                         const float m = mins[l];
                         int rank = 0;
+#pragma unroll 8
                         for (int o = 0; o < nb; o += 4) {
                             const float4 v = *reinterpret_cast<const float4 *>(mins + o);
                             rank += (v.x < m || (v.x == m && o < l)) ? 1 : 0;

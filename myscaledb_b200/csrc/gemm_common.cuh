@@ -409,6 +409,22 @@ static __device__ __noinline__ void list_publish(ThreadTopK &t, float *out_keys,
     }
 }
 
+// v[j] = v[j] * scale[j] + bias[j] for the 32 columns of a chunk; scale / bias are the per-tile side arrays in SHARED memory.
+// Explicit ld.shared: through generic pointers the compiler emitted LD.E.128 (generic path, scoreboarded like a global load).
+__device__ __forceinline__ void side_fma32(float (&v)[32], const float *scale, const float *bias) {
+    const uint32_t sa = smem_u32(scale), ba = smem_u32(bias);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        float s0, s1, s2, s3, b0, b1, b2, b3;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(s0), "=f"(s1), "=f"(s2), "=f"(s3) : "r"(sa + j * 4));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "r"(ba + j * 4));
+        v[j] = fmaf(v[j], s0, b0);
+        v[j + 1] = fmaf(v[j + 1], s1, b1);
+        v[j + 2] = fmaf(v[j + 2], s2, b2);
+        v[j + 3] = fmaf(v[j + 3], s3, b3);
+    }
+}
+
 // Cooperative insert (t.coop): called by the whole warp; lane `src` contributes the candidate and owns the list.
 __device__ __forceinline__ void list_insert_coop(ThreadTopK &t, int src, float key, uint32_t id) {
     const int lane = threadIdx.x & 31;
@@ -488,8 +504,7 @@ __device__ __forceinline__ void epilogue_chunk(ThreadTopK &list, float (&v)[32],
     float thr = fminf(list.thr_key, ext_bound);
     bool mine;
     if (use_side) {
-#pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = fmaf(v[j], scale[j], bias[j]);  // broadcast LDS
+        side_fma32(v, scale, bias);  // 16 broadcast LDS.128
         float m0 = fminf(v[0], v[1]), m1 = fminf(v[2], v[3]), m2 = fminf(v[4], v[5]), m3 = fminf(v[6], v[7]);
 #pragma unroll
         for (int j = 8; j < 32; j += 8) {

@@ -310,6 +310,21 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             for (uint32_t j = 0; j < item.page_count; j++) {
                 const uint32_t page = p.list_pages[item.page_begin + j];
                 const uint8_t *codes = p.codes + (size_t)page * BN * p.code_bytes;
+                {
+                    // The code loads below are consumed right away: without help every (k-block, row pass) waits one HBM
+                    // latency (ncu at the cfg-4 shape: long-scoreboard stalls on half of all samples, 14 k cycles per page).
+                    // Pull the NEXT page of this CTA's walk (codes and row biases) into L2 while this one is decoded.
+                    uint32_t next_page = 0xffffffffu;
+                    if (j + 1 < item.page_count) next_page = p.list_pages[item.page_begin + j + 1];
+                    else if (it + (int)gridDim.x < n_items) next_page = p.list_pages[p.items[it + gridDim.x].page_begin];
+                    if (next_page != 0xffffffffu) {
+                        const unsigned char *nc = p.codes + (size_t)next_page * BN * p.code_bytes;
+                        const int lines = (BN * p.code_bytes + 127) >> 7;
+                        for (int l = dw * 32 + lane; l < lines; l += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nc + (size_t)l * 128));
+                        if (p.row_bias && dw == 0 && lane < (BN * 4) / 128)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const unsigned char *>(p.row_bias + (size_t)next_page * BN) + lane * 128));
+                    }
+                }
                 for (int kb = 0; kb < kb_count; kb++) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char *bt = sB + stage * C::B_BYTES;
@@ -329,11 +344,16 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                                 uint32_t o[8];
 #pragma unroll
                                 for (int h = 0; h < 4; h++) {
-                                    // bytes are offset-binary (value + 128): subtract in fp32, pack two bf16 per word
-                                    const float f0 = (float)(int)(ww[h] & 255) - 128.f, f1 = (float)(int)((ww[h] >> 8) & 255) - 128.f;
-                                    const float f2 = (float)(int)((ww[h] >> 16) & 255) - 128.f, f3 = (float)(int)(ww[h] >> 24) - 128.f;
-                                    o[h * 2] = (__float_as_uint(f0) >> 16) | (__float_as_uint(f1) & 0xffff0000u);
-                                    o[h * 2 + 1] = (__float_as_uint(f2) >> 16) | (__float_as_uint(f3) & 0xffff0000u);
+                                    // bytes are offset-binary (value + 128).  No I2F (quarter-rate pipe: 196 k conversions per
+                                    // page would take longer than the page's HBM time): a byte dropped into the mantissa of 2^23
+                                    // is the float 8388608 + byte, one FADD removes the offset exactly, and the upper halves of
+                                    // two floats are the two bf16 (|value| <= 128 is exact in bf16).  PRMT + FADD + 1/2 PRMT each.
+                                    const float f0 = __uint_as_float(__byte_perm(ww[h], 0x4B000000u, 0x7440)) - 8388736.f;
+                                    const float f1 = __uint_as_float(__byte_perm(ww[h], 0x4B000000u, 0x7441)) - 8388736.f;
+                                    const float f2 = __uint_as_float(__byte_perm(ww[h], 0x4B000000u, 0x7442)) - 8388736.f;
+                                    const float f3 = __uint_as_float(__byte_perm(ww[h], 0x4B000000u, 0x7443)) - 8388736.f;
+                                    o[h * 2] = __byte_perm(__float_as_uint(f0), __float_as_uint(f1), 0x7632);
+                                    o[h * 2 + 1] = __byte_perm(__float_as_uint(f2), __float_as_uint(f3), 0x7632);
                                 }
                                 const int c0 = c4 * 2;
                                 *reinterpret_cast<uint4 *>(rowp + (((c0) ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);

@@ -27,12 +27,16 @@ __global__ void coop_test_kernel(const float *keys /*[tiles][slots][256]*/, int 
     for (int t = 0; t < tiles; t++) {
         uint32_t chunk_mask = 0;
         for (int chunk = 0; chunk < 8; chunk++) {
-            float v[32], one[32], zero[32];
+            float v[32];
+            __shared__ __align__(16) float one[32], zero[32];   // the side arrays live in shared memory (ld.shared in side_fma32)
             for (int j = 0; j < 32; j++) {
                 v[j] = lane < slots ? keys[((size_t)t * slots + lane) * 256 + chunk * 32 + j] : 0.f;
-                one[j] = 1.f;
-                zero[j] = 0.f;
+                if (lane == 0) {
+                    one[j] = 1.f;
+                    zero[j] = 0.f;
+                }
             }
+            __syncwarp();
             coop_stage_chunk(thr, v, one, zero, tile_row, chunk, chunk_mask, lane);
         }
         __syncwarp();

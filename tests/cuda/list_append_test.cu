@@ -30,11 +30,14 @@ __global__ void list_test_kernel(const float *keys /*[chunks][128][32]*/, int ch
         list.keys = list_keys + t;
         list.ids = list_ids + t;
     }
-    float one[32], zero[32];
+    __shared__ __align__(16) float one[32], zero[32];   // side arrays live in shared memory (ld.shared in side_fma32)
     for (int j = 0; j < 32; j++) {
-        one[j] = 1.f;
-        zero[j] = 0.f;
+        if (t == 0) {
+            one[j] = 1.f;
+            zero[j] = 0.f;
+        }
     }
+    __syncthreads();
     for (int c = 0; c < chunks; c++) {
         float v[32];
         for (int j = 0; j < 32; j++) v[j] = keys[((size_t)c * EPI_THREADS + t) * 32 + j];

@@ -34,8 +34,9 @@ __global__ void __launch_bounds__(128) perf_kernel(int chunks, int k, int cap, i
     if (pad == 1) {   // the one-lane rescan form whatever k
         list.coop = 0; list.stride = EPI_THREADS; list.keys = kb + t; list.ids = ib + t;
     }
-    float one[32], zero[32];
-    for (int j = 0; j < 32; j++) { one[j] = 1.f; zero[j] = 0.f; }
+    __shared__ __align__(16) float one[32], zero[32];
+    if (t < 32) { one[t] = 1.f; zero[t] = 0.f; }
+    __syncthreads();
     for (int c = 0; c < chunks; c++) {
         float v[32];
 #pragma unroll
