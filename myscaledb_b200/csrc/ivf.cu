@@ -1710,7 +1710,12 @@ static int search_device_locked(b200_index *ix, const float *d_queries, int64_t 
     uint32_t ppc;
     {
         const double want_items = 4.0 * ix->sms;
-        ppc = (uint32_t)std::min(16.0, std::max(8.0, std::ceil(est_pages / want_items)));
+        // Lists probed by more than 16 queries run on per-lane top-k lists, whose cold start is paid per item: longer items pay
+        // (cfg-4 shape, ~78 queries per list: 21.5 / 18.6 / 18.5 / 16.5 ms at 8 / 16 / 32 / 48 pages per item, profiles/r02_gpu32.log);
+        // cooperative items (<= 16 queries) keep the 16-page cap (sweep at 100 M x 768 above).
+        const double q_per_list = (double)n_pairs / std::max(1.0, est_lists);
+        const double cap = q_per_list > 16.0 ? 48.0 : 16.0;
+        ppc = (uint32_t)std::min(cap, std::max(8.0, std::ceil(est_pages / want_items)));
         if (est_lists * 2 < want_items) ppc = (uint32_t)std::max(2.0, std::min<double>(ppc, std::ceil(1.5 * avg_pages * est_lists / want_items)));   // a handful of queries
         ppc = std::max<uint32_t>(ppc, (ix->max_list_pages + 63) / 64);   // at most 64 chunks per list
         ppc = std::max<uint32_t>(ppc, 1);

@@ -328,18 +328,36 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 for (int kb = 0; kb < kb_count; kb++) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char *bt = sB + stage * C::B_BYTES;
-#pragma unroll 1
+                    // the code bytes of BOTH row passes are requested before either is decoded (ncu on the SQ8 scan: the
+                    // decoder warps sat on long-scoreboard stalls, one exposed memory latency per (k-block, row pass))
+                    uint4 raw[2][4];
+                    {
+                        constexpr int LD_BYTES = PRODUCER == IVF_PRODUCER_SQ8 ? BK : BK / (DSUB > 0 ? DSUB : 1);   // code bytes per row and k-block
+                        const int boff = kb * LD_BYTES;
+#pragma unroll
+                        for (int rr = 0; rr < 2; rr++) {
+                            const uint8_t *cr = codes + (size_t)(dw * 64 + rr * 32 + lane) * p.code_bytes + boff;
+                            if (LD_BYTES >= 16) {
+#pragma unroll
+                                for (int t = 0; t < LD_BYTES / 16; t++)
+                                    raw[rr][t] = (boff + t * 16 < p.code_bytes) ? *reinterpret_cast<const uint4 *>(cr + t * 16)
+                                                                                : (PRODUCER == IVF_PRODUCER_SQ8 ? make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u)
+                                                                                                                : make_uint4(0, 0, 0, 0));
+                            } else {
+                                const uint2 v = (boff < p.code_bytes) ? *reinterpret_cast<const uint2 *>(cr) : make_uint2(0, 0);
+                                raw[rr][0] = make_uint4(v.x, v.y, 0, 0);
+                            }
+                        }
+                    }
+#pragma unroll
                     for (int rr = 0; rr < 2; rr++) {
                         const int r = dw * 64 + rr * 32 + lane;
                         unsigned char *rowp = bt + (r >> 3) * 1024 + (r & 7) * 128;
-                        const uint8_t *code_r = codes + (size_t)r * p.code_bytes;
                         if (PRODUCER == IVF_PRODUCER_SQ8) {
                             // 64 int8 codes of this k-block -> 64 bf16 (exact: |code| <= 127); query side carries the scales
-                            const uint4 *src = reinterpret_cast<const uint4 *>(code_r + kb * BK);
 #pragma unroll
                             for (int c4 = 0; c4 < 4; c4++) {
-                                const bool in = kb * BK + c4 * 16 < p.code_bytes;
-                                const uint4 w = in ? src[c4] : make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+                                const uint4 w = raw[rr][c4];
                                 const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
                                 uint32_t o[8];
 #pragma unroll
@@ -370,13 +388,11 @@ ivf_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                             if (NSUB >= 16) {
 #pragma unroll
                                 for (int t = 0; t < NSUB / 16; t++) {
-                                    const uint4 v = (j0 + t * 16 < p.code_bytes) ? *reinterpret_cast<const uint4 *>(code_r + j0 + t * 16)
-                                                                                 : make_uint4(0, 0, 0, 0);
+                                    const uint4 v = raw[rr][t];
                                     cw[t * 4] = v.x; cw[t * 4 + 1] = v.y; cw[t * 4 + 2] = v.z; cw[t * 4 + 3] = v.w;
                                 }
                             } else {
-                                const uint2 v = (j0 < p.code_bytes) ? *reinterpret_cast<const uint2 *>(code_r + j0) : make_uint2(0, 0);
-                                cw[0] = v.x; cw[1] = v.y;
+                                cw[0] = raw[rr][0].x; cw[1] = raw[rr][0].y;
                             }
                             constexpr int PER_CHUNK_F = 16 / BYTES_PER;
                             const int valid = min(NSUB, p.m - j0);          // sub-quantisers of this k-block that exist
