@@ -200,7 +200,10 @@ int b200_index_finalize(b200_index *ix);
 int b200_index_info(const b200_index *ix, int64_t *n, int *nlist, int *m, int *uses_ivf);
 /* first_stage_only (two-stage types): return the first-stage candidates with first-stage distances;
  * out_num_candidates receives the width the first stage ran with (SearchResult::getNumCandidates).
- * "exact_batch=1" in `params` answers by an exact pass over the fp32 rows instead (recall 1). */
+ * "exact_batch=1" in `params` answers by an exact pass over the fp32 rows instead (recall 1).
+ * Tuning / A-B switches, also in `params` (defaults are chosen from the batch shape): "pages_per_chunk=N" (pages of a list one work
+ * item streams), "shared_bound=0" (do not share a per-query bound between the work items of a launch), "coarse_path=1|2|3" (centroid
+ * probe by the scan kernel / the tensor-core top-k / score tiles + warp select; default 3 for nprobe > 8). */
 int b200_index_search(b200_index *ix, const float *queries, int64_t nq, int k, const char *params, int first_stage_only,
                       const uint8_t *alive_bits /*nullable*/, float *out_dis, int64_t *out_ids, int64_t *out_num_candidates);
 /* same with device buffers, asynchronous on `stream` (NULL = the index's own stream, synchronised); id_offset is added to
