@@ -228,6 +228,8 @@ struct ThreadTopK {
     int cap;           // slots of the buffer: == k -> "rescan" mode, > k (>= k + 32) -> "append" mode, see below
     int stride;        // EPI_THREADS: lists interleaved (entry j of all 128 lists side by side); 1: each list contiguous
     int coop;          // warp-uniform: inserts are done by the whole warp, one (lane, candidate) at a time (needs stride 1)
+    int append;        // cap >= 2k + 32: append form
+    int tourn;         // cap == list_cap_tourn(k): slots [k, cap) hold the worst (key, id) of every group of 8 / 16 entries; `worst` = a group
     float thr_key;     // key of the current worst kept element (FLT_MAX while n < k)
     uint32_t thr_id;
 };
@@ -244,9 +246,19 @@ struct ThreadTopK {
 #define B200_LIST_COOP_MIN_K (1 << 30)
 #endif
 constexpr int kListCoopMinK = B200_LIST_COOP_MIN_K;
+// Element j of a list sits at keys[j * LIST_STRIDE(t)].  Production builds have no contiguous (cooperative) lists, so the stride is
+// the compile-time constant EPI_THREADS and the rescans address their entries with immediate offsets; a run-time stride cost the
+// default form 16 % at k = 30 and 36 % at k = 100 (profiles/r02_gpu35.log vs r02_gpu22.log).
+#if B200_LIST_COOP_MIN_K >= (1 << 30)
+#define LIST_STRIDE(t) EPI_THREADS
+#else
+#define LIST_STRIDE(t) ((t).stride)
+#endif
 __device__ __forceinline__ void list_bind(ThreadTopK &t, float *keys_base, uint32_t *ids_base, int row, int k, int cap) {
     t.k = k;
     t.cap = cap;
+    t.append = cap >= 2 * k + 32 ? 1 : 0;
+    t.tourn = (!t.append && cap > k && cap == list_cap_tourn(k)) ? 1 : 0;
     t.coop = (cap == k && k >= kListCoopMinK) ? 1 : 0;
     t.stride = t.coop ? 1 : EPI_THREADS;
     t.keys = keys_base + (t.coop ? (size_t)row * cap : (size_t)row);
@@ -345,7 +357,7 @@ static __device__ __noinline__ ListThr list_compact(float *keys, uint32_t *ids, 
 
 __device__ __forceinline__ void list_compact_if_over(ThreadTopK &t) {
     if (t.n > t.k) {
-        const ListThr r = list_compact(t.keys, t.ids, t.k, t.n, t.stride);
+        const ListThr r = list_compact(t.keys, t.ids, t.k, t.n, LIST_STRIDE(t));
         t.n = t.k;
         t.thr_key = r.key;
         t.thr_id = r.id;
@@ -354,29 +366,100 @@ __device__ __forceinline__ void list_compact_if_over(ThreadTopK &t) {
 
 __device__ __forceinline__ void list_insert(ThreadTopK &t, float key, uint32_t id) {
     if (!better(key, id, t.thr_key, t.thr_id)) return;
-    if (t.cap > t.k) {   // append mode: the caller keeps n + 32 <= cap before every chunk (epilogue_chunk)
+    if (t.append) {   // append mode: the caller keeps n + 32 <= cap before every chunk (epilogue_chunk)
         B200_LIST_STAT(3, 1);
-        t.keys[t.n * t.stride] = key;
-        t.ids[t.n * t.stride] = id;
+        t.keys[t.n * LIST_STRIDE(t)] = key;
+        t.ids[t.n * LIST_STRIDE(t)] = id;
         t.n++;
         return;
     }
+    if (t.tourn) {
+        // Two-level form: the worst entry of each group of G = 8 / 16 is cached behind the list, so an insert rescans ONE group (to
+        // find the slot of the entry it evicts and that group's new worst) and the group worsts: 2 (G + k / G) loads instead of 2 k.
+        const int G = list_tourn_group(t.k);
+        const int ng = (t.k + G - 1) / G;
+        float *gk = t.keys + (size_t)t.k * LIST_STRIDE(t);
+        uint32_t *gi = t.ids + (size_t)t.k * LIST_STRIDE(t);
+        if (t.n < t.k) {
+            t.keys[t.n * LIST_STRIDE(t)] = key;
+            t.ids[t.n * LIST_STRIDE(t)] = id;
+            t.n++;
+            if (t.n < t.k) return;
+            for (int g = 0; g < ng; g++) {   // the list just became full: every group's worst, once
+                const int base = g * G, end = base + G < t.k ? base + G : t.k;
+                float wk = t.keys[base * LIST_STRIDE(t)];
+                uint32_t wi = t.ids[base * LIST_STRIDE(t)];
+                for (int j = base + 1; j < end; j++) {
+                    const float kj = t.keys[j * LIST_STRIDE(t)];
+                    const uint32_t ij = t.ids[j * LIST_STRIDE(t)];
+                    if (better(wk, wi, kj, ij)) {
+                        wk = kj;
+                        wi = ij;
+                    }
+                }
+                gk[g * LIST_STRIDE(t)] = wk;
+                gi[g * LIST_STRIDE(t)] = wi;
+            }
+        } else {
+            const int g = t.worst;   // the group that holds the evicted entry (= the current threshold)
+            const int base = g * G, end = base + G < t.k ? base + G : t.k;
+            float wk = 0.f;
+            uint32_t wi = 0;
+            int slot = -1;
+            bool have = false;
+            for (int j = base; j < end; j++) {
+                float kj = t.keys[j * LIST_STRIDE(t)];
+                uint32_t ij = t.ids[j * LIST_STRIDE(t)];
+                if (slot < 0 && kj == t.thr_key && ij == t.thr_id) {
+                    slot = j;
+                    kj = key;
+                    ij = id;
+                }
+                if (!have || better(wk, wi, kj, ij)) {
+                    wk = kj;
+                    wi = ij;
+                    have = true;
+                }
+            }
+            if (slot < 0) slot = base;   // cannot happen (ids are unique and the threshold is an entry of this group); never write out of range
+            t.keys[slot * LIST_STRIDE(t)] = key;
+            t.ids[slot * LIST_STRIDE(t)] = id;
+            gk[g * LIST_STRIDE(t)] = wk;
+            gi[g * LIST_STRIDE(t)] = wi;
+        }
+        float wk = gk[0];
+        uint32_t wi = gi[0];
+        int wg = 0;
+        for (int g = 1; g < ng; g++) {
+            const float kg = gk[g * LIST_STRIDE(t)];
+            const uint32_t ig = gi[g * LIST_STRIDE(t)];
+            if (better(wk, wi, kg, ig)) {
+                wk = kg;
+                wi = ig;
+                wg = g;
+            }
+        }
+        t.worst = wg;
+        t.thr_key = wk;
+        t.thr_id = wi;
+        return;
+    }
     if (t.n < t.k) {
-        t.keys[t.n * t.stride] = key;
-        t.ids[t.n * t.stride] = id;
+        t.keys[t.n * LIST_STRIDE(t)] = key;
+        t.ids[t.n * LIST_STRIDE(t)] = id;
         t.n++;
         if (t.n < t.k) return;
     } else {
-        t.keys[t.worst * t.stride] = key;
-        t.ids[t.worst * t.stride] = id;
+        t.keys[t.worst * LIST_STRIDE(t)] = key;
+        t.ids[t.worst * LIST_STRIDE(t)] = id;
     }
     // rescan for the worst (largest key, ties -> larger id)
     float wk = t.keys[0];
     uint32_t wi = t.ids[0];
     int wp = 0;
     for (int j = 1; j < t.k; j++) {
-        const float kj = t.keys[j * t.stride];
-        const uint32_t ij = t.ids[j * t.stride];
+        const float kj = t.keys[j * LIST_STRIDE(t)];
+        const uint32_t ij = t.ids[j * LIST_STRIDE(t)];
         if (better(wk, wi, kj, ij)) {
             wk = kj;
             wi = ij;
@@ -392,20 +475,20 @@ __device__ __forceinline__ void list_insert(ThreadTopK &t, float key, uint32_t i
 static __device__ __noinline__ void list_publish(ThreadTopK &t, float *out_keys, uint32_t *out_ids) {
     list_compact_if_over(t);
     for (int i = 1; i < t.n; i++) {
-        const float ki = t.keys[i * t.stride];
-        const uint32_t ii = t.ids[i * t.stride];
+        const float ki = t.keys[i * LIST_STRIDE(t)];
+        const uint32_t ii = t.ids[i * LIST_STRIDE(t)];
         int j = i;
-        while (j > 0 && better(ki, ii, t.keys[(j - 1) * t.stride], t.ids[(j - 1) * t.stride])) {
-            t.keys[j * t.stride] = t.keys[(j - 1) * t.stride];
-            t.ids[j * t.stride] = t.ids[(j - 1) * t.stride];
+        while (j > 0 && better(ki, ii, t.keys[(j - 1) * LIST_STRIDE(t)], t.ids[(j - 1) * LIST_STRIDE(t)])) {
+            t.keys[j * LIST_STRIDE(t)] = t.keys[(j - 1) * LIST_STRIDE(t)];
+            t.ids[j * LIST_STRIDE(t)] = t.ids[(j - 1) * LIST_STRIDE(t)];
             j--;
         }
-        t.keys[j * t.stride] = ki;
-        t.ids[j * t.stride] = ii;
+        t.keys[j * LIST_STRIDE(t)] = ki;
+        t.ids[j * LIST_STRIDE(t)] = ii;
     }
     for (int j = 0; j < t.k; j++) {
-        out_keys[j] = j < t.n ? t.keys[j * t.stride] : FLT_MAX;
-        out_ids[j] = j < t.n ? t.ids[j * t.stride] : kNoId;
+        out_keys[j] = j < t.n ? t.keys[j * LIST_STRIDE(t)] : FLT_MAX;
+        out_ids[j] = j < t.n ? t.ids[j * LIST_STRIDE(t)] : kNoId;
     }
 }
 
@@ -528,7 +611,7 @@ __device__ __forceinline__ void epilogue_chunk(ThreadTopK &list, float (&v)[32],
     }
     if (__any_sync(0xffffffffu, mine)) {
         if ((threadIdx.x & 31) == 0) B200_LIST_STAT(0, 1);
-        if (list.cap > list.k && __any_sync(0xffffffffu, list.n + 32 > list.cap)) {
+        if (list.append && __any_sync(0xffffffffu, list.n + 32 > list.cap)) {
             if ((threadIdx.x & 31) == 0) B200_LIST_STAT(1, 1);
             list_compact_if_over(list);   // every lane, in lock-step: room for this chunk and a fresh threshold
             thr = fminf(list.thr_key, ext_bound);

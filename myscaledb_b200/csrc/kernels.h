@@ -108,6 +108,10 @@ constexpr int kGemmSmemK = 128;
 // of 2k + 32 slots compacted in lock-step (B200_LIST_APPEND_MIN_K=<k>: lists of at least that k use it; measured in
 // profiles/r02_list_modes.md -- it only pays when the doubled buffer still fits in shared memory, which it does not at k = 100)
 __host__ __device__ inline int list_cap_append(int k) { return 2 * k + 32; }
+// tournament form: k entries + one (key, id) slot per group of 8 (k <= 64) or 16 entries holding the group's worst
+// (B200_LIST_TOURN_MIN_K); 16 keeps k = 100 at 107 slots, which still leaves the flat kernel a 3-stage operand ring
+__host__ __device__ inline int list_tourn_group(int k) { return k <= 64 ? 8 : 16; }
+__host__ __device__ inline int list_cap_tourn(int k) { return k + (k + list_tourn_group(k) - 1) / list_tourn_group(k); }
 int list_cap_for(int k);   // capi.cu: k, or list_cap_append(k) when the environment asks for the append form
 int gemm_topk_grid(int q_tiles, int64_t n, int num_sms);
 // returns cudaSuccess or an error; tensor maps are encoded inside

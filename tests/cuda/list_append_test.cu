@@ -51,8 +51,8 @@ int main() {
     std::mt19937 rng(1234);
     int cases = 0, bad = 0;
     for (int k : {1, 10, 16, 17, 30, 64, 100, 256}) {
-        for (int mode = 0; mode < 3; mode++) {   // 0: default form for this k (cooperative from k = 17), 1: append, 2: one-lane rescan
-            const int cap = mode == 1 ? list_cap_append(k) : k;
+        for (int mode = 0; mode < 4; mode++) {   // 0: default form for this k (cooperative from k = 17), 1: append, 2: one-lane rescan, 3: tournament
+            const int cap = mode == 1 ? list_cap_append(k) : mode == 3 ? list_cap_tourn(k) : k;
             for (int dist = 0; dist < 4; dist++) {
                 const int chunks = dist == 3 ? 3 : 200;
                 std::vector<float> h((size_t)chunks * EPI_THREADS * 32);

@@ -52,9 +52,9 @@ int main(int argc, char **argv) {
     const int grid = 148;
     const int big_smem = argc > 2 ? atoi(argv[2]) : 1;
     for (int k : {10, 30, 64, 100}) {
-        for (int mode = -1; mode < 3; mode++) {          // -1 one-lane rescan, 0 default (cooperative from k = 17), 1 append (2k / k+32), 2 append with 4k slots
+        for (int mode = -1; mode < 4; mode++) {          // 3: tournament (group worsts)          // -1 one-lane rescan, 0 default (cooperative from k = 17), 1 append (2k / k+32), 2 append with 4k slots
             for (int in_smem = 1; in_smem >= 0; in_smem--) {
-                const int cap = mode <= 0 ? k : mode == 1 ? (2 * k > k + 32 ? 2 * k : k + 32) : 4 * k > k + 64 ? 4 * k : k + 64;
+                const int cap = mode <= 0 ? k : mode == 3 ? list_cap_tourn(k) : mode == 1 ? (2 * k > k + 32 ? 2 * k : k + 32) : 4 * k > k + 64 ? 4 * k : k + 64;
                 size_t smem = SCRATCH_BYTES + (in_smem ? (size_t)cap * EPI_THREADS * 8 : 0);
                 if (smem > 220 * 1024) continue;
                 if (big_smem) smem = 220 * 1024;   // like the tensor-core kernels: the operand ring leaves ~28 KB of L1
@@ -79,7 +79,7 @@ int main(int argc, char **argv) {
 #endif
                 const double warps = grid * 4.0;
                 printf("k %3d cap %3d %-6s %-6s  %8.3f ms   per warp: slow-path events %8.0f  compactions %7.1f  select rounds/compaction %5.1f  appends/lane %7.1f\n", k, cap,
-                       mode == -1 ? "1-lane" : mode == 0 ? "deflt" : "append", in_smem ? "smem" : "global", ms, st[0] / warps, st[1] / warps,
+                       mode == -1 ? "1-lane" : mode == 0 ? "deflt" : mode == 3 ? "tourn" : "append", in_smem ? "smem" : "global", ms, st[0] / warps, st[1] / warps,
                        st[1] ? (double)st[2] / 32.0 / st[1] : 0.0, st[3] / (warps * 32));
                 cudaFree(g_keys); cudaFree(g_ids); cudaFree(ok); cudaFree(oi);
             }
